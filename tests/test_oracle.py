@@ -1,0 +1,122 @@
+"""The oracle is pinned before it is trusted (CPU-only tests).
+
+Golden vectors come from the REFERENCE's own architecture file run in the build container
+(tools/gen_golden.py); the OpenCV convertTo KAT comes from cv2 (same cvt_32f arithmetic the hook
+calls at EncCu.cpp:835-838)."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ref_arch
+from tests.oracle_lib import OracleModel
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+REF_ARCH = "/root/reference/mlt-cnn-python/codes/models/archs/mlt_ctu_or_pq_arch.py"
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(GOLD, "logits_seed10.npz"))
+
+
+@pytest.fixture(scope="module")
+def sd():
+    return ref_arch.make_state_dict(10)
+
+
+@pytest.fixture(scope="module")
+def model(sd):
+    m = OracleModel(sd)
+    yield m
+    m.close()
+
+
+def test_seeded_inputs_and_params_are_the_golden_ones(gold, sd):
+    orgpred, pocqp = ref_arch.synth_ctus(int(gold["n"]), int(gold["seed"]))
+    assert hashlib.sha256(orgpred.tobytes()).digest() == gold["orgpred_sha256"].tobytes()
+    assert np.array_equal(pocqp, gold["pocqp"])
+    h = hashlib.sha256(b"".join(np.ascontiguousarray(sd[k]).tobytes() for k in sorted(sd))).digest()
+    assert h == gold["params_sha256"].tobytes()
+
+
+def test_stage_matches_opencv_kat():
+    """C oracle staging == cv2 convertTo on every 10-bit code, bit for bit."""
+    kat = np.load(os.path.join(GOLD, "stage_kat.npz"))
+    codes = kat["codes"].astype(np.int16)
+    org = np.resize(codes, (128, 128)).astype(np.int16)  # all 1024 codes, 16 times
+    pred = np.zeros((128, 128), np.int16)
+    m = OracleModel(ref_arch.make_state_dict(10))
+    x = m.stage(org, pred)
+    want = kat["cv2_convert_to"][org.astype(np.int64)]
+    assert np.array_equal(x[0].view(np.uint32), want.view(np.uint32))
+    assert np.array_equal(x[1].view(np.uint32), want.view(np.uint32))  # |org-0| == org
+    assert np.float32(1.0 / 1023).view(np.uint32) == 0x3A802008
+
+
+def test_stage_bit_exact_vs_numpy_and_golden_hash(gold, model):
+    orgpred, _ = ref_arch.synth_ctus(int(gold["n"]), int(gold["seed"]))
+    want = ref_arch.stage_numpy(orgpred)
+    assert hashlib.sha256(want.tobytes()).digest() == gold["staged_sha256"].tobytes()
+    for i in range(len(orgpred)):
+        got = model.stage(orgpred[i, 0], orgpred[i, 1])
+        assert np.array_equal(got.view(np.uint32), want[i].view(np.uint32))
+
+
+def test_stage_edge_cases(model):
+    """Strided buffers, org<pred, negative Pel (cast to uint16 > 1023 -> clamp to 1), extremes."""
+    rng = np.random.RandomState(3)
+    big = rng.randint(-300, 1400, (140, 200)).astype(np.int16)  # includes negatives and >1023
+    org = big[5:133, 17:145]
+    pred = np.ascontiguousarray(rng.randint(0, 1024, (128, 128)).astype(np.int16))
+    x = model.stage(org, pred)
+    o = org.astype(np.uint16).astype(np.int64)
+    p = pred.astype(np.uint16).astype(np.int64)
+    a = np.float32(1.0 / 1023)
+    assert np.array_equal(x[0], np.clip(o.astype(np.float32) * a, 0, 1).astype(np.float32))
+    assert np.array_equal(x[1], np.clip(np.abs(o - p).astype(np.float32) * a, 0, 1).astype(np.float32))
+    assert x.min() >= 0.0 and x.max() <= 1.0
+    z = np.zeros((128, 128), np.int16)
+    f = np.full((128, 128), 1023, np.int16)
+    assert np.all(model.stage(z, z) == 0)
+    x = model.stage(f, z)
+    assert np.all(x == 1.0)
+    x = model.stage(z, f)
+    assert np.all(x[0] == 0) and np.all(x[1] == 1.0)
+
+
+def test_c_oracle_matches_reference_golden_logits(gold, model):
+    """C restatement vs the reference arch's logits (fp32 reassociation only)."""
+    orgpred, pocqp = ref_arch.synth_ctus(int(gold["n"]), int(gold["seed"]))
+    lg, sp = model.predict_batch(orgpred, pocqp)
+    err = np.abs(lg - gold["logits"]).max()
+    assert err < 2e-4, err
+    assert np.array_equal(sp, gold["split"])
+    assert set(gold["split"].tolist()) == {0, 1, 2, 3}  # every setNewModeList branch is reachable
+    assert np.abs(gold["logits_traced"] - gold["logits"]).max() == 0.0
+
+
+def test_torch_restatement_matches_golden(gold, sd):
+    orgpred, pocqp = ref_arch.synth_ctus(8, int(gold["seed"]))
+    net = ref_arch.build_model(sd)
+    lg = ref_arch.forward_logits(net, ref_arch.stage_numpy(orgpred), pocqp, batch=1)
+    assert np.abs(lg - gold["logits"][:8]).max() < 1e-5
+
+
+@pytest.mark.skipif(not os.path.exists(REF_ARCH), reason="reference mount absent (GPU box)")
+def test_torch_restatement_equals_reference_arch_file(sd):
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("ref_arch_file", REF_ARCH)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    ref = mod.GapBigMltCtuORPQ()
+    ref.load_state_dict(ref_arch.to_torch_state_dict(sd), strict=True)
+    ref.eval()
+    orgpred, pocqp = ref_arch.synth_ctus(3, 77)
+    x = ref_arch.stage_numpy(orgpred)
+    a = ref_arch.forward_logits(ref, x, pocqp, batch=1)
+    b = ref_arch.forward_logits(ref_arch.build_model(sd), x, pocqp, batch=1)
+    assert np.array_equal(a, b)
+    assert sum(p.numel() for p in ref.parameters()) == 2797403
