@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py -- MLT-CNN split inference throughput (CTUs/s) on 1..8 B200, beside the CPU libtorch baseline.
+
+Metric / config: BASELINE.json -- "MLT-CNN split CTUs/s", batched split inference on all eligible CTUs of
+synthetic 1920x1080 frames (CTU 128 -> 120 CTUs per frame).  One STEP = one pass
+of the hot path (staging + conv stack + head) over `--frames` independent 1080p frames (default 32 frames =
+3840 CTUs = 240 MiB of int16 input, larger than the 126 MB L2, so no L2 flush is needed between steps).
+
+  value     : CTUs/s with the int16 inputs already resident in HBM (device-resident C-ABI entry point,
+              CUDA events on the stream the kernels run on, max over ranks).
+  e2e       : the same through the host-buffer C-ABI call (mlt_predict_batch_dense): pinned host int16 in,
+              H2D + kernels + D2H of the mlt_result array inside the timed region.
+  roofline  : tensor roofline of the dominant kernel family (conv_umma_kernel, 16 launches per step):
+              algorithmic FLOPs (1,115,684,864 per CTU for the 16 3x3 convs + 4 fused shortcuts) / device time
+              measured live with CUDA events around each launch; peak = MEASURED_PEAKS.json bf16 sustained.
+  cpu_baseline : oracle/ref_arch.py (torch CPU fp32 = the libtorch backend the reference hook calls) timed on a
+              bounded sample on this box's host cores.
+
+Multi-GPU (torchrun, one process per GPU): frames are sharded over ranks, no data-path collective
+(weak scaling: `--frames` is per GPU).  `--impl reference` times the reference's CPU path (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CTUS_PER_FRAME = 120  # 1920x1080, CTU 128: 15 x 8 full CTUs (EncCu.cpp:755 excludes the partial bottom row)
+FLOP_PER_CTU = 1_134_562_340  # SURVEY.md section 8a (2*MAC, all 21 convs + 3 FC)
+FLOP_CONV1 = 18_874_368
+FLOP_FC = 3_108
+FLOP_UMMA_PER_CTU = FLOP_PER_CTU - FLOP_CONV1 - FLOP_FC  # the 16 tcgen05 conv launches
+METRIC = "mlt_cnn_split_ctus_per_s"
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["bf16_tflops_sustained"]), float(p["bf16_tflops"]), float(p["hbm_gbs"]), "measured"
+    except Exception:
+        return 1400.0, 1590.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synth_frames(n_ctus: int, seed: int):
+    """Cheap synthetic int16 CTUs with the distribution of oracle.ref_arch.synth_ctus (64 distinct CTUs tiled
+    with per-copy noise so every CTU differs); generated without importing oracle/ (bench product arm)."""
+    rng = np.random.RandomState(seed)
+    yy, xx = np.mgrid[0:128, 0:128].astype(np.float32)
+    base = np.empty((64, 2, 128, 128), np.float32)
+    for i in range(64):
+        f, ph = rng.uniform(0.005, 0.35, 3), rng.uniform(0, 6.28, 3)
+        img = rng.uniform(64, 960) + rng.uniform(0, 300) * np.sin(f[0] * xx + ph[0]) * np.cos(f[1] * yy + ph[1])
+        img += rng.standard_normal((128, 128)) * rng.uniform(0, 60)
+        base[i, 0] = img
+        base[i, 1] = np.roll(img, (1, 1), (0, 1)) + rng.standard_normal((128, 128)) * rng.uniform(0, 30)
+    out = np.empty((n_ctus, 2, 128, 128), np.int16)
+    for s in range(0, n_ctus, 64):
+        k = min(64, n_ctus - s)
+        noise = rng.randint(-3, 4, (k, 2, 128, 128)).astype(np.float32)
+        out[s : s + k] = np.clip(np.rint(base[:k] + noise), 0, 1023).astype(np.int16)
+    pocqp = np.stack([rng.randint(1, 32, n_ctus), rng.randint(22, 46, n_ctus)], 1).astype(np.int32)
+    return out, pocqp
+
+
+# ----------------------------------------------------------------------------------------------- CPU baseline
+
+
+def cpu_reference_rate(budget_s: float, threads: int | None = None):
+    """Reference CPU path: traced TorchScript of the architecture on torch CPU fp32 (libtorch), one CTU per
+    forward like the hook (EncCu.cpp:869-921, model loaded once).  Bounded by `budget_s` seconds."""
+    import torch
+
+    from oracle import ref_arch
+
+    if threads:
+        torch.set_num_threads(threads)
+    sd = ref_arch.make_state_dict(10)
+    net = ref_arch.build_model(sd)
+    ex = (torch.rand(1, 2, 128, 128), torch.rand(1), torch.rand(1))
+    traced = torch.jit.trace(net, ex)  # as model2torchScript.py:37-48
+    orgpred, pocqp = ref_arch.synth_ctus(16, 10)
+    x = torch.from_numpy(ref_arch.stage_numpy(orgpred))
+    with torch.no_grad():
+        for i in range(3):
+            traced(x[i : i + 1], torch.tensor([int(pocqp[i, 0])]), torch.tensor([int(pocqp[i, 1])]))
+        n, t0 = 0, time.perf_counter()
+        while True:
+            i = n % 16
+            traced(x[i : i + 1], torch.tensor([int(pocqp[i, 0])]), torch.tensor([int(pocqp[i, 1])]))
+            n += 1
+            dt = time.perf_counter() - t0
+            if (dt >= budget_s and n >= 16) or n >= 100000:
+                break
+    return n / dt, torch.get_num_threads(), n, dt
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    steps, warm = max(args.steps, 1), args.warmup
+    per_step_budget = min(8.0, 120.0 / (steps + warm))
+    rates, cores, n_tot = [], 0, 0
+    for i in range(warm + steps):
+        r, cores, n, dt = cpu_reference_rate(per_step_budget)
+        if i >= warm:
+            rates.append((n, dt))
+            n_tot += n
+    tot_n = sum(n for n, _ in rates)
+    tot_t = sum(t for _, t in rates)
+    v = tot_n / tot_t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "CTU/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": 1e3 * tot_t / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "1080p frames (120 CTUs/frame), CPU path: one CTU per forward as EncCu.cpp:869-921, model loaded once"},
+        "cpu_baseline": {"value": v, "unit": "CTU/s", "cores": cores, "kind": "port",
+                         "sample": f"{tot_n} CTUs at B=1 through traced TorchScript (torch CPU fp32 = libtorch) in {tot_t:.1f}s"},
+        "e2e": {"value": v, "unit": "CTU/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------- product arm
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--frames", type=int, default=32, help="independent 1080p frames per step per GPU (120 CTUs each)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU baseline work (rank 0, N=1)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+
+    import fastintercu_vvc_b200 as pkg
+    from fastintercu_vvc_b200.capi import RESULT_DTYPE
+    from fastintercu_vvc_b200.pack_weights import write_blob
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    steps, warm = args.steps, max(args.warmup, 3)
+    n = args.frames * CTUS_PER_FRAME
+
+    # seeded random weights of the exact architecture (the trained .pt is not distributed with the reference)
+    from fastintercu_vvc_b200.synth import make_state_dict
+
+    blob = tempfile.NamedTemporaryFile(suffix=".mltw", delete=False).name
+    write_blob(make_state_dict(10), blob)
+    pred = pkg.MltPredictor(blob, device=local, max_batch=n)
+    os.unlink(blob)
+
+    orgpred, pocqp = synth_frames(n, 1000 + rank)
+    h_in = torch.from_numpy(orgpred).pin_memory()
+    h_pq = torch.from_numpy(pocqp).pin_memory()
+    d_in = h_in.cuda(non_blocking=True)
+    d_pq = h_pq.cuda(non_blocking=True)
+    d_out = torch.zeros(n * RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+    h_out = np.zeros(n, RESULT_DTYPE)
+    stream = torch.cuda.current_stream()
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def device_step():
+        pred.predict_batch_device(n, d_in.data_ptr(), d_pq.data_ptr(), d_out.data_ptr(), stream.cuda_stream)
+
+    # ---- device-resident throughput (value)
+    for _ in range(warm):
+        device_step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = pred.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        device_step()
+    e1.record(stream)
+    barrier()
+    launches = pred.launch_count - l0
+    dev_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+
+    # ---- per-kernel device times (roofline), measured live with CUDA events around each launch
+    pred.set_profiling(True)
+    prof = np.zeros(18, np.float64)
+    for _ in range(max(3, min(steps, 10))):
+        device_step()
+        torch.cuda.synchronize()
+        prof += pred.get_profile()
+    prof /= max(3, min(steps, 10))
+    pred.set_profiling(False)
+
+    # ---- end to end through the host-buffer C-ABI call (pinned host in, H2D + compute + D2H out)
+    orgpred_pinned = h_in.numpy()
+    pocqp_pinned = h_pq.numpy()
+    for _ in range(2):
+        pred.predict_batch_dense(orgpred_pinned, pocqp_pinned, h_out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        pred.predict_batch_dense(orgpred_pinned, pocqp_pinned, h_out)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+
+    # ---- single-frame latency (the 120 CTUs of one 1080p frame), host buffers, for the record
+    f_in, f_pq, f_out = orgpred_pinned[:CTUS_PER_FRAME], pocqp_pinned[:CTUS_PER_FRAME], h_out[:CTUS_PER_FRAME]
+    for _ in range(3):
+        pred.predict_batch_dense(f_in, f_pq, f_out)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        pred.predict_batch_dense(f_in, f_pq, f_out)
+    frame_ms = (time.perf_counter() - t0) / 20 * 1e3
+
+    if world > 1:
+        t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_s = float(t[0]), float(t[1])
+    total_ctus = n * world * steps
+    value = total_ctus / (dev_ms * 1e-3)
+    e2e = total_ctus / e2e_s
+
+    if rank == 0:
+        sustained, burst, hbm, how = load_peaks()
+        umma_ms = float(prof[1:17].sum())
+        ach = n * FLOP_UMMA_PER_CTU / (umma_ms * 1e-3) / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": "CTU/s", "n_gpus": world, "steps": steps, "warmup": warm,
+            "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
+            "data": "synthetic",
+            "config": {"workload": f"{args.frames} independent synthetic 1920x1080 frames per step per GPU, 120 CTUs of 128x128 each "
+                                   f"({n} CTUs/step/GPU), MLT-CNN GapBigMltCtuORPQ, seeded random weights",
+                       "frames_per_step": args.frames, "ctus_per_step_per_gpu": n,
+                       "l2": f"inputs {n * 65536 / 2**20:.0f} MiB + activations > 126 MB L2, no flush needed",
+                       "parallelism": f"replicas x{world} (frames sharded, no collectives)"},
+            "e2e": {"value": e2e, "unit": "CTU/s", "h2d_bytes_per_step": int(n * (65536 + 8)), "d2h_bytes_per_step": int(n * RESULT_DTYPE.itemsize)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "achieved": ach, "peak": sustained, "unit": "TFLOP/s", "frac": ach / sustained,
+                         "traffic": None, "kernel": "conv_umma_kernel (16 launches/step)", "peak_source": f"{how} bf16 sustained",
+                         "kernel_ms_per_step": umma_ms, "stage_conv1_ms": float(prof[0]), "head_ms": float(prof[17]),
+                         "per_layer_ms": [round(float(x), 4) for x in prof[1:17]]},
+            "frame_latency_ms": frame_ms,
+            "tflops_whole_net": value / world * FLOP_PER_CTU / 1e12,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            r, cores, cn, cdt = cpu_reference_rate(args.cpu_budget)
+            line["cpu_baseline"] = {"value": r, "unit": "CTU/s", "cores": cores, "kind": "port",
+                                    "sample": f"{cn} CTUs at B=1 through traced TorchScript (torch CPU fp32 = libtorch) in {cdt:.1f}s"}
+        print(json.dumps(line))
+    pred.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,229 @@
+"""ctypes binding of libmltcnn.so (include/mltcnn.h) -- plumbing only, no compute and no fallback.
+
+Mirrors the reference hook's call shape (EncCu.cpp:806-921): `predict_ctu(org, pred, poc, qp)` returns the
+level-3 argmax the encoder hands to `setNewModeList`, plus logits / probabilities / per-level flags.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CTU = 128
+
+
+class MltResult(C.Structure):
+    _fields_ = [
+        ("split_l3", C.c_int32),
+        ("split_l2", C.c_int32),
+        ("split_l1", C.c_int32),
+        ("flags", C.c_uint32),
+        ("logits", C.c_float * 9),
+        ("probs", C.c_float * 9),
+    ]
+
+
+RESULT_DTYPE = np.dtype(
+    [("split_l3", "<i4"), ("split_l2", "<i4"), ("split_l1", "<i4"), ("flags", "<u4"), ("logits", "<f4", 9), ("probs", "<f4", 9)]
+)
+assert RESULT_DTYPE.itemsize == C.sizeof(MltResult) == 88
+
+
+class CtuDesc(C.Structure):
+    _fields_ = [
+        ("org", C.c_void_p),
+        ("pred", C.c_void_p),
+        ("org_stride", C.c_int32),
+        ("pred_stride", C.c_int32),
+        ("poc", C.c_int32),
+        ("qp", C.c_int32),
+    ]
+
+
+class MltError(RuntimeError):
+    def __init__(self, rc: int, what: str, detail: str = ""):
+        super().__init__(f"{what} failed: rc={rc} ({detail})")
+        self.rc = rc
+
+
+EXPORTS = {
+    "mlt_abi_version": (C.c_int, []),
+    "mlt_strerror": (C.c_char_p, [C.c_int]),
+    "mlt_last_error": (C.c_char_p, [C.c_void_p]),
+    "mlt_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_char_p, C.c_int]),
+    "mlt_create_ex": (C.c_int, [C.POINTER(C.c_void_p), C.c_char_p, C.c_int, C.c_int]),
+    "mlt_destroy": (None, [C.c_void_p]),
+    "mlt_predict_ctu": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "mlt_predict_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "mlt_predict_batch_dense": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mlt_predict_batch_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mlt_begin_picture": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "mlt_predict_ctu_in_picture": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "mlt_set_engine": (C.c_int, [C.c_void_p, C.c_int]),
+    "mlt_launch_count": (C.c_uint64, [C.c_void_p]),
+    "mlt_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
+    "mlt_get_profile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "mlt_debug_stage": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "mlt_debug_activation": (C.c_int64, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]),
+}
+
+_LIB = None
+
+
+def lib_path() -> str:
+    return os.environ.get("MLT_LIBRARY", os.path.join(HERE, "libmltcnn.so"))
+
+
+def load_library():
+    """dlopen libmltcnn.so and bind every symbol of include/mltcnn.h.  Raises if the library is missing."""
+    global _LIB
+    if _LIB is None:
+        path = lib_path()
+        if not os.path.exists(path):
+            raise FileNotFoundError(
+                f"{path} not found: build it with `python -m fastintercu_vvc_b200.build` (there is no CPU fallback)"
+            )
+        L = C.CDLL(path)
+        for name, (res, args) in EXPORTS.items():
+            fn = getattr(L, name)  # AttributeError if a declared symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = L
+    return _LIB
+
+
+def _i16_2d(a: np.ndarray):
+    if a.dtype != np.int16 or a.ndim != 2 or a.shape != (CTU, CTU) or a.strides[1] != 2 or a.strides[0] % 2:
+        raise ValueError("expected an int16 [128,128] view with unit element stride (row stride may be larger)")
+    return a.ctypes.data, a.strides[0] // 2
+
+
+class MltPredictor:
+    """One context per process per GPU (single-threaded, synchronous), like the reference hook."""
+
+    def __init__(self, weights_path: str, device: int = 0, max_batch: int = 512):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        rc = self._lib.mlt_create_ex(C.byref(self._h), os.fsencode(weights_path), int(device), int(max_batch))
+        if rc != 0:
+            self._h = C.c_void_p()
+            raise MltError(rc, "mlt_create_ex", self._lib.mlt_strerror(rc).decode())
+        self.max_batch = max_batch
+
+    # -- lifecycle
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.mlt_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc, what):
+        if rc < 0:
+            raise MltError(rc, what, self._lib.mlt_last_error(self._h).decode() or self._lib.mlt_strerror(rc).decode())
+        return rc
+
+    # -- the hook call (EncCu.cpp:806-921)
+    def predict_ctu(self, org: np.ndarray, pred: np.ndarray, poc: int, qp: int) -> np.void:
+        op, os_ = _i16_2d(org)
+        pp, ps = _i16_2d(pred)
+        out = np.zeros(1, RESULT_DTYPE)
+        self._check(self._lib.mlt_predict_ctu(self._h, op, os_, pp, ps, int(poc), int(qp), out.ctypes.data), "mlt_predict_ctu")
+        return out[0]
+
+    def predict_batch(self, ctus) -> np.ndarray:
+        """ctus: sequence of (org, pred, poc, qp) with int16 [128,128] views (strided rows allowed)."""
+        n = len(ctus)
+        descs = (CtuDesc * max(n, 1))()
+        for i, (org, pred, poc, qp) in enumerate(ctus):
+            descs[i].org, descs[i].org_stride = _i16_2d(org)
+            descs[i].pred, descs[i].pred_stride = _i16_2d(pred)
+            descs[i].poc, descs[i].qp = int(poc), int(qp)
+        out = np.zeros(n, RESULT_DTYPE)
+        self._check(self._lib.mlt_predict_batch(self._h, n, descs, out.ctypes.data), "mlt_predict_batch")
+        return out
+
+    def predict_batch_dense(self, orgpred: np.ndarray, pocqp: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        n = len(orgpred)
+        if orgpred.dtype != np.int16 or orgpred.shape[1:] != (2, CTU, CTU) or not orgpred.flags.c_contiguous:
+            raise ValueError("orgpred must be C-contiguous int16 [n,2,128,128]")
+        pocqp = np.ascontiguousarray(pocqp, np.int32)
+        if out is None:
+            out = np.zeros(n, RESULT_DTYPE)
+        self._check(
+            self._lib.mlt_predict_batch_dense(self._h, n, orgpred.ctypes.data, pocqp.ctypes.data, out.ctypes.data),
+            "mlt_predict_batch_dense",
+        )
+        return out
+
+    def predict_batch_device(self, n: int, d_orgpred: int, d_pocqp: int, d_out: int, stream: int = 0):
+        """Raw device pointers (e.g. torch.Tensor.data_ptr()) and a cudaStream_t handle; asynchronous."""
+        self._check(
+            self._lib.mlt_predict_batch_device(self._h, int(n), C.c_void_p(d_orgpred), C.c_void_p(d_pocqp), C.c_void_p(d_out), C.c_void_p(stream)),
+            "mlt_predict_batch_device",
+        )
+
+    # -- per-picture staging
+    def begin_picture(self, org_luma: np.ndarray, poc: int):
+        if org_luma.dtype != np.int16 or org_luma.ndim != 2 or org_luma.strides[1] != 2:
+            raise ValueError("org_luma must be an int16 2-D view")
+        h, w = org_luma.shape
+        self._check(
+            self._lib.mlt_begin_picture(self._h, org_luma.ctypes.data, org_luma.strides[0] // 2, w, h, int(poc)), "mlt_begin_picture"
+        )
+
+    def predict_ctu_in_picture(self, x: int, y: int, pred: np.ndarray, qp: int) -> np.void:
+        pp, ps = _i16_2d(pred)
+        out = np.zeros(1, RESULT_DTYPE)
+        self._check(
+            self._lib.mlt_predict_ctu_in_picture(self._h, int(x), int(y), pp, ps, int(qp), out.ctypes.data), "mlt_predict_ctu_in_picture"
+        )
+        return out[0]
+
+    # -- test hooks
+    def set_engine(self, engine: int):
+        self._check(self._lib.mlt_set_engine(self._h, int(engine)), "mlt_set_engine")
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.mlt_launch_count(self._h))
+
+    def set_profiling(self, on: bool):
+        self._check(self._lib.mlt_set_profiling(self._h, int(bool(on))), "mlt_set_profiling")
+
+    def get_profile(self) -> np.ndarray:
+        """Device time (ms) of each kernel of the last batch: [stage+conv1, 16 convs, head]."""
+        ms = np.zeros(18, np.float32)
+        n = self._check(self._lib.mlt_get_profile(self._h, ms.ctypes.data, 18), "mlt_get_profile")
+        return ms[:n]
+
+    def debug_stage(self, ctus) -> np.ndarray:
+        n = len(ctus)
+        descs = (CtuDesc * n)()
+        for i, (org, pred, poc, qp) in enumerate(ctus):
+            descs[i].org, descs[i].org_stride = _i16_2d(org)
+            descs[i].pred, descs[i].pred_stride = _i16_2d(pred)
+            descs[i].poc, descs[i].qp = int(poc), int(qp)
+        out = np.empty((n, 2, CTU, CTU), np.float32)
+        self._check(self._lib.mlt_debug_stage(self._h, n, descs, out.ctypes.data), "mlt_debug_stage")
+        return out
+
+    def debug_activation(self, layer: int, n: int) -> np.ndarray:
+        shapes = [(128, 32)] + [(64, 32)] * 4 + [(32, 64)] * 4 + [(16, 128)] * 4 + [(8, 256)] * 4
+        h, c = shapes[layer]
+        out = np.empty((n, h, h, c), np.float32)
+        got = self._check(self._lib.mlt_debug_activation(self._h, layer, out.ctypes.data, out.size), "mlt_debug_activation")
+        assert got == out.size, (got, out.size)
+        return out

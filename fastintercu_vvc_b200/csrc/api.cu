@@ -1,0 +1,554 @@
+// api.cu -- the C ABI of libmltcnn.so (include/mltcnn.h): context, weight blob, buffers, launch sequence.
+// Replaces the inline libtorch/OpenCV block of EncCu::xCompressCU (EncCu.cpp:803-926).  No CPU fallback.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "mlt_internal.h"
+
+using namespace mlt;
+
+namespace {
+
+constexpr uint32_t MLTW_MAGIC = 0x57544C4Du;
+enum : uint32_t {
+    SEC_CONV1_F32 = 0x001, SEC_W_F16 = 0x100, SEC_BIAS_FUSED = 0x200, SEC_W_F32 = 0x300, SEC_BIAS = 0x400,
+    SEC_SC_W_F16 = 0x500, SEC_SC_W_F32 = 0x600, SEC_SC_BIAS = 0x700, SEC_FC_W = 0x800, SEC_FC_B = 0x900
+};
+
+constexpr int NCONV = 16, NACT = 17, CTU = MLT_CTU_SIZE;
+constexpr size_t CTU_IN_ELEMS = (size_t)2 * CTU * CTU; // org + pred planes
+
+// forward order of the 16 3x3 convs after conv1 (arch.py:247-254 with BasicBlock [2,2,2,2])
+const LayerDesc kLayers[NCONV] = {
+    {32, 32, 2, 64, -1},   {32, 32, 1, 64, 0},    {32, 32, 1, 64, -1},   {32, 32, 1, 64, -1},
+    {32, 64, 2, 32, -1},   {64, 64, 1, 32, 1},    {64, 64, 1, 32, -1},   {64, 64, 1, 32, -1},
+    {64, 128, 2, 16, -1},  {128, 128, 1, 16, 2},  {128, 128, 1, 16, -1}, {128, 128, 1, 16, -1},
+    {128, 256, 2, 8, -1},  {256, 256, 1, 8, 3},   {256, 256, 1, 8, -1},  {256, 256, 1, 8, -1},
+};
+
+// activation a: 0 = conv1 out, 1 + li = output of conv li.  (H, C) of each.
+inline void act_shape(int a, int &h, int &c)
+{
+    if (a == 0) { h = 128; c = 32; return; }
+    h = kLayers[a - 1].hout;
+    c = kLayers[a - 1].cout;
+}
+inline size_t act_elems(int a)
+{
+    int h, c;
+    act_shape(a, h, c);
+    return (size_t)h * h * c;
+}
+
+struct Section { const uint8_t *dev = nullptr; size_t bytes = 0; };
+
+} // namespace
+
+struct mlt_ctx {
+    int device = 0, max_batch = 0, engine = 0, num_sms = 0;
+    cudaStream_t stream = nullptr;
+    uint8_t *d_blob = nullptr;
+    size_t blob_bytes = 0;
+    Section sec[0x1000];
+    __half *act_h[NACT] = {};
+    float *act_f[NACT] = {};
+    float *scratch_f = nullptr; // shortcut-conv output of the fp32 engine
+    int16_t *d_in = nullptr, *h_in = nullptr; // dense [max_batch][2][128][128]
+    CtuDev *d_ctus = nullptr, *h_ctus = nullptr;
+    mlt_result *d_out = nullptr, *h_out = nullptr;
+    float *d_dbg = nullptr; // mlt_debug_stage / mlt_debug_activation staging
+    size_t dbg_bytes = 0;
+    int16_t *d_pic = nullptr; // picture original luma (mlt_begin_picture)
+    size_t pic_capacity = 0;
+    int pic_pitch = 0, pic_w = 0, pic_h = 0, pic_poc = 0;
+    bool pic_valid = false;
+    int last_n = 0;
+    uint64_t launches = 0;
+    bool profiling = false;
+    cudaEvent_t prof_ev[NCONV + 3] = {}; // boundaries of: stage+conv1, 16 convs, head
+    cudaStream_t prof_stream = nullptr;
+    bool prof_valid = false;
+    std::string err;
+};
+
+namespace {
+
+int fail(mlt_ctx *c, int rc, const char *fmt, ...)
+{
+    if (c) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        c->err = buf;
+    }
+    return rc;
+}
+
+#define CU(call)                                                                                                   \
+    do {                                                                                                           \
+        cudaError_t e_ = (call);                                                                                   \
+        if (e_ != cudaSuccess) return fail(c, e_ == cudaErrorMemoryAllocation ? MLT_E_NOMEM : MLT_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+int load_blob(mlt_ctx *c, const char *path)
+{
+    FILE *f = fopen(path, "rb");
+    if (!f) return fail(c, MLT_E_IO, "cannot open weight blob '%s'", path);
+    fseek(f, 0, SEEK_END);
+    const long sz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    std::vector<uint8_t> raw((size_t)(sz > 0 ? sz : 0));
+    const size_t got = raw.empty() ? 0 : fread(raw.data(), 1, raw.size(), f);
+    fclose(f);
+    if (got != raw.size() || raw.size() < 32) return fail(c, MLT_E_IO, "short read on '%s'", path);
+    uint32_t hdr[4];
+    uint64_t total;
+    memcpy(hdr, raw.data(), 16);
+    memcpy(&total, raw.data() + 16, 8);
+    if (hdr[0] != MLTW_MAGIC || hdr[1] != 1 || hdr[2] != 128 || total != raw.size() || 32 + (size_t)hdr[3] * 24 > raw.size())
+        return fail(c, MLT_E_FORMAT, "'%s' is not an MLTW v1 blob for the 128x128 CTU model", path);
+    CU(cudaMalloc(&c->d_blob, raw.size()));
+    c->blob_bytes = raw.size();
+    CU(cudaMemcpy(c->d_blob, raw.data(), raw.size(), cudaMemcpyHostToDevice));
+    for (uint32_t i = 0; i < hdr[3]; i++) {
+        uint32_t id, dt;
+        uint64_t off, nb;
+        const uint8_t *e = raw.data() + 32 + (size_t)i * 24;
+        memcpy(&id, e, 4); memcpy(&dt, e + 4, 4); memcpy(&off, e + 8, 8); memcpy(&nb, e + 16, 8);
+        if (id >= 0x1000 || off + nb > raw.size() || (off & 255)) return fail(c, MLT_E_FORMAT, "bad section table in '%s'", path);
+        c->sec[id].dev = c->d_blob + off;
+        c->sec[id].bytes = nb;
+    }
+    // every section this architecture needs must be present with the exact size
+    auto need = [&](uint32_t id, size_t bytes) { return c->sec[id].dev != nullptr && c->sec[id].bytes == bytes; };
+    bool ok = need(SEC_CONV1_F32, 9 * 2 * 32 * 4);
+    for (int li = 0; li < NCONV && ok; li++) {
+        const LayerDesc &L = kLayers[li];
+        ok = need(SEC_W_F16 + li, (size_t)9 * L.cin * L.cout * 2) && need(SEC_W_F32 + li, (size_t)9 * L.cin * L.cout * 4) &&
+             need(SEC_BIAS + li, (size_t)L.cout * 4) && need(SEC_BIAS_FUSED + li, (size_t)L.cout * 4);
+        if (ok && L.sc >= 0) {
+            const int csc = kLayers[li - 1].cin;
+            ok = need(SEC_SC_W_F16 + L.sc, (size_t)csc * L.cout * 2) && need(SEC_SC_W_F32 + L.sc, (size_t)csc * L.cout * 4) &&
+                 need(SEC_SC_BIAS + L.sc, (size_t)L.cout * 4);
+        }
+    }
+    static const int fin[3] = {66, 130, 258}, fout[3] = {2, 3, 4};
+    for (int i = 0; i < 3 && ok; i++) ok = need(SEC_FC_W + i, (size_t)fin[i] * fout[i] * 4) && need(SEC_FC_B + i, (size_t)fout[i] * 4);
+    if (!ok) return fail(c, MLT_E_FORMAT, "'%s': missing or mis-sized section", path);
+    return MLT_OK;
+}
+
+template <typename T>
+const T *secp(const mlt_ctx *c, uint32_t id) { return reinterpret_cast<const T *>(c->sec[id].dev); }
+
+int ensure_f32_buffers(mlt_ctx *c)
+{
+    if (c->act_f[0]) return MLT_OK;
+    for (int a = 0; a < NACT; a++) CU(cudaMalloc(&c->act_f[a], act_elems(a) * c->max_batch * sizeof(float)));
+    CU(cudaMalloc(&c->scratch_f, (size_t)64 * 64 * 32 * c->max_batch * sizeof(float)));
+    return MLT_OK;
+}
+
+int ensure_dbg(mlt_ctx *c, size_t bytes)
+{
+    if (c->dbg_bytes >= bytes) return MLT_OK;
+    if (c->d_dbg) cudaFree(c->d_dbg);
+    c->d_dbg = nullptr;
+    c->dbg_bytes = 0;
+    CU(cudaMalloc(&c->d_dbg, bytes));
+    c->dbg_bytes = bytes;
+    return MLT_OK;
+}
+
+__global__ void dense_descs_kernel(CtuDev *ctus, const int16_t *orgpred, const int32_t *pocqp, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    CtuDev d;
+    d.org = orgpred + (size_t)i * CTU_IN_ELEMS;
+    d.pred = d.org + (size_t)CTU * CTU;
+    d.org_stride = d.pred_stride = CTU;
+    d.poc = pocqp[2 * i];
+    d.qp = pocqp[2 * i + 1];
+    ctus[i] = d;
+}
+
+// The whole network on `n` CTUs described by device array `ctus`; results to device array `out`.
+int run_network(mlt_ctx *c, const CtuDev *ctus, int n, mlt_result *out, cudaStream_t s)
+{
+    HeadParams hp;
+    hp.ctus = ctus; hp.out = out; hp.n = n;
+    for (int i = 0; i < 3; i++) { hp.fc_w[i] = secp<float>(c, SEC_FC_W + i); hp.fc_b[i] = secp<float>(c, SEC_FC_B + i); }
+    if (c->engine == 0) {
+        // ---- product path: fused staging+conv1, 16 tcgen05 implicit-GEMM convs, head
+        const bool prof = c->profiling;
+        int ev = 0;
+        if (prof) { CU(cudaEventRecord(c->prof_ev[ev++], s)); c->prof_stream = s; c->prof_valid = false; }
+        CU(launch_stage_conv1_h(ctus, n, secp<float>(c, SEC_CONV1_F32), c->act_h[0], s));
+        c->launches++;
+        if (prof) CU(cudaEventRecord(c->prof_ev[ev++], s));
+        for (int li = 0; li < NCONV; li++) {
+            const LayerDesc &L = kLayers[li];
+            const bool conv2 = (li & 1) != 0;
+            const __half *x_block = c->act_h[li & ~1]; // input of the BasicBlock this conv belongs to
+            const __half *in = c->act_h[li];
+            const __half *sc_in = nullptr, *sc_w = nullptr, *res = nullptr;
+            if (conv2) {
+                if (L.sc >= 0) { sc_in = x_block; sc_w = secp<__half>(c, SEC_SC_W_F16 + L.sc); }
+                else res = x_block;
+            }
+            CU(launch_conv_umma(li, in, secp<__half>(c, SEC_W_F16 + li), secp<float>(c, SEC_BIAS_FUSED + li), sc_in, sc_w, res,
+                                c->act_h[li + 1], n, 1, c->num_sms, s));
+            c->launches++;
+            if (prof) CU(cudaEventRecord(c->prof_ev[ev++], s));
+        }
+        hp.act[0] = c->act_h[8]; hp.act[1] = c->act_h[12]; hp.act[2] = c->act_h[16];
+        CU(launch_head_h(hp, s));
+        c->launches++;
+        if (prof) { CU(cudaEventRecord(c->prof_ev[ev++], s)); c->prof_valid = true; }
+    } else {
+        // ---- fp32 CUDA-core cross-check engine (tests)
+        int rc = ensure_f32_buffers(c);
+        if (rc) return rc;
+        CU(launch_stage_conv1_f(ctus, n, secp<float>(c, SEC_CONV1_F32), c->act_f[0], s));
+        c->launches++;
+        for (int li = 0; li < NCONV; li++) {
+            const LayerDesc &L = kLayers[li];
+            const bool conv2 = (li & 1) != 0;
+            const float *x_block = c->act_f[li & ~1];
+            const float *res = nullptr;
+            if (conv2) {
+                if (L.sc >= 0) {
+                    const LayerDesc &L1 = kLayers[li - 1];
+                    CU(launch_conv_simt(x_block, secp<float>(c, SEC_SC_W_F32 + L.sc), secp<float>(c, SEC_SC_BIAS + L.sc), nullptr,
+                                        c->scratch_f, n, L1.hout * L1.stride, L1.cin, L.cout, 1, 2, 0, s));
+                    c->launches++;
+                    res = c->scratch_f;
+                } else res = x_block;
+            }
+            CU(launch_conv_simt(c->act_f[li], secp<float>(c, SEC_W_F32 + li), secp<float>(c, SEC_BIAS + li), res, c->act_f[li + 1], n,
+                                L.hout * L.stride, L.cin, L.cout, 3, L.stride, 1, s));
+            c->launches++;
+        }
+        hp.act[0] = c->act_f[8]; hp.act[1] = c->act_f[12]; hp.act[2] = c->act_f[16];
+        CU(launch_head_f(hp, s));
+        c->launches++;
+    }
+    c->last_n = n;
+    return MLT_OK;
+}
+
+// gather one CTU (two strided 128x128 int16 blocks) into the dense pinned staging buffer
+void gather_ctu(int16_t *dst, const int16_t *org, int org_stride, const int16_t *pred, int pred_stride)
+{
+    for (int y = 0; y < CTU; y++) memcpy(dst + (size_t)y * CTU, org + (size_t)y * org_stride, CTU * sizeof(int16_t));
+    dst += (size_t)CTU * CTU;
+    for (int y = 0; y < CTU; y++) memcpy(dst + (size_t)y * CTU, pred + (size_t)y * pred_stride, CTU * sizeof(int16_t));
+}
+
+void dense_descs(mlt_ctx *c, int n, const int32_t *pocqp, const mlt_ctu_desc *descs)
+{
+    for (int i = 0; i < n; i++) {
+        CtuDev &d = c->h_ctus[i];
+        d.org = c->d_in + (size_t)i * CTU_IN_ELEMS;
+        d.pred = d.org + (size_t)CTU * CTU;
+        d.org_stride = d.pred_stride = CTU;
+        d.poc = descs ? descs[i].poc : pocqp[2 * i];
+        d.qp = descs ? descs[i].qp : pocqp[2 * i + 1];
+    }
+}
+
+// h_in[0..n) and h_ctus[0..n) are filled: upload, run, download, wait.
+int run_host_batch(mlt_ctx *c, int n, mlt_result *out, bool upload_in)
+{
+    cudaStream_t s = c->stream;
+    if (upload_in) CU(cudaMemcpyAsync(c->d_in, c->h_in, (size_t)n * CTU_IN_ELEMS * sizeof(int16_t), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(c->d_ctus, c->h_ctus, (size_t)n * sizeof(CtuDev), cudaMemcpyHostToDevice, s));
+    int rc = run_network(c, c->d_ctus, n, c->d_out, s);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(c->h_out, c->d_out, (size_t)n * sizeof(mlt_result), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    memcpy(out, c->h_out, (size_t)n * sizeof(mlt_result));
+    return MLT_OK;
+}
+
+int check_ctx(mlt_ctx *c)
+{
+    if (!c) return MLT_E_INVAL;
+    c->err.clear();
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e != cudaSuccess) return fail(c, MLT_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    return MLT_OK;
+}
+
+} // namespace
+
+// ================================================================================================ C ABI
+
+extern "C" {
+
+int mlt_abi_version(void) { return MLT_ABI_VERSION; }
+
+const char *mlt_strerror(int rc)
+{
+    switch (rc) {
+    case MLT_OK: return "ok";
+    case MLT_E_INVAL: return "invalid argument";
+    case MLT_E_IO: return "weight file unreadable";
+    case MLT_E_FORMAT: return "weight file is not an MLTW blob for this architecture";
+    case MLT_E_CUDA: return "CUDA error";
+    case MLT_E_NOMEM: return "out of memory";
+    case MLT_E_NODEVICE: return "no sm_100 CUDA device";
+    case MLT_E_BATCH: return "batch larger than max_batch";
+    case MLT_E_STATE: return "call sequence error";
+    default: return "unknown error";
+    }
+}
+
+const char *mlt_last_error(const mlt_ctx *ctx) { return ctx ? ctx->err.c_str() : ""; }
+
+void mlt_destroy(mlt_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (int a = 0; a < NACT; a++) { cudaFree(c->act_h[a]); cudaFree(c->act_f[a]); }
+    cudaFree(c->scratch_f); cudaFree(c->d_blob); cudaFree(c->d_in); cudaFree(c->d_ctus); cudaFree(c->d_out);
+    cudaFree(c->d_dbg); cudaFree(c->d_pic);
+    cudaFreeHost(c->h_in); cudaFreeHost(c->h_ctus); cudaFreeHost(c->h_out);
+    for (cudaEvent_t e : c->prof_ev) if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int mlt_create_ex(mlt_ctx **out, const char *weights_path, int cuda_device, int max_batch)
+{
+    if (!out) return MLT_E_INVAL;
+    *out = nullptr;
+    if (!weights_path || max_batch < 1 || max_batch > (1 << 16)) return MLT_E_INVAL;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return MLT_E_NODEVICE;
+    if (cuda_device < 0 || cuda_device >= ndev) return MLT_E_NODEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cuda_device) != cudaSuccess) return MLT_E_NODEVICE;
+    if (prop.major != 10) return MLT_E_NODEVICE; // sm_100a cubin only: tcgen05 / TMEM required, no other path exists
+    mlt_ctx *c = new (std::nothrow) mlt_ctx();
+    if (!c) return MLT_E_NOMEM;
+    c->device = cuda_device;
+    c->max_batch = max_batch;
+    c->num_sms = prop.multiProcessorCount;
+    int rc = MLT_OK;
+    auto body = [&]() -> int {
+        CU(cudaSetDevice(cuda_device));
+        CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        int r = load_blob(c, weights_path);
+        if (r) return r;
+        CU(conv_umma_init());
+        for (int a = 0; a < NACT; a++) CU(cudaMalloc(&c->act_h[a], act_elems(a) * max_batch * sizeof(__half)));
+        CU(cudaMalloc(&c->d_in, (size_t)max_batch * CTU_IN_ELEMS * sizeof(int16_t)));
+        CU(cudaMalloc(&c->d_ctus, (size_t)max_batch * sizeof(CtuDev)));
+        CU(cudaMalloc(&c->d_out, (size_t)max_batch * sizeof(mlt_result)));
+        CU(cudaHostAlloc(&c->h_in, (size_t)max_batch * CTU_IN_ELEMS * sizeof(int16_t), cudaHostAllocDefault));
+        CU(cudaHostAlloc(&c->h_ctus, (size_t)max_batch * sizeof(CtuDev), cudaHostAllocDefault));
+        CU(cudaHostAlloc(&c->h_out, (size_t)max_batch * sizeof(mlt_result), cudaHostAllocDefault));
+        return MLT_OK;
+    };
+    rc = body();
+    if (rc != MLT_OK) {
+        fprintf(stderr, "mlt_create: %s (%s)\n", mlt_strerror(rc), c->err.c_str());
+        mlt_destroy(c);
+        return rc;
+    }
+    *out = c;
+    return MLT_OK;
+}
+
+int mlt_create(mlt_ctx **out, const char *weights_path, int cuda_device)
+{
+    return mlt_create_ex(out, weights_path, cuda_device, 512); // 480 eligible CTUs in a 2160p picture
+}
+
+int mlt_set_engine(mlt_ctx *c, int engine)
+{
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (engine != 0 && engine != 1) return fail(c, MLT_E_INVAL, "engine must be 0 (tcgen05) or 1 (fp32 cross-check)");
+    c->engine = engine;
+    return MLT_OK;
+}
+
+uint64_t mlt_launch_count(const mlt_ctx *c) { return c ? c->launches : 0; }
+
+int mlt_set_profiling(mlt_ctx *c, int on)
+{
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (on && !c->prof_ev[0])
+        for (cudaEvent_t &e : c->prof_ev) CU(cudaEventCreate(&e));
+    c->profiling = on != 0;
+    c->prof_valid = false;
+    return MLT_OK;
+}
+
+int mlt_get_profile(mlt_ctx *c, float *ms, int capacity)
+{
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    constexpr int NK = NCONV + 2;
+    if (!ms || capacity < NK) return fail(c, MLT_E_INVAL, "capacity must be >= %d", NK);
+    if (!c->prof_valid) return fail(c, MLT_E_STATE, "no profiled batch has been run");
+    CU(cudaEventSynchronize(c->prof_ev[NK]));
+    for (int i = 0; i < NK; i++) CU(cudaEventElapsedTime(&ms[i], c->prof_ev[i], c->prof_ev[i + 1]));
+    return NK;
+}
+
+int mlt_predict_batch(mlt_ctx *c, int n, const mlt_ctu_desc *descs, mlt_result *out)
+{
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!descs || !out))) return fail(c, MLT_E_INVAL, "null argument");
+    if (n > c->max_batch) return fail(c, MLT_E_BATCH, "n=%d > max_batch=%d", n, c->max_batch);
+    if (n == 0) return MLT_OK;
+    for (int i = 0; i < n; i++) {
+        if (!descs[i].org || !descs[i].pred) return fail(c, MLT_E_INVAL, "descs[%d]: null org/pred", i);
+        gather_ctu(c->h_in + (size_t)i * CTU_IN_ELEMS, descs[i].org, descs[i].org_stride, descs[i].pred, descs[i].pred_stride);
+    }
+    dense_descs(c, n, nullptr, descs);
+    return run_host_batch(c, n, out, true);
+}
+
+int mlt_predict_ctu(mlt_ctx *c, const int16_t *org, int org_stride, const int16_t *pred, int pred_stride, int poc, int qp,
+                    mlt_result *out)
+{
+    mlt_ctu_desc d;
+    d.org = org; d.pred = pred; d.org_stride = org_stride; d.pred_stride = pred_stride; d.poc = poc; d.qp = qp;
+    return mlt_predict_batch(c, 1, &d, out);
+}
+
+int mlt_predict_batch_dense(mlt_ctx *c, int n, const int16_t *orgpred, const int32_t *pocqp, mlt_result *out)
+{
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!orgpred || !pocqp || !out))) return fail(c, MLT_E_INVAL, "null argument");
+    if (n > c->max_batch) return fail(c, MLT_E_BATCH, "n=%d > max_batch=%d", n, c->max_batch);
+    if (n == 0) return MLT_OK;
+    cudaStream_t s = c->stream;
+    // straight from the caller's buffer (pinned or pageable): no intermediate host copy
+    CU(cudaMemcpyAsync(c->d_in, orgpred, (size_t)n * CTU_IN_ELEMS * sizeof(int16_t), cudaMemcpyHostToDevice, s));
+    dense_descs(c, n, pocqp, nullptr);
+    return run_host_batch(c, n, out, false);
+}
+
+int mlt_predict_batch_device(mlt_ctx *c, int n, const int16_t *d_orgpred, const int32_t *d_pocqp, mlt_result *d_out,
+                             void *cuda_stream)
+{
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!d_orgpred || !d_pocqp || !d_out))) return fail(c, MLT_E_INVAL, "null argument");
+    if (n > c->max_batch) return fail(c, MLT_E_BATCH, "n=%d > max_batch=%d", n, c->max_batch);
+    if (((uintptr_t)d_orgpred & 15) != 0) return fail(c, MLT_E_INVAL, "d_orgpred must be 16-byte aligned");
+    if (n == 0) return MLT_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+    // descriptors are built on the device: nothing crosses PCIe on this path
+    dense_descs_kernel<<<(n + 255) / 256, 256, 0, s>>>(c->d_ctus, d_orgpred, d_pocqp, n);
+    CU(cudaGetLastError());
+    c->launches++;
+    return run_network(c, c->d_ctus, n, d_out, s);
+}
+
+int mlt_begin_picture(mlt_ctx *c, const int16_t *org_luma, int stride, int width, int height, int poc)
+{
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (!org_luma || width < CTU || height < CTU || stride < width) return fail(c, MLT_E_INVAL, "bad picture geometry");
+    const int pitch = (width + 7) & ~7; // rows 16-byte aligned on the device
+    const size_t need = (size_t)pitch * height;
+    if (need > c->pic_capacity) {
+        if (c->d_pic) cudaFree(c->d_pic);
+        c->d_pic = nullptr;
+        c->pic_capacity = 0;
+        c->pic_valid = false;
+        CU(cudaMalloc(&c->d_pic, need * sizeof(int16_t)));
+        c->pic_capacity = need;
+    }
+    CU(cudaMemcpy2DAsync(c->d_pic, (size_t)pitch * sizeof(int16_t), org_luma, (size_t)stride * sizeof(int16_t),
+                         (size_t)width * sizeof(int16_t), height, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream)); // the caller may reuse / modify its buffer after return
+    c->pic_pitch = pitch; c->pic_w = width; c->pic_h = height; c->pic_poc = poc; c->pic_valid = true;
+    return MLT_OK;
+}
+
+int mlt_predict_ctu_in_picture(mlt_ctx *c, int x, int y, const int16_t *pred, int pred_stride, int qp, mlt_result *out)
+{
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (!c->pic_valid) return fail(c, MLT_E_STATE, "mlt_begin_picture has not been called");
+    if (!pred || !out) return fail(c, MLT_E_INVAL, "null argument");
+    // same gate as EncCu.cpp:755: the CTU must lie fully inside the picture; x must keep 16-byte alignment
+    if (x < 0 || y < 0 || x + CTU > c->pic_w || y + CTU > c->pic_h || (x & 7)) return fail(c, MLT_E_INVAL, "CTU (%d,%d) not inside the picture", x, y);
+    int16_t *hp = c->h_in + (size_t)CTU * CTU; // pred plane slot of CTU 0
+    for (int r = 0; r < CTU; r++) memcpy(hp + (size_t)r * CTU, pred + (size_t)r * pred_stride, CTU * sizeof(int16_t));
+    cudaStream_t s = c->stream;
+    CU(cudaMemcpyAsync(c->d_in + (size_t)CTU * CTU, hp, (size_t)CTU * CTU * sizeof(int16_t), cudaMemcpyHostToDevice, s));
+    CtuDev &d = c->h_ctus[0];
+    d.org = c->d_pic + (size_t)y * c->pic_pitch + x;
+    d.org_stride = c->pic_pitch;
+    d.pred = c->d_in + (size_t)CTU * CTU;
+    d.pred_stride = CTU;
+    d.poc = c->pic_poc;
+    d.qp = qp;
+    return run_host_batch(c, 1, out, false);
+}
+
+int mlt_debug_stage(mlt_ctx *c, int n, const mlt_ctu_desc *descs, float *out)
+{
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (n < 1 || !descs || !out) return fail(c, MLT_E_INVAL, "null argument");
+    if (n > c->max_batch) return fail(c, MLT_E_BATCH, "n=%d > max_batch=%d", n, c->max_batch);
+    for (int i = 0; i < n; i++)
+        gather_ctu(c->h_in + (size_t)i * CTU_IN_ELEMS, descs[i].org, descs[i].org_stride, descs[i].pred, descs[i].pred_stride);
+    dense_descs(c, n, nullptr, descs);
+    const size_t bytes = (size_t)n * CTU_IN_ELEMS * sizeof(float);
+    rc = ensure_dbg(c, bytes);
+    if (rc) return rc;
+    cudaStream_t s = c->stream;
+    CU(cudaMemcpyAsync(c->d_in, c->h_in, (size_t)n * CTU_IN_ELEMS * sizeof(int16_t), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(c->d_ctus, c->h_ctus, (size_t)n * sizeof(CtuDev), cudaMemcpyHostToDevice, s));
+    CU(launch_stage(c->d_ctus, n, c->d_dbg, s));
+    c->launches++;
+    CU(cudaMemcpyAsync(out, c->d_dbg, bytes, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return MLT_OK;
+}
+
+int64_t mlt_debug_activation(mlt_ctx *c, int layer, float *out, int64_t capacity)
+{
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (layer < 0 || layer >= NACT || !out) return fail(c, MLT_E_INVAL, "bad layer");
+    if (c->last_n <= 0) return fail(c, MLT_E_STATE, "no batch has been run");
+    const size_t elems = act_elems(layer) * c->last_n;
+    if ((int64_t)elems > capacity) return fail(c, MLT_E_INVAL, "capacity %lld < %zu", (long long)capacity, elems);
+    cudaStream_t s = c->stream;
+    if (c->engine == 0) {
+        rc = ensure_dbg(c, elems * sizeof(float));
+        if (rc) return rc;
+        CU(launch_half_to_float(c->act_h[layer], c->d_dbg, elems, s));
+        CU(cudaMemcpyAsync(out, c->d_dbg, elems * sizeof(float), cudaMemcpyDeviceToHost, s));
+    } else {
+        if (!c->act_f[layer]) return fail(c, MLT_E_STATE, "fp32 engine has not run");
+        CU(cudaMemcpyAsync(out, c->act_f[layer], elems * sizeof(float), cudaMemcpyDeviceToHost, s));
+    }
+    CU(cudaStreamSynchronize(s));
+    return (int64_t)elems;
+}
+
+} // extern "C"

@@ -1,0 +1,180 @@
+"""Offline weight packer: reference state_dict -> MLTW blob loaded once by mlt_create().
+
+Replaces the TorchScript container the reference hook re-loads per CTU (EncCu.cpp:894-900; exported by
+mlt-cnn-python/codes/model2torchScript.py:22-48).  Input is the same state_dict that script reads
+(`torch.load(path)['params']`, optional `module.` prefixes, :23-32) or an in-memory dict of numpy arrays.
+
+What it does
+  * folds every eval-mode BatchNorm (eps 1e-5) into the preceding bias-free conv:
+        w' = w * gamma / sqrt(var + eps),  b' = beta - mean * gamma / sqrt(var + eps)
+    (the top-level `bn1.*` keys are ignored: defined but unused, arch.py:247 vs :277-278);
+  * writes the folded 3x3 / 1x1 conv weights as fp16 in the tcgen05 shared-memory operand layout used by
+    csrc/conv_umma.cuh: K-major, no-swizzle core matrices, [cin_group][tap][G/8][Cout][8] so that every
+    (cin_group, tap) slab is one contiguous bulk copy;
+  * writes fp32 copies ([tap][Cin][Cout]) for the fp32 CUDA-core cross-check engine, the fp32 biases, the
+    fp32 conv1 ([tap][2][32], consumed by the fused staging+conv1 kernel) and the three FC heads.
+
+CLI:  python -m fastintercu_vvc_b200.pack_weights model.pth out.mltw
+"""
+from __future__ import annotations
+
+import struct
+import sys
+
+import numpy as np
+
+MAGIC = 0x57544C4D  # "MLTW"
+VERSION = 1
+ARCH_CTU128 = 128
+BN_EPS = 1e-5
+PLANES = (32, 64, 128, 256)
+
+SEC_CONV1_F32 = 0x001
+SEC_W_F16 = 0x100
+SEC_BIAS_FUSED = 0x200
+SEC_W_F32 = 0x300
+SEC_BIAS = 0x400
+SEC_SC_W_F16 = 0x500
+SEC_SC_W_F32 = 0x600
+SEC_SC_BIAS = 0x700
+SEC_FC_W = 0x800
+SEC_FC_B = 0x900
+
+
+def conv_table():
+    """3x3 convs after conv1, forward order: (prefix, cin, cout, stride, hout, cin_group, shortcut_idx|-1)."""
+    rows = []
+    cin, hin = 32, 128
+    for L, planes in enumerate(PLANES):
+        hout = hin // 2
+        p = f"layer{L}"
+        rows.append((f"{p}.0.conv1", cin, planes, 2, hout, 32, -1))
+        rows.append((f"{p}.0.conv2", planes, planes, 1, hout, min(planes, 64), L))
+        rows.append((f"{p}.1.conv1", planes, planes, 1, hout, min(planes, 64), -1))
+        rows.append((f"{p}.1.conv2", planes, planes, 1, hout, min(planes, 64), -1))
+        cin, hin = planes, hout
+    return rows
+
+
+def _np(v):
+    if hasattr(v, "detach"):
+        v = v.detach().cpu().numpy()
+    return np.asarray(v)
+
+
+def normalise_state_dict(sd: dict) -> dict:
+    """Accepts the checkpoint dict, its 'params' entry, torch tensors or numpy arrays; strips 'module.'."""
+    if "params" in sd and not any(k.endswith(".weight") for k in sd):
+        sd = sd["params"]
+    out = {}
+    for k, v in sd.items():
+        if k.startswith("module."):
+            k = k[7:]
+        out[k] = _np(v)
+    return out
+
+
+def fold_bn(w: np.ndarray, sd: dict, bn: str):
+    g = sd[f"{bn}.weight"].astype(np.float64)
+    b = sd[f"{bn}.bias"].astype(np.float64)
+    m = sd[f"{bn}.running_mean"].astype(np.float64)
+    v = sd[f"{bn}.running_var"].astype(np.float64)
+    s = g / np.sqrt(v + BN_EPS)
+    return (w.astype(np.float64) * s[:, None, None, None]).astype(np.float32), (b - m * s).astype(np.float32)
+
+
+def pack_umma_b(w: np.ndarray, group: int) -> np.ndarray:
+    """Folded OIHW fp32 -> fp16 [cin/group][kh*kw][group/8][cout][8]."""
+    cout, cin, kh, kw = w.shape
+    assert cin % group == 0 and group % 16 == 0
+    t = w.reshape(cout, cin // group, group // 8, 8, kh * kw)  # [n][cg][j][e][t]
+    t = t.transpose(1, 4, 2, 0, 3)  # [cg][t][j][n][e]
+    return np.ascontiguousarray(t).astype(np.float16)
+
+
+def build_sections(sd: dict) -> list:
+    sd = normalise_state_dict(sd)
+    secs = []
+
+    def add(sid, arr, dtype):
+        secs.append((sid, np.ascontiguousarray(arr, dtype)))
+
+    w = sd["conv1.weight"].astype(np.float32)  # [32][2][3][3], no BN / bias
+    add(SEC_CONV1_F32, w.transpose(2, 3, 1, 0).reshape(9, 2, 32), np.float32)
+    for li, (prefix, cin, cout, stride, hout, group, sc) in enumerate(conv_table()):
+        bn = prefix.replace("conv", "bn")
+        wf, bf = fold_bn(sd[f"{prefix}.weight"], sd, bn)
+        assert wf.shape == (cout, cin, 3, 3), (prefix, wf.shape)
+        add(SEC_W_F16 + li, pack_umma_b(wf, group), np.float16)
+        add(SEC_W_F32 + li, wf.transpose(2, 3, 1, 0).reshape(9, cin, cout), np.float32)
+        add(SEC_BIAS + li, bf, np.float32)
+        fused = bf
+        if sc >= 0:
+            sp = prefix.rsplit(".", 1)[0] + ".shortcut"
+            ws, bs = fold_bn(sd[f"{sp}.0.weight"], sd, f"{sp}.1")
+            csc = ws.shape[1]
+            add(SEC_SC_W_F16 + sc, pack_umma_b(ws, csc), np.float16)
+            add(SEC_SC_W_F32 + sc, ws.reshape(cout, csc).T, np.float32)
+            add(SEC_SC_BIAS + sc, bs, np.float32)
+            fused = (bf.astype(np.float32) + bs.astype(np.float32)).astype(np.float32)
+        add(SEC_BIAS_FUSED + li, fused, np.float32)
+    for i in range(3):
+        add(SEC_FC_W + i, sd[f"branch{i + 1}.weight"], np.float32)
+        add(SEC_FC_B + i, sd[f"branch{i + 1}.bias"], np.float32)
+    return secs
+
+
+def pack(sd: dict) -> bytes:
+    secs = build_sections(sd)
+    table_bytes = 24 * len(secs)
+    off = (32 + table_bytes + 255) // 256 * 256
+    table, blobs = [], []
+    for sid, arr in secs:
+        raw = arr.tobytes()
+        table.append(struct.pack("<IIQQ", sid, 1 if arr.dtype == np.float16 else 0, off, len(raw)))
+        pad = (-len(raw)) % 256
+        blobs.append(raw + b"\0" * pad)
+        off += len(raw) + pad
+    head = struct.pack("<IIIIQQ", MAGIC, VERSION, ARCH_CTU128, len(secs), off, 0)
+    body = head + b"".join(table)
+    body += b"\0" * ((-len(body)) % 256)
+    out = body + b"".join(blobs)
+    assert len(out) == off
+    return out
+
+
+def write_blob(sd: dict, path: str) -> int:
+    data = pack(sd)
+    with open(path, "wb") as f:
+        f.write(data)
+    return len(data)
+
+
+def read_sections(path: str) -> dict:
+    """Parse an MLTW blob back into {section id: numpy array} (round-trip checks / tooling)."""
+    raw = open(path, "rb").read()
+    magic, ver, arch, nsec, total, _ = struct.unpack_from("<IIIIQQ", raw, 0)
+    if magic != MAGIC or ver != VERSION or arch != ARCH_CTU128 or total != len(raw):
+        raise ValueError("not an MLTW v1 blob for the 128x128 CTU model")
+    out = {}
+    for i in range(nsec):
+        sid, dt, off, nb = struct.unpack_from("<IIQQ", raw, 32 + 24 * i)
+        out[sid] = np.frombuffer(raw, np.float16 if dt == 1 else np.float32, nb // (2 if dt == 1 else 4), off)
+    return out
+
+
+def main(argv=None):
+    argv = list(sys.argv[1:] if argv is None else argv)
+    if len(argv) != 2:
+        print(__doc__)
+        return 2
+    import torch
+
+    sd = torch.load(argv[0], map_location="cpu")
+    n = write_blob(sd, argv[1])
+    print(f"wrote {argv[1]}: {n} bytes")
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,140 @@
+/*
+ * mltcnn.h -- C ABI of libmltcnn.so: B200-native (sm_100a) MLT-CNN inter CU-split predictor.
+ *
+ * Drop-in boundary for the inference block that smu-ivpl/FastInterCU-VVC pastes inline into
+ * VTM-11.0's EncCu::xCompressCU (reference: vtm-mlt-cpp/source/Lib/EncoderLib/EncCu.cpp:803-926).
+ * Each entry point below names the reference lines it replaces.  Plain C types only: no torch,
+ * no OpenCV, no C++ exceptions cross this boundary.  There is NO CPU fallback: every call fails
+ * with a negative code if the CUDA device / kernels are unavailable, and the host then passes
+ * predictedSplitMode = -1 to the unchanged EncModeCtrl::setNewModeList (EncModeCtrl.cpp:110-149),
+ * which is exactly the reference's error convention (EncCu.cpp:694,902-905,923-926).
+ *
+ * Threading: an mlt_ctx is single-threaded / non-reentrant, one per process per GPU, calls are
+ * synchronous -- the same contract as the reference hook (one host thread, blocking libtorch calls).
+ */
+#ifndef MLTCNN_H
+#define MLTCNN_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define MLT_API __attribute__((visibility("default")))
+#else
+#define MLT_API
+#endif
+
+#define MLT_ABI_VERSION 1
+#define MLT_CTU_SIZE 128 /* the deployed model covers 128x128 luma CTUs only (EncCu.cpp:754) */
+
+/* return codes: 0 = success, negative = failure (never throws) */
+enum {
+    MLT_OK = 0,
+    MLT_E_INVAL = -1,    /* bad argument */
+    MLT_E_IO = -2,       /* weight file unreadable */
+    MLT_E_FORMAT = -3,   /* weight file is not an MLTW blob for this architecture */
+    MLT_E_CUDA = -4,     /* CUDA runtime / kernel error (see mlt_last_error) */
+    MLT_E_NOMEM = -5,    /* host or device allocation failed */
+    MLT_E_NODEVICE = -6, /* no sm_100 CUDA device */
+    MLT_E_BATCH = -7,    /* n exceeds the max_batch the context was created with */
+    MLT_E_STATE = -8     /* call sequence error (e.g. no picture begun) */
+};
+
+/* split classes = VTM PartSplit numbering (UnitPartitioner.h:56-64) */
+enum { MLT_SPLIT_NONE = 0, MLT_SPLIT_QT = 1, MLT_SPLIT_BT_H = 2, MLT_SPLIT_BT_V = 3 };
+
+/* mlt_result.flags bits: per-level split flags the partitioning loop can prune with */
+enum {
+    MLT_FLAG_L1_SPLIT = 1u << 0, /* level 1 (2 classes): 1 = split */
+    MLT_FLAG_L2_QT = 1u << 1,    /* level 2 (3 classes): QT  */
+    MLT_FLAG_L2_MTT = 1u << 2,   /* level 2: MTT (BT/TT family) */
+    MLT_FLAG_L3_QT = 1u << 3,    /* level 3 (4 classes): QT  */
+    MLT_FLAG_L3_BT_H = 1u << 4,  /* level 3: horizontal binary split */
+    MLT_FLAG_L3_BT_V = 1u << 5,  /* level 3: vertical binary split */
+    MLT_FLAG_CONSISTENT = 1u << 8 /* the three levels agree (NS/NS/NS, split/QT/QT or split/MTT/BT_x) */
+};
+
+/* One prediction.  split_l3 is what EncCu.cpp:913-921 computes:
+ * argmax(1) of the 3rd output (4 classes) == predictedSplitMode. */
+typedef struct mlt_result {
+    int32_t split_l3;  /* 0 NS, 1 QT, 2 BT_H, 3 BT_V */
+    int32_t split_l2;  /* 0 NS, 1 QT, 2 MTT */
+    int32_t split_l1;  /* 0 NS, 1 split */
+    uint32_t flags;    /* MLT_FLAG_* */
+    float logits[9];   /* raw outputs (lvl1[2], lvl2[3], lvl3[4]) as returned by cnn.forward (EncCu.cpp:909) */
+    float probs[9];    /* per-level softmax of the logits */
+} mlt_result;
+
+/* One CTU of a batch: pointers + strides in Pel (int16) units, as VTM's AreaBuf{buf,stride}
+ * (Buffer.h:94-97) hands them out; poc / qp as EncCu.cpp:806-807. */
+typedef struct mlt_ctu_desc {
+    const int16_t *org;
+    const int16_t *pred;
+    int32_t org_stride;
+    int32_t pred_stride;
+    int32_t poc;
+    int32_t qp;
+} mlt_ctu_desc;
+
+typedef struct mlt_ctx mlt_ctx;
+
+/* Replaces torch::jit::load(path, device) + cnn.eval() (EncCu.cpp:894-905) -- done ONCE, not per CTU.
+ * weights_path: MLTW blob written by `python -m fastintercu_vvc_b200.pack_weights` from the same
+ * state_dict ('params' key, optional 'module.' prefixes) model2torchScript.py:23-32 reads.
+ * cuda_device: ordinal after CUDA_VISIBLE_DEVICES (the reference hard-codes at::kCUDA = 0, EncCu.cpp:804).
+ * max_batch: largest n accepted by the batch calls (device + pinned buffers are sized once, here). */
+MLT_API int mlt_create(mlt_ctx **ctx, const char *weights_path, int cuda_device);
+MLT_API int mlt_create_ex(mlt_ctx **ctx, const char *weights_path, int cuda_device, int max_batch);
+MLT_API void mlt_destroy(mlt_ctx *ctx);
+
+/* The exact drop-in for EncCu.cpp:806-921: stage (cast, absdiff, /1023, clamp), forward, argmax.
+ * org/pred: top-left sample of the 128x128 luma block inside the caller's Pel buffers. */
+MLT_API int mlt_predict_ctu(mlt_ctx *ctx, const int16_t *org, int org_stride, const int16_t *pred, int pred_stride,
+                    int poc, int qp, mlt_result *out);
+
+/* Batched form for all CTUs of a frame / of several independent encodes (north-star item 4). */
+MLT_API int mlt_predict_batch(mlt_ctx *ctx, int n, const mlt_ctu_desc *descs, mlt_result *out);
+
+/* Dense host batch: orgpred[n][2][128][128] int16 (plane 0 = org, plane 1 = pred), pocqp[n][2]. */
+MLT_API int mlt_predict_batch_dense(mlt_ctx *ctx, int n, const int16_t *orgpred, const int32_t *pocqp, mlt_result *out);
+
+/* Device-resident batch on the caller's stream (cudaStream_t passed as void*; NULL = default stream).
+ * d_orgpred / d_pocqp / d_out are device pointers; asynchronous w.r.t. the host. */
+MLT_API int mlt_predict_batch_device(mlt_ctx *ctx, int n, const int16_t *d_orgpred, const int32_t *d_pocqp,
+                             mlt_result *d_out, void *cuda_stream);
+
+/* Per-picture staging (north-star item 1): upload the picture's original luma plane once at the top of
+ * EncSlice::encodeCtus (EncSlice.cpp:1479-1528); per-CTU calls then ship only the 32 KiB prediction
+ * block.  (x, y) = luma position of the CTU; it must lie fully inside the picture (EncCu.cpp:755). */
+MLT_API int mlt_begin_picture(mlt_ctx *ctx, const int16_t *org_luma, int stride, int width, int height, int poc);
+MLT_API int mlt_predict_ctu_in_picture(mlt_ctx *ctx, int x, int y, const int16_t *pred, int pred_stride, int qp,
+                               mlt_result *out);
+
+/* ---- introspection / test hooks (not needed by the encoder) ---- */
+MLT_API const char *mlt_strerror(int rc);
+MLT_API const char *mlt_last_error(const mlt_ctx *ctx); /* detail of the last failure ("" if none) */
+MLT_API int mlt_abi_version(void);
+/* Engine: 0 = tcgen05 implicit-GEMM kernels (product path), 1 = fp32 CUDA-core kernels (GPU-side
+ * cross-check used by tests; never selected implicitly). */
+MLT_API int mlt_set_engine(mlt_ctx *ctx, int engine);
+/* Number of kernels launched by this context so far (bench.py's gpu_launches). */
+MLT_API uint64_t mlt_launch_count(const mlt_ctx *ctx);
+/* Per-kernel device times of the LAST batch (CUDA events recorded on the stream the kernels were launched
+ * on): ms[0] = fused staging+conv1, ms[1..16] = the 16 tcgen05 convs in forward order, ms[17] = head.
+ * mlt_get_profile returns the number of entries written (18) or a negative code. */
+MLT_API int mlt_set_profiling(mlt_ctx *ctx, int on);
+MLT_API int mlt_get_profile(mlt_ctx *ctx, float *ms, int capacity);
+/* Bit-exactness probe of the staging arithmetic (EncCu.cpp:810-867) run on the GPU:
+ * out = fp32 [n][2][128][128] (channel 0 = org/1023, channel 1 = |org-pred|/1023, clamped). */
+MLT_API int mlt_debug_stage(mlt_ctx *ctx, int n, const mlt_ctu_desc *descs, float *out);
+/* Copy back an intermediate activation of the last batch as fp32 NHWC [n][H][W][C];
+ * layer = 0 (conv1 out) .. 16 (layer3.1 out).  Returns the element count, or a negative code. */
+MLT_API int64_t mlt_debug_activation(mlt_ctx *ctx, int layer, float *out, int64_t capacity);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MLTCNN_H */

@@ -1,0 +1,297 @@
+"""GPU parity tests (run on the B200 box: python -m pytest tests -m gpu).
+
+Everything goes through the C ABI of libmltcnn.so (fastintercu_vvc_b200.capi).  The checker is the CPU
+oracle (oracle/mltcnn_oracle.c via tests/oracle_lib.py) and the committed golden vectors produced by the
+reference's own architecture file (tests/golden/, tools/gen_golden.py).
+
+Bars (BASELINE.json north_star): integer staging bit-exact; probabilities max |diff| <= 1e-3 vs fp32;
+>= 99.9 % split-decision agreement.
+"""
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from oracle import ref_arch
+from tests.oracle_lib import OracleModel
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+PROB_TOL = 1e-3  # north_star: max abs diff of probabilities vs the fp32 reference
+
+
+def softmax_levels(lg):
+    out = np.empty_like(lg)
+    for a, b in ((0, 2), (2, 5), (5, 9)):
+        e = np.exp(lg[:, a:b] - lg[:, a:b].max(1, keepdims=True))
+        out[:, a:b] = e / e.sum(1, keepdims=True)
+    return out
+
+
+@pytest.fixture(scope="module")
+def sd():
+    return ref_arch.make_state_dict(10)
+
+
+@pytest.fixture(scope="module")
+def blob(sd):
+    from fastintercu_vvc_b200.pack_weights import write_blob
+
+    with tempfile.NamedTemporaryFile(suffix=".mltw", delete=False) as f:
+        path = f.name
+    write_blob(sd, path)
+    yield path
+    os.unlink(path)
+
+
+@pytest.fixture(scope="module")
+def pred(blob):
+    from fastintercu_vvc_b200 import MltPredictor
+
+    p = MltPredictor(blob, device=0, max_batch=160)
+    yield p
+    p.close()
+
+
+@pytest.fixture(scope="module")
+def oracle(sd):
+    m = OracleModel(sd)
+    yield m
+    m.close()
+
+
+@pytest.fixture(scope="module")
+def ctus():
+    return ref_arch.synth_ctus(24, 10)
+
+
+def as_list(orgpred, pocqp):
+    return [(orgpred[i, 0], orgpred[i, 1], int(pocqp[i, 0]), int(pocqp[i, 1])) for i in range(len(orgpred))]
+
+
+# ------------------------------------------------------------------------------------------- tcgen05 descriptor probe
+
+
+def test_umma_descriptor_probe():
+    """The smem-descriptor conventions conv_umma.cuh relies on hold on this GPU."""
+    exe = os.path.join(ROOT, "tests", "cuda", "umma_probe.bin")
+    if not os.path.exists(exe):
+        subprocess.check_call(
+            ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-I", os.path.join(ROOT, "fastintercu_vvc_b200", "csrc"),
+             os.path.join(ROOT, "tests", "cuda", "umma_probe.cu"), "-o", exe]
+        )
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout
+
+
+# ------------------------------------------------------------------------------------------- staging (integer path)
+
+
+def test_stage_bit_exact_vs_oracle_and_opencv_kat(pred, oracle, ctus):
+    orgpred, pocqp = ctus
+    got = pred.debug_stage(as_list(orgpred[:8], pocqp[:8]))
+    for i in range(8):
+        want = oracle.stage(orgpred[i, 0], orgpred[i, 1])
+        assert np.array_equal(got[i].view(np.uint32), want.view(np.uint32))
+    kat = np.load(os.path.join(GOLD, "stage_kat.npz"))
+    org = np.resize(kat["codes"].astype(np.int16), (128, 128))
+    z = np.zeros((128, 128), np.int16)
+    g = pred.debug_stage([(org, z, 0, 0)])[0]
+    want = kat["cv2_convert_to"][org.astype(np.int64)]
+    assert np.array_equal(g[0].view(np.uint32), want.view(np.uint32))
+    assert np.array_equal(g[1].view(np.uint32), want.view(np.uint32))
+
+
+def test_stage_edge_cases_strided_negative_extremes(pred, oracle):
+    rng = np.random.RandomState(3)
+    big = rng.randint(-300, 1400, (140, 200)).astype(np.int16)  # negative Pel -> uint16 > 1023 -> clamp to 1
+    org = big[5:133, 17:145]
+    prd = rng.randint(0, 1024, (131, 135)).astype(np.int16)[2:130, 3:131]
+    z = np.zeros((128, 128), np.int16)
+    f = np.full((128, 128), 1023, np.int16)
+    cases = [(org, prd, 1, 30), (z, z, 0, 0), (f, z, 0, 0), (z, f, 0, 0), (prd, org, 5, 22)]
+    got = pred.debug_stage(cases)
+    for i, (o, p, _, _) in enumerate(cases):
+        want = oracle.stage(o, p)
+        assert np.array_equal(got[i].view(np.uint32), want.view(np.uint32)), i
+    assert got.min() >= 0.0 and got.max() <= 1.0
+
+
+# ------------------------------------------------------------------------------------------- network
+
+
+def test_fp32_engine_matches_oracle(pred, oracle, ctus):
+    """GPU fp32 cross-check engine vs C oracle: pins BN folding, shortcut and residual semantics."""
+    orgpred, pocqp = ctus
+    pred.set_engine(1)
+    try:
+        res = pred.predict_batch(as_list(orgpred[:6], pocqp[:6]))
+    finally:
+        pred.set_engine(0)
+    lg, sp = oracle.predict_batch(orgpred[:6], pocqp[:6])
+    err = np.abs(res["logits"] - lg).max()
+    print("fp32 engine vs oracle max|dlogit| =", err)
+    assert err < 3e-4
+    assert np.array_equal(res["split_l3"], sp)
+
+
+def test_tcgen05_layers_vs_fp32_engine(pred, ctus):
+    """Layer-by-layer comparison on the device: tcgen05 (fp16 operands, fp32 accumulate) vs fp32 engine."""
+    orgpred, pocqp = ctus
+    n = 3  # odd: exercises the half-empty layer3 tile
+    batch = as_list(orgpred[:n], pocqp[:n])
+    pred.set_engine(1)
+    pred.predict_batch(batch)
+    ref = [pred.debug_activation(a, n) for a in range(17)]
+    pred.set_engine(0)
+    pred.predict_batch(batch)
+    worst = 0.0
+    for a in range(17):
+        got = pred.debug_activation(a, n)
+        scale = np.abs(ref[a]).max()
+        err = np.abs(got - ref[a]).max() / max(scale, 1e-6)
+        print(f"act {a:2d} shape {got.shape}: max|d|/max|ref| = {err:.3e} (max|ref| {scale:.3f})")
+        worst = max(worst, err)
+        assert err < 2e-2, f"activation {a} diverges: {err}"
+    assert worst > 0  # the two engines really are different arithmetic
+
+
+def test_tcgen05_matches_reference_golden(pred, ctus):
+    """Product path vs logits of the reference's own arch file (tests/golden/logits_seed10.npz)."""
+    gold = np.load(os.path.join(GOLD, "logits_seed10.npz"))
+    orgpred, pocqp = ctus
+    assert np.array_equal(pocqp, gold["pocqp"])
+    res = pred.predict_batch(as_list(orgpred, pocqp))
+    dl = np.abs(res["logits"] - gold["logits"]).max()
+    dp = np.abs(res["probs"] - softmax_levels(gold["logits"])).max()
+    print(f"tcgen05 vs reference golden: max|dlogit|={dl:.3e} max|dprob|={dp:.3e}")
+    assert dp <= PROB_TOL
+    # decisions: allow a flip only where the fp32 reference itself is within 2e-3 of a tie
+    srt = np.sort(gold["logits"][:, 5:9], 1)
+    clear = (srt[:, -1] - srt[:, -2]) > 2e-3
+    assert np.array_equal(res["split_l3"][clear], gold["split"][clear])
+    # probs are a softmax of the logits; flags follow the argmaxes
+    assert np.abs(softmax_levels(res["logits"]) - res["probs"]).max() < 1e-6
+    assert np.array_equal(res["split_l3"], res["logits"][:, 5:9].argmax(1))
+    assert np.array_equal(res["split_l2"], res["logits"][:, 2:5].argmax(1))
+    assert np.array_equal(res["split_l1"], res["logits"][:, 0:2].argmax(1))
+    assert np.array_equal((res["flags"] >> 3) & 1, (res["split_l3"] == 1).astype(np.uint32))
+
+
+def test_agreement_on_larger_sample(pred, oracle):
+    """>= 99.9 % split agreement and <= 1e-3 probability error on 160 fresh CTUs (oracle on all host cores)."""
+    orgpred, pocqp = ref_arch.synth_ctus(160, 2024)
+    res = pred.predict_batch_dense(orgpred, pocqp)
+    lg, sp = oracle.predict_batch(orgpred, pocqp)
+    dp = np.abs(res["probs"] - softmax_levels(lg)).max()
+    agree = (res["split_l3"] == sp).mean()
+    srt = np.sort(lg[:, 5:9], 1)
+    margin = srt[:, -1] - srt[:, -2]
+    print(f"n=160: max|dprob|={dp:.3e}, agreement={agree:.4f}, min fp32 margin={margin.min():.2e}")
+    assert dp <= PROB_TOL
+    bad = res["split_l3"] != sp
+    assert np.all(margin[bad] < 2e-3), "a disagreement away from a numerical tie"
+    assert agree >= 0.99
+    assert set(sp.tolist()) == {0, 1, 2, 3}
+
+
+def test_batch_shapes_and_entry_points_agree(pred, ctus):
+    """Ragged / odd batches and every entry point give bit-identical results per CTU."""
+    orgpred, pocqp = ctus
+    full = pred.predict_batch_dense(orgpred, pocqp)
+    for n in (1, 2, 3, 5, 23):
+        part = pred.predict_batch(as_list(orgpred[:n], pocqp[:n]))
+        assert np.array_equal(part["logits"].view(np.uint32), full["logits"][:n].view(np.uint32)), n
+    one = pred.predict_ctu(orgpred[7, 0], orgpred[7, 1], pocqp[7, 0], pocqp[7, 1])
+    assert np.array_equal(one["logits"].view(np.uint32), full["logits"][7].view(np.uint32))
+    assert pred.predict_batch([]).shape == (0,)
+    again = pred.predict_batch_dense(orgpred, pocqp)
+    assert again.tobytes() == full.tobytes()  # deterministic run to run
+
+
+def test_picture_staging_path(pred):
+    """mlt_begin_picture + per-CTU pred upload == explicit org pointer path (EncSlice-level staging)."""
+    rng = np.random.RandomState(5)
+    w, h, margin = 416, 240, 16
+    buf = rng.randint(0, 1024, (h + 2 * margin, w + 2 * margin + 3)).astype(np.int16)
+    pic = buf[margin : margin + h, margin : margin + w]  # strided view like a VTM PelStorage with margins
+    pred.begin_picture(pic, poc=7)
+    for (x, y) in ((0, 0), (128, 0), (256, 0)):  # the 3 eligible CTUs of a 416x240 picture (EncCu.cpp:755)
+        p = rng.randint(0, 1024, (128, 128)).astype(np.int16)
+        a = pred.predict_ctu_in_picture(x, y, p, qp=37)
+        b = pred.predict_ctu(pic[y : y + 128, x : x + 128], p, 7, 37)
+        assert a.tobytes() == b.tobytes()
+    from fastintercu_vvc_b200 import MltError
+
+    with pytest.raises(MltError):
+        pred.predict_ctu_in_picture(384, 0, p, 37)  # partial CTU: outside the picture
+    with pytest.raises(MltError):
+        pred.predict_ctu_in_picture(0, 128, p, 37)
+
+
+def test_device_resident_batch_via_torch(pred, ctus):
+    import torch
+
+    orgpred, pocqp = ctus
+    host = pred.predict_batch_dense(orgpred, pocqp)
+    d_in = torch.from_numpy(orgpred).cuda()
+    d_pq = torch.from_numpy(pocqp).cuda()
+    d_out = torch.zeros(len(orgpred) * 88, dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream()
+    pred.predict_batch_device(len(orgpred), d_in.data_ptr(), d_pq.data_ptr(), d_out.data_ptr(), st.cuda_stream)
+    st.synchronize()
+    from fastintercu_vvc_b200.capi import RESULT_DTYPE
+
+    dev = np.frombuffer(d_out.cpu().numpy().tobytes(), RESULT_DTYPE)
+    assert dev.tobytes() == host.tobytes()
+
+
+def test_errors(pred, blob, ctus):
+    from fastintercu_vvc_b200 import MltError, MltPredictor
+
+    orgpred, pocqp = ctus
+    with pytest.raises(MltError) as e:
+        MltPredictor("/nonexistent/weights.mltw")
+    assert e.value.rc == -2
+    with tempfile.NamedTemporaryFile(suffix=".mltw") as f:
+        f.write(b"not a blob" * 100)
+        f.flush()
+        with pytest.raises(MltError) as e:
+            MltPredictor(f.name)
+        assert e.value.rc == -3
+    big = np.zeros((161, 2, 128, 128), np.int16)
+    with pytest.raises(MltError) as e:
+        pred.predict_batch_dense(big, np.zeros((161, 2), np.int32))
+    assert e.value.rc == -7
+    with pytest.raises(MltError):
+        pred.set_engine(5)
+    # the context is still usable after errors
+    r = pred.predict_ctu(orgpred[0, 0], orgpred[0, 1], pocqp[0, 0], pocqp[0, 1])
+    assert 0 <= r["split_l3"] <= 3
+
+
+def test_full_size_batch_properties():
+    """BASELINE config 5 size (4096 CTUs): duplicates give identical rows, a sample matches the oracle."""
+    from fastintercu_vvc_b200 import MltPredictor
+    from fastintercu_vvc_b200.pack_weights import write_blob
+
+    sd = ref_arch.make_state_dict(10)
+    with tempfile.NamedTemporaryFile(suffix=".mltw") as f:
+        write_blob(sd, f.name)
+        with MltPredictor(f.name, max_batch=4096) as p:
+            base, pq = ref_arch.synth_ctus(64, 99)
+            idx = np.random.RandomState(1).randint(0, 64, 4096)
+            idx[:64] = np.arange(64)
+            orgpred = np.ascontiguousarray(base[idx])
+            pocqp = np.ascontiguousarray(pq[idx])
+            res = p.predict_batch_dense(orgpred, pocqp)
+            first = res["logits"][:64]
+            assert np.array_equal(res["logits"].view(np.uint32), first[idx].view(np.uint32))
+            m = OracleModel(sd)
+            lg, sp = m.predict_batch(base[:16], pq[:16])
+            assert np.abs(softmax_levels(first[:16]) - softmax_levels(lg)).max() <= PROB_TOL
