@@ -17,7 +17,7 @@ namespace {
 constexpr uint32_t MLTW_MAGIC = 0x57544C4Du;
 enum : uint32_t {
     SEC_CONV1_F32 = 0x001, SEC_W_F16 = 0x100, SEC_BIAS_FUSED = 0x200, SEC_W_F32 = 0x300, SEC_BIAS = 0x400,
-    SEC_SC_W_F16 = 0x500, SEC_SC_W_F32 = 0x600, SEC_SC_BIAS = 0x700, SEC_FC_W = 0x800, SEC_FC_B = 0x900
+    SEC_SC_W_F16 = 0x500, SEC_SC_W_F32 = 0x600, SEC_SC_BIAS = 0x700, SEC_FC_W = 0x800, SEC_FC_B = 0x900, SEC_BIAS_MMA = 0xA00
 };
 
 constexpr int NCONV = 16, NACT = 17, CTU = MLT_CTU_SIZE;
@@ -44,6 +44,12 @@ inline size_t act_elems(int a)
     act_shape(a, h, c);
     return (size_t)h * h * c;
 }
+inline size_t act_elems_haloed(int a) // fp16 product-path layout: [h+2][h+2][c] per image (conv_umma.cuh)
+{
+    int h, c;
+    act_shape(a, h, c);
+    return (size_t)(h + 2) * (h + 2) * c;
+}
 
 struct Section { const uint8_t *dev = nullptr; size_t bytes = 0; };
 
@@ -69,6 +75,8 @@ struct mlt_ctx {
     bool pic_valid = false;
     int last_n = 0;
     uint64_t launches = 0;
+    int trace_layer = -1;
+    long long *d_trace = nullptr;
     bool profiling = false;
     cudaEvent_t prof_ev[NCONV + 3] = {}; // boundaries of: stage+conv1, 16 convs, head
     cudaStream_t prof_stream = nullptr;
@@ -132,7 +140,8 @@ int load_blob(mlt_ctx *c, const char *path)
     for (int li = 0; li < NCONV && ok; li++) {
         const LayerDesc &L = kLayers[li];
         ok = need(SEC_W_F16 + li, (size_t)9 * L.cin * L.cout * 2) && need(SEC_W_F32 + li, (size_t)9 * L.cin * L.cout * 4) &&
-             need(SEC_BIAS + li, (size_t)L.cout * 4) && need(SEC_BIAS_FUSED + li, (size_t)L.cout * 4);
+             need(SEC_BIAS + li, (size_t)L.cout * 4) && need(SEC_BIAS_FUSED + li, (size_t)L.cout * 4) &&
+             need(SEC_BIAS_MMA + li, (size_t)L.cout * 32);
         if (ok && L.sc >= 0) {
             const int csc = kLayers[li - 1].cin;
             ok = need(SEC_SC_W_F16 + L.sc, (size_t)csc * L.cout * 2) && need(SEC_SC_W_F32 + L.sc, (size_t)csc * L.cout * 4) &&
@@ -204,8 +213,14 @@ int run_network(mlt_ctx *c, const CtuDev *ctus, int n, mlt_result *out, cudaStre
                 if (L.sc >= 0) { sc_in = x_block; sc_w = secp<__half>(c, SEC_SC_W_F16 + L.sc); }
                 else res = x_block;
             }
-            CU(launch_conv_umma(li, in, secp<__half>(c, SEC_W_F16 + li), secp<float>(c, SEC_BIAS_FUSED + li), sc_in, sc_w, res,
-                                c->act_h[li + 1], n, 1, c->num_sms, s));
+            long long *trace = nullptr;
+            if (c->trace_layer == li) { // debug: MLT_TRACE_LAYER=<li> MLT_TRACE_FILE=<path>
+                if (!c->d_trace) CU(cudaMalloc(&c->d_trace, 4 * 64 * 4 * sizeof(long long)));
+                CU(cudaMemsetAsync(c->d_trace, 0, 4 * 64 * 4 * sizeof(long long), s));
+                trace = c->d_trace;
+            }
+            CU(launch_conv_umma(li, in, secp<__half>(c, SEC_W_F16 + li), secp<__half>(c, SEC_BIAS_MMA + li), sc_in, sc_w, res,
+                                c->act_h[li + 1], n, 1, c->num_sms, s, trace));
             c->launches++;
             if (prof) CU(cudaEventRecord(c->prof_ev[ev++], s));
         }
@@ -242,6 +257,18 @@ int run_network(mlt_ctx *c, const CtuDev *ctus, int n, mlt_result *out, cudaStre
         c->launches++;
     }
     c->last_n = n;
+    if (c->trace_layer >= 0 && c->d_trace && getenv("MLT_TRACE_FILE")) {
+        std::vector<long long> h(4 * 64 * 4);
+        CU(cudaStreamSynchronize(s));
+        CU(cudaMemcpy(h.data(), c->d_trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        if (FILE *f = fopen(getenv("MLT_TRACE_FILE"), "w")) {
+            fprintf(f, "# layer %d n %d: role tile t0 t1 t2 t3 (clock64 of CTA 0; role 0 producer, 1 mma, 2/3 epilogue groups)\n", c->trace_layer, n);
+            for (int r = 0; r < 4; r++)
+                for (int t = 0; t < 64; t++)
+                    fprintf(f, "%d %d %lld %lld %lld %lld\n", r, t, h[(r * 64 + t) * 4], h[(r * 64 + t) * 4 + 1], h[(r * 64 + t) * 4 + 2], h[(r * 64 + t) * 4 + 3]);
+            fclose(f);
+        }
+    }
     return MLT_OK;
 }
 
@@ -321,7 +348,7 @@ void mlt_destroy(mlt_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (int a = 0; a < NACT; a++) { cudaFree(c->act_h[a]); cudaFree(c->act_f[a]); }
     cudaFree(c->scratch_f); cudaFree(c->d_blob); cudaFree(c->d_in); cudaFree(c->d_ctus); cudaFree(c->d_out);
-    cudaFree(c->d_dbg); cudaFree(c->d_pic);
+    cudaFree(c->d_dbg); cudaFree(c->d_pic); cudaFree(c->d_trace);
     cudaFreeHost(c->h_in); cudaFreeHost(c->h_ctus); cudaFreeHost(c->h_out);
     for (cudaEvent_t e : c->prof_ev) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -344,6 +371,7 @@ int mlt_create_ex(mlt_ctx **out, const char *weights_path, int cuda_device, int 
     c->device = cuda_device;
     c->max_batch = max_batch;
     c->num_sms = prop.multiProcessorCount;
+    if (const char *tl = getenv("MLT_TRACE_LAYER")) c->trace_layer = atoi(tl);
     int rc = MLT_OK;
     auto body = [&]() -> int {
         CU(cudaSetDevice(cuda_device));
@@ -351,7 +379,13 @@ int mlt_create_ex(mlt_ctx **out, const char *weights_path, int cuda_device, int 
         int r = load_blob(c, weights_path);
         if (r) return r;
         CU(conv_umma_init());
-        for (int a = 0; a < NACT; a++) CU(cudaMalloc(&c->act_h[a], act_elems(a) * max_batch * sizeof(__half)));
+        for (int a = 0; a < NACT; a++) {
+            // +1 image: spare for the tile that pairs the last image of an odd batch; halos are zeroed once, here
+            const size_t bytes = act_elems_haloed(a) * ((size_t)max_batch + 1) * sizeof(__half);
+            CU(cudaMalloc(&c->act_h[a], bytes));
+            CU(cudaMemsetAsync(c->act_h[a], 0, bytes, c->stream));
+        }
+        CU(cudaStreamSynchronize(c->stream));
         CU(cudaMalloc(&c->d_in, (size_t)max_batch * CTU_IN_ELEMS * sizeof(int16_t)));
         CU(cudaMalloc(&c->d_ctus, (size_t)max_batch * sizeof(CtuDev)));
         CU(cudaMalloc(&c->d_out, (size_t)max_batch * sizeof(mlt_result)));
@@ -541,7 +575,9 @@ int64_t mlt_debug_activation(mlt_ctx *c, int layer, float *out, int64_t capacity
     if (c->engine == 0) {
         rc = ensure_dbg(c, elems * sizeof(float));
         if (rc) return rc;
-        CU(launch_half_to_float(c->act_h[layer], c->d_dbg, elems, s));
+        int h, ch;
+        act_shape(layer, h, ch);
+        CU(launch_unhalo_to_float(c->act_h[layer], c->d_dbg, c->last_n, h, ch, s));
         CU(cudaMemcpyAsync(out, c->d_dbg, elems * sizeof(float), cudaMemcpyDeviceToHost, s));
     } else {
         if (!c->act_f[layer]) return fail(c, MLT_E_STATE, "fp32 engine has not run");

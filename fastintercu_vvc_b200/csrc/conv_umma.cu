@@ -45,13 +45,13 @@ cudaError_t conv_umma_init()
     return cudaSuccess;
 }
 
-cudaError_t launch_conv_umma(int layer, const __half *in, const __half *w, const float *bias, const __half *sc_in,
+cudaError_t launch_conv_umma(int layer, const __half *in, const __half *w, const __half *bias, const __half *sc_in,
                              const __half *sc_w, const __half *res, __half *out, int nimg, int relu, int num_sms,
-                             cudaStream_t s)
+                             cudaStream_t s, long long *trace)
 {
     ConvParams p;
     p.in = in; p.w = w; p.bias = bias; p.sc_in = sc_in; p.sc_w = sc_w; p.res = res; p.out = out;
-    p.nimg = nimg; p.relu = relu;
+    p.nimg = nimg; p.relu = relu; p.trace = trace;
     switch (layer) {
     case 0: return launch_one<L0a>(p, num_sms, s);
     case 1: return launch_one<L0b>(p, num_sms, s);

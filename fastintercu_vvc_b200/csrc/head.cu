@@ -28,10 +28,12 @@ __device__ __forceinline__ void load8<float>(const float *p, float (&f)[8])
     f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
 }
 
-// mean over P pixels of an NHWC [P][C] map -> feat[C]; 256 threads, deterministic
-template <typename T, int P, int C>
+// mean over the H x H pixels of an NHWC map -> feat[C]; 256 threads, deterministic.  The fp16 maps carry a
+// one-pixel zero halo ([H+2][H+2][C]); summing over it is harmless, so the whole buffer is read linearly.
+template <typename T, int H, int C>
 __device__ __forceinline__ void gap(const T *act, float *partial /*[256/(C/8)][C]*/, float *feat)
 {
+    constexpr int HP = sizeof(T) == 2 ? H + 2 : H, P = HP * HP;
     constexpr int CH = C / 8, PH = 256 / CH;
     const int cj = threadIdx.x % CH, pp = threadIdx.x / CH;
     float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -47,7 +49,7 @@ __device__ __forceinline__ void gap(const T *act, float *partial /*[256/(C/8)][C
     for (int c = threadIdx.x; c < C; c += 256) {
         float t = 0.0f;
         for (int k = 0; k < PH; k++) t += partial[k * C + c];
-        feat[c] = t * (1.0f / (float)P);
+        feat[c] = t * (1.0f / (float)(H * H));
     }
     __syncthreads();
 }
@@ -59,9 +61,10 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadParams p)
     __shared__ float feat[64 + 128 + 256];
     __shared__ float logits[9];
     const int n = blockIdx.x;
-    gap<T, 32 * 32, 64>(static_cast<const T *>(p.act[0]) + (size_t)n * 32 * 32 * 64, partial, feat);
-    gap<T, 16 * 16, 128>(static_cast<const T *>(p.act[1]) + (size_t)n * 16 * 16 * 128, partial, feat + 64);
-    gap<T, 8 * 8, 256>(static_cast<const T *>(p.act[2]) + (size_t)n * 8 * 8 * 256, partial, feat + 192);
+    constexpr int E = sizeof(T) == 2 ? 2 : 0; // halo
+    gap<T, 32, 64>(static_cast<const T *>(p.act[0]) + (size_t)n * (32 + E) * (32 + E) * 64, partial, feat);
+    gap<T, 16, 128>(static_cast<const T *>(p.act[1]) + (size_t)n * (16 + E) * (16 + E) * 128, partial, feat + 64);
+    gap<T, 8, 256>(static_cast<const T *>(p.act[2]) + (size_t)n * (8 + E) * (8 + E) * 256, partial, feat + 192);
 
     const float poc = (float)p.ctus[n].poc, qp = (float)p.ctus[n].qp; // raw ints promoted by torch.cat (arch.py:274-275)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -40,14 +40,14 @@ cudaError_t launch_conv_simt(const float *in, const float *w /*[k*k][cin][cout]*
 
 // ---- conv_umma.cu : tcgen05 implicit-GEMM engine
 struct ConvParams;
-cudaError_t launch_conv_umma(int layer, const __half *in, const __half *w, const float *bias, const __half *sc_in,
+cudaError_t launch_conv_umma(int layer, const __half *in, const __half *w, const __half *bias, const __half *sc_in,
                              const __half *sc_w, const __half *res, __half *out, int nimg, int relu, int num_sms,
-                             cudaStream_t s);
+                             cudaStream_t s, long long *trace = nullptr);
 cudaError_t conv_umma_init(); // opt in to large dynamic shared memory for every instantiation
 
 // ---- head.cu : global average pools + FC heads + softmax + argmax + flags (arch.py:281-297, EncCu.cpp:913-921)
 struct HeadParams {
-    const void *act[3];   // layer1 / layer2 / layer3 outputs, NHWC (fp16 or fp32)
+    const void *act[3];   // layer1 / layer2 / layer3 outputs: haloed NHWC fp16 (product) or dense NHWC fp32 (cross-check)
     const float *fc_w[3]; // [out][in]
     const float *fc_b[3];
     const CtuDev *ctus;   // poc / qp
@@ -58,6 +58,6 @@ cudaError_t launch_head_h(const HeadParams &p, cudaStream_t s);
 cudaError_t launch_head_f(const HeadParams &p, cudaStream_t s);
 
 // ---- misc
-cudaError_t launch_half_to_float(const __half *in, float *out, size_t n, cudaStream_t s);
+cudaError_t launch_unhalo_to_float(const __half *in, float *out, int nimg, int h, int c, cudaStream_t s);
 
 } // namespace mlt

@@ -9,6 +9,20 @@ namespace mlt {
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One elected lane of a converged warp (elect.sync).  Guarding single-thread issue (tcgen05.mma, bulk copies)
+// with this instead of `lane == 0` keeps the surrounding control flow warp-uniform, so the compiler feeds the
+// uniform-register operands directly instead of wrapping every instruction in a uniformisation loop.
+__device__ __forceinline__ bool elect_one_sync()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {
@@ -50,12 +64,18 @@ __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void *gsrc, 
     const uint32_t nbytes = valid ? 16u : 0u; // src-size 0 => 16 zero bytes are written
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(nbytes) : "memory");
 }
+// arrive on `bar` (without incrementing its pending count) once all prior cp.async of this thread have landed
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t *bar)
+{
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait()
 {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 // make generic-proxy smem writes visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -90,6 +110,13 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_noswz(uint32_t smem_addr, u
     return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
            ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46); // bits 46-47: descriptor version 1 (sm_100)
 }
+// Same descriptor as two 32-bit halves: `hi` is constant per operand layout, `lo` = start address + LBO.
+__host__ __device__ constexpr uint32_t umma_desc_hi(uint32_t sbo) { return ((sbo >> 4) & 0x3FFFu) | (1u << 14); }
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr, uint32_t lbo)
+{
+    return ((smem_addr >> 4) & 0x3FFFu) | (((lbo >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ uint64_t umma_desc_pack(uint32_t lo, uint32_t hi) { return (uint64_t)lo | ((uint64_t)hi << 32); }
 // Instruction descriptor for kind::f16: A,B = fp16 (K-major), D = fp32, M x N tile.
 __host__ __device__ constexpr uint32_t umma_idesc_f16(int m, int n)
 {

@@ -124,7 +124,9 @@ __global__ void __launch_bounds__(256) stage_conv1_kernel(const CtuDev *__restri
         }
     }
 
-    const size_t pix0 = ((size_t)ctu * 128 + (y0 + row)) * 128 + (x0 + sx);
+    // fp16 product path: haloed NHWC [n+1][130][130][32] (conv_umma.cuh); fp32 cross-check path: dense NHWC
+    const size_t pix0 = sizeof(OutT) == 2 ? ((size_t)ctu * 130 + (y0 + row + 1)) * 130 + (x0 + sx + 1)
+                                          : ((size_t)ctu * 128 + (y0 + row)) * 128 + (x0 + sx);
 #pragma unroll
     for (int px = 0; px < 4; px++) {
         OutT *o = out + (pix0 + px) * 32 + half * 16;
@@ -159,15 +161,22 @@ cudaError_t launch_stage_conv1_f(const CtuDev *ctus, int n, const float *w, floa
     return cudaGetLastError();
 }
 
-__global__ void half_to_float_kernel(const __half *__restrict__ in, float *__restrict__ out, size_t n)
+// debug: haloed NHWC fp16 [nimg][h+2][h+2][c] -> dense NHWC fp32 [nimg][h][h][c]
+__global__ void unhalo_to_float_kernel(const __half *__restrict__ in, float *__restrict__ out, int h, int c, size_t n)
 {
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-        out[i] = __half2float(in[i]);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % c);
+        const size_t pix = i / c;
+        const int x = (int)(pix % h), y = (int)((pix / h) % h);
+        const size_t img = pix / ((size_t)h * h);
+        out[i] = __half2float(in[((img * (h + 2) + y + 1) * (h + 2) + x + 1) * c + ch]);
+    }
 }
-cudaError_t launch_half_to_float(const __half *in, float *out, size_t n, cudaStream_t s)
+cudaError_t launch_unhalo_to_float(const __half *in, float *out, int nimg, int h, int c, cudaStream_t s)
 {
+    const size_t n = (size_t)nimg * h * h * c;
     const int blocks = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
-    half_to_float_kernel<<<blocks > 0 ? blocks : 1, 256, 0, s>>>(in, out, n);
+    unhalo_to_float_kernel<<<blocks > 0 ? blocks : 1, 256, 0, s>>>(in, out, h, c, n);
     return cudaGetLastError();
 }
 

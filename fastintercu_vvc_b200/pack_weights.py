@@ -11,6 +11,8 @@ What it does
   * writes the folded 3x3 / 1x1 conv weights as fp16 in the tcgen05 shared-memory operand layout used by
     csrc/conv_umma.cuh: K-major, no-swizzle core matrices, [cin_group][tap][G/8][Cout][8] so that every
     (cin_group, tap) slab is one contiguous bulk copy;
+  * writes each conv's (shortcut-fused) bias as a K=16 fp16 operand (hi/lo split) that one extra MMA adds
+    into the accumulator;
   * writes fp32 copies ([tap][Cin][Cout]) for the fp32 CUDA-core cross-check engine, the fp32 biases, the
     fp32 conv1 ([tap][2][32], consumed by the fused staging+conv1 kernel) and the three FC heads.
 
@@ -37,6 +39,7 @@ SEC_BIAS = 0x400
 SEC_SC_W_F16 = 0x500
 SEC_SC_W_F32 = 0x600
 SEC_SC_BIAS = 0x700
+SEC_BIAS_MMA = 0xA00
 SEC_FC_W = 0x800
 SEC_FC_B = 0x900
 
@@ -92,6 +95,17 @@ def pack_umma_b(w: np.ndarray, group: int) -> np.ndarray:
     return np.ascontiguousarray(t).astype(np.float16)
 
 
+def bias_operand(b: np.ndarray) -> np.ndarray:
+    """fp32 bias [cout] -> fp16 tcgen05 B operand [2][cout][8]: k=0 hi(b), k=1 lo(b) = b - hi(b), rest 0.
+    Multiplied by an A operand whose k=0,1 columns are 1.0 it initialises the accumulator to b (to ~2^-22)."""
+    hi = b.astype(np.float16)
+    lo = (b.astype(np.float32) - hi.astype(np.float32)).astype(np.float16)
+    out = np.zeros((2, b.shape[0], 8), np.float16)
+    out[0, :, 0] = hi
+    out[0, :, 1] = lo
+    return out
+
+
 def build_sections(sd: dict) -> list:
     sd = normalise_state_dict(sd)
     secs = []
@@ -118,6 +132,7 @@ def build_sections(sd: dict) -> list:
             add(SEC_SC_BIAS + sc, bs, np.float32)
             fused = (bf.astype(np.float32) + bs.astype(np.float32)).astype(np.float32)
         add(SEC_BIAS_FUSED + li, fused, np.float32)
+        add(SEC_BIAS_MMA + li, bias_operand(fused), np.float16)
     for i in range(3):
         add(SEC_FC_W + i, sd[f"branch{i + 1}.weight"], np.float32)
         add(SEC_FC_B + i, sd[f"branch{i + 1}.bias"], np.float32)
