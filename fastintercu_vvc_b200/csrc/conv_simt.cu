@@ -1,5 +1,5 @@
 // conv_simt.cu -- fp32 CUDA-core convolution: the GPU-side CROSS-CHECK engine (mlt_set_engine(ctx, 1)).
-// It pins layer semantics (BN folding, shortcut, residual order; arch.py:52-57) to ~1e-5 of the CPU oracle
+// It pins layer semantics (BN folding, shortcut, residual order; arch.py:52-57) to ~1e-5 of the fp32 CPU restatement used by the tests
 // and lets tests compare the tcgen05 engine layer by layer ON the device.  It is never selected implicitly
 // and is not a fallback: the product path is conv_umma.cuh.
 #include "mlt_internal.h"

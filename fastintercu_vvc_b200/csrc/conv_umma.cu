@@ -1,5 +1,7 @@
 // conv_umma.cu -- instantiations + launcher of the tcgen05 implicit-GEMM conv kernel for the 16
 // 3x3 convolutions of the MLT-CNN residual stack (shapes: SURVEY.md section 8a / arch.py:247-254).
+#include <cstdlib>
+
 #include "conv_umma.cuh"
 #include "mlt_internal.h"
 
@@ -52,6 +54,8 @@ cudaError_t launch_conv_umma(int layer, const __half *in, const __half *w, const
     ConvParams p;
     p.in = in; p.w = w; p.bias = bias; p.sc_in = sc_in; p.sc_w = sc_w; p.res = res; p.out = out;
     p.nimg = nimg; p.relu = relu; p.trace = trace;
+    static const int dbg = getenv("MLT_DEBUG_FLAGS") ? atoi(getenv("MLT_DEBUG_FLAGS")) : 0;
+    p.dbg = dbg;
     switch (layer) {
     case 0: return launch_one<L0a>(p, num_sms, s);
     case 1: return launch_one<L0b>(p, num_sms, s);

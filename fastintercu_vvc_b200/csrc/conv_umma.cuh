@@ -39,6 +39,8 @@ struct ConvParams {
     __half *out;         // haloed NHWC, H = HOUT, C = COUT
     int nimg;
     int relu;
+    int dbg;          // debug timing knobs (MLT_DEBUG_FLAGS; results invalid when != 0): 1 = producers skip the copies,
+                      // 2 = epilogue skips global loads/stores, 4 = epilogue skips the TMEM reads too
     long long *trace; // debug (MLT_TRACE_LAYER): [role 0..3][64 tiles][4] clock64() stamps of CTA 0, or nullptr
 };
 
@@ -170,7 +172,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const ConvPar
                 oy = (rem / (C::HOUT / 8)) * 16 + r;
                 ox = (rem % (C::HOUT / 8)) * 8 + c;
             }
-            const bool valid = img < p.nimg;
+            const bool valid = img < p.nimg && !(p.dbg & 2);
             const size_t off = (size_t)img * C::IMG_OUT + (size_t)((oy + 1) * C::HPO + ox + 1) * C::COUT;
             const uint32_t acc = acc_it % C::NACC;
             // identity residual: issue the loads of the first 32 channels BEFORE blocking on the accumulator
@@ -186,7 +188,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const ConvPar
             tc_fence_after();
             if (wq == 0 && lane == 0) trace_stamp(p.trace, 2 + grp, acc_it, 1);
 #pragma unroll 1
-            for (int c0 = 0; c0 < C::COUT; c0 += 32) {
+            for (int c0 = 0; c0 < ((p.dbg & 4) ? 0 : C::COUT); c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + acc * C::COUT + c0, v);
                 uint4 rn[4];
@@ -412,7 +414,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const ConvPar
                     const __half *src = tin + it * C::G;
 #pragma unroll
                     for (int k = 0; k < C::KIT; k++)
-                        if (rel[k] >= 0) cp_async16(abase + dst0 + k * (PXSTEP * 16), src + rel[k], true);
+                        if (rel[k] >= 0 && !(p.dbg & 1)) cp_async16(abase + dst0 + k * (PXSTEP * 16), src + rel[k], true);
                 } else if constexpr (C::CSC > 0) {
                     // shortcut operand: block input sampled at (2*oy, 2*ox), rows in accumulator order
                     const __half *src = p.sc_in + (size_t)img0 * C::IMG_SC + (size_t)((2 * oy0) * C::HPS + 2 * ox0) * C::CSC;

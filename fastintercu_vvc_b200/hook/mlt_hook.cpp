@@ -1,0 +1,104 @@
+// mlt_hook.cpp -- see mlt_hook.h.  Links against libmltcnn.so only.
+#include "mlt_hook.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "../../include/mltcnn.h"
+
+namespace mlt_hook {
+
+bool useCNN(int chType, bool isIntraSlice, int cuw, int cuh, int cux, int cuy, int picWidth, int picHeight)
+{
+    if (chType != 0 || isIntraSlice) return false;          // luma tree of a non-I slice
+    if (cuw != MLT_CTU_SIZE || cuh != MLT_CTU_SIZE) return false; // only the 128x128 model is wired (EncCu.cpp:754)
+    return cux + cuw <= picWidth && cuy + cuh <= picHeight;  // CU entirely inside the picture
+}
+
+SplitPredictor &SplitPredictor::instance()
+{
+    static SplitPredictor p;
+    return p;
+}
+
+SplitPredictor::SplitPredictor()
+{
+    const char *dis = std::getenv("MLT_DISABLE");
+    if (dis && std::strcmp(dis, "0") != 0) return; // anchor run: hook off, stock RDO
+    const char *weights = std::getenv("MLT_WEIGHTS");
+    const char *dev = std::getenv("MLT_DEVICE");
+    if (!weights) {
+        std::fprintf(stderr, "error loading the model\n"); // same message as EncCu.cpp:904
+        std::fprintf(stderr, "mlt_hook: MLT_WEIGHTS is not set\n");
+        return;
+    }
+    const int rc = mlt_create(&m_ctx, weights, dev ? std::atoi(dev) : 0);
+    if (rc != MLT_OK) {
+        std::fprintf(stderr, "error loading the model\n");
+        std::fprintf(stderr, "mlt_hook: mlt_create(%s) -> %d (%s)\n", weights, rc, mlt_strerror(rc));
+        m_ctx = nullptr;
+    }
+}
+
+SplitPredictor::~SplitPredictor()
+{
+    if (m_ctx) mlt_destroy(m_ctx);
+}
+
+int SplitPredictor::predict(const int16_t *org, int orgStride, const int16_t *pred, int predStride, int poc, int qp)
+{
+    if (!m_ctx) return -1;
+    mlt_result r;
+    const int rc = mlt_predict_ctu(m_ctx, org, orgStride, pred, predStride, poc, qp, &r);
+    if (rc != MLT_OK) {
+        std::fprintf(stderr, "error\n"); // EncCu.cpp:925
+        return -1;
+    }
+    return r.split_l3;
+}
+
+bool SplitPredictor::beginPicture(const int16_t *orgLuma, int stride, int width, int height, int poc)
+{
+    return m_ctx && mlt_begin_picture(m_ctx, orgLuma, stride, width, height, poc) == MLT_OK;
+}
+
+int SplitPredictor::predictInPicture(int cux, int cuy, const int16_t *pred, int predStride, int qp)
+{
+    if (!m_ctx) return -1;
+    mlt_result r;
+    if (mlt_predict_ctu_in_picture(m_ctx, cux, cuy, pred, predStride, qp, &r) != MLT_OK) {
+        std::fprintf(stderr, "error\n");
+        return -1;
+    }
+    return r.split_l3;
+}
+
+void setNewModeList(ModeListState &st, int predictedSplitMode, int qp, bool canSplit)
+{
+    if (predictedSplitMode > 0) {
+        // a split was predicted: it becomes the only mode left to test, followed by a sacrificial
+        // POST_DONT_SPLIT that the next nextMode() pops (EncModeCtrl.cpp:95-107)
+        st.untouched = false;
+        st.testModes.clear();
+        const bool horz = predictedSplitMode == 2, vert = predictedSplitMode == 3;
+        if (canSplit) {
+            st.testModes.push_back({EncTestModeType(predictedSplitMode + 6), qp}); // PartSplit 1..5 -> ETM 7..11
+            if (horz) st.didHorzSplit = true;
+            if (vert) st.didVertSplit = true;
+        } else {
+            st.testModes.push_back({ETM_SPLIT_QT, qp}); // predicted split illegal here: fall back to QT
+            if (horz) st.didHorzSplit = false;
+            if (vert) st.didVertSplit = false;
+        }
+        st.testModes.push_back({ETM_POST_DONT_SPLIT, -1});
+    } else if (predictedSplitMode == 0) {
+        // no split: drop everything below POST_DONT_SPLIT (the splits sit at the bottom of the stack)
+        st.untouched = false;
+        while (!st.testModes.empty() && st.testModes.front().type != ETM_POST_DONT_SPLIT) st.testModes.erase(st.testModes.begin());
+    } else {
+        std::printf("Hello\n"); // inference failed: stack untouched, full RDO (EncModeCtrl.cpp:147-148)
+    }
+}
+
+} // namespace mlt_hook

@@ -1,0 +1,67 @@
+// mlt_hook.h -- host-side (C++14, no CUDA / torch / OpenCV headers) mirror of the reference's MLT-CNN hook, written
+// against the C ABI of libmltcnn.so (include/mltcnn.h).  This is the code a VTM maintainer drops into
+// EncCu::xCompressCU in place of the inline libtorch block (EncCu.cpp:803-926); see INTEGRATION.md.
+//
+//   reference                                   here
+//   ------------------------------------------  -----------------------------------------------------------
+//   useCNN gate            EncCu.cpp:746-756     mlt_hook::useCNN(...)
+//   at::kCUDA / model path EncCu.cpp:804,899     env MLT_DEVICE / MLT_WEIGHTS (MLT_DISABLE=1 -> anchor run)
+//   jit::load per CTU      EncCu.cpp:894-905     SplitPredictor::instance() loads the MLTW blob ONCE
+//   staging + forward      EncCu.cpp:806-921     SplitPredictor::predict(org, stride, pred, stride, poc, qp)
+//   error convention       EncCu.cpp:694,923     any failure -> "error\n" on stderr, returns -1 (full RDO)
+//   consumer               EncModeCtrl.cpp:110   unchanged in VTM; restated below only so tests can pin it
+#pragma once
+#include <cstdint>
+#include <vector>
+
+struct mlt_ctx;
+
+namespace mlt_hook {
+
+// EncCu.cpp:752-756 : luma tree, non-I slice, 128x128 CU, fully inside the picture.
+bool useCNN(int chType, bool isIntraSlice, int cuw, int cuh, int cux, int cuy, int picWidth, int picHeight);
+
+class SplitPredictor {
+public:
+    // Process-wide instance (the reference hook is single-threaded: ENABLE_SPLIT_PARALLELISM 0, TypeDef.h:113).
+    static SplitPredictor &instance();
+
+    bool enabled() const { return m_ctx != nullptr; } // false: MLT_DISABLE=1, or creation failed (message on stderr)
+
+    // == predictedSplitMode of EncCu.cpp:913-921: 0 NS, 1 QT, 2 BT_H, 3 BT_V; -1 on failure (caller passes it on
+    // to setNewModeList, which then leaves the mode stack untouched, EncModeCtrl.cpp:147-148).
+    int predict(const int16_t *org, int orgStride, const int16_t *pred, int predStride, int poc, int qp);
+
+    // Optional per-picture staging from EncSlice::encodeCtus (EncSlice.cpp:1479-1528): upload the original luma
+    // once, then only the 32 KiB prediction block per CTU.
+    bool beginPicture(const int16_t *orgLuma, int stride, int width, int height, int poc);
+    int predictInPicture(int cux, int cuy, const int16_t *pred, int predStride, int qp);
+
+    ~SplitPredictor();
+    SplitPredictor(const SplitPredictor &) = delete;
+    SplitPredictor &operator=(const SplitPredictor &) = delete;
+
+private:
+    SplitPredictor();
+    mlt_ctx *m_ctx = nullptr;
+};
+
+// ---- restatement of the consumer's semantics (EncModeCtrl.cpp:95-149), used by tests only ------------------
+enum EncTestModeType { // numbering of EncModeCtrl.h:56-78 with REUSE_CU_RESULTS
+    ETM_HASH_INTER, ETM_MERGE_SKIP, ETM_INTER_ME, ETM_AFFINE, ETM_MERGE_GEO, ETM_INTRA, ETM_PALETTE,
+    ETM_SPLIT_QT, ETM_SPLIT_BT_H, ETM_SPLIT_BT_V, ETM_SPLIT_TT_H, ETM_SPLIT_TT_V, ETM_POST_DONT_SPLIT,
+    ETM_RECO_CACHED, ETM_TRIGGER_IMV_LIST, ETM_IBC, ETM_IBC_MERGE, ETM_INVALID
+};
+struct TestMode {
+    EncTestModeType type;
+    int qp;
+};
+struct ModeListState {
+    std::vector<TestMode> testModes; // back() is tested next (EncModeCtrl.cpp:95-107)
+    bool didHorzSplit = false, didVertSplit = false;
+    bool untouched = true;
+};
+// canSplit: result of partitioner.canSplit(PartSplit(predictedSplitMode), cs) (UnitPartitioner.cpp:458-475)
+void setNewModeList(ModeListState &st, int predictedSplitMode, int qp, bool canSplit);
+
+} // namespace mlt_hook

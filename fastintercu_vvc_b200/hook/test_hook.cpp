@@ -1,0 +1,68 @@
+// test_hook.cpp -- CPU-only checks of the host-side hook mirror (run by tests/test_hook.py).
+#include <cassert>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "mlt_hook.h"
+
+using namespace mlt_hook;
+
+static ModeListState ra_stack_128()
+{
+    // RA cfg, 128x128 inter CTU after MERGE_SKIP was popped: bottom -> top
+    ModeListState s;
+    for (EncTestModeType t : {ETM_SPLIT_QT, ETM_SPLIT_BT_V, ETM_SPLIT_BT_H, ETM_POST_DONT_SPLIT, ETM_INTRA, ETM_INTER_ME})
+        s.testModes.push_back({t, 37});
+    return s;
+}
+
+int main()
+{
+    // ---- gate (EncCu.cpp:752-756): eligible CTUs per inter frame 416x240 -> 3, 1920x1080 -> 120, 3840x2160 -> 480
+    struct { int w, h, want; } pics[] = {{416, 240, 3}, {1920, 1080, 120}, {3840, 2160, 480}};
+    for (auto &p : pics) {
+        int n = 0;
+        for (int y = 0; y < p.h; y += 128)
+            for (int x = 0; x < p.w; x += 128) n += useCNN(0, false, 128, 128, x, y, p.w, p.h);
+        assert(n == p.want);
+    }
+    assert(!useCNN(1, false, 128, 128, 0, 0, 416, 240)); // chroma tree
+    assert(!useCNN(0, true, 128, 128, 0, 0, 416, 240));  // I slice
+    assert(!useCNN(0, false, 64, 64, 0, 0, 416, 240));   // smaller CUs are gated off (EncCu.cpp:754)
+    assert(!useCNN(0, false, 128, 64, 0, 0, 416, 240));
+
+    // ---- consumer semantics
+    for (int pred = 1; pred <= 3; pred++) {
+        ModeListState s = ra_stack_128();
+        setNewModeList(s, pred, 37, true);
+        assert(s.testModes.size() == 2 && s.testModes[0].type == EncTestModeType(pred + 6) && s.testModes[0].qp == 37);
+        assert(s.testModes[1].type == ETM_POST_DONT_SPLIT);
+        assert(s.didHorzSplit == (pred == 2) && s.didVertSplit == (pred == 3));
+    }
+    {
+        ModeListState s = ra_stack_128(); // predicted BT_H not allowed here -> QT
+        s.didHorzSplit = true;
+        setNewModeList(s, 2, 30, false);
+        assert(s.testModes.size() == 2 && s.testModes[0].type == ETM_SPLIT_QT && !s.didHorzSplit);
+    }
+    {
+        ModeListState s = ra_stack_128(); // no split: splits removed, the rest kept in order
+        setNewModeList(s, 0, 37, true);
+        assert(s.testModes.size() == 3 && s.testModes[0].type == ETM_POST_DONT_SPLIT && s.testModes[2].type == ETM_INTER_ME);
+    }
+    {
+        ModeListState s = ra_stack_128(); // failure: untouched
+        setNewModeList(s, -1, 37, true);
+        assert(s.untouched && s.testModes.size() == 6);
+    }
+
+    // ---- predictor failure convention: no usable GPU / weights here -> -1, never throws, never falls back
+    setenv("MLT_WEIGHTS", "/nonexistent/weights.mltw", 1);
+    SplitPredictor &p = SplitPredictor::instance();
+    std::vector<int16_t> blk(128 * 128, 512);
+    const int r = p.predict(blk.data(), 128, blk.data(), 128, 1, 32);
+    if (!p.enabled()) assert(r == -1);
+    std::printf("test_hook: OK (predictor %s, predict -> %d)\n", p.enabled() ? "enabled" : "disabled", r);
+    return 0;
+}

@@ -1,0 +1,169 @@
+"""CPU-only tests: weight packer, C-ABI surface, host-side hook mirror, multi-GPU sharding (gloo, world_size 2)."""
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+from fastintercu_vvc_b200 import pack_weights as pw
+from fastintercu_vvc_b200 import shard
+from fastintercu_vvc_b200.synth import make_state_dict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ------------------------------------------------------------------------------------------- packer
+
+
+@pytest.fixture(scope="module")
+def sd():
+    return make_state_dict(10)
+
+
+def test_bn_folding_matches_torch_eval(sd):
+    """w*gamma/sqrt(var+eps), beta-mean*gamma/sqrt(var+eps) == conv followed by eval-mode BatchNorm2d."""
+    import torch
+    import torch.nn.functional as F
+
+    w, b = pw.fold_bn(sd["layer1.0.conv1.weight"], sd, "layer1.0.bn1")
+    x = torch.randn(2, 32, 16, 16, generator=torch.Generator().manual_seed(0))
+    y = F.conv2d(x, torch.from_numpy(sd["layer1.0.conv1.weight"]), stride=2, padding=1)
+    y = F.batch_norm(y, torch.from_numpy(sd["layer1.0.bn1.running_mean"]), torch.from_numpy(sd["layer1.0.bn1.running_var"]),
+                     torch.from_numpy(sd["layer1.0.bn1.weight"]), torch.from_numpy(sd["layer1.0.bn1.bias"]), False, 0.0, 1e-5)
+    z = F.conv2d(x, torch.from_numpy(w), torch.from_numpy(b), stride=2, padding=1)
+    assert (y - z).abs().max() < 2e-5
+
+
+def test_blob_roundtrip_and_operand_layout(sd):
+    with tempfile.NamedTemporaryFile(suffix=".mltw") as f:
+        n = pw.write_blob(sd, f.name)
+        assert n == os.path.getsize(f.name)
+        secs = pw.read_sections(f.name)
+    table = pw.conv_table()
+    assert len(table) == 16
+    for li, (prefix, cin, cout, stride, hout, group, sc) in enumerate(table):
+        wf, bf = pw.fold_bn(sd[f"{prefix}.weight"], sd, prefix.replace("conv", "bn"))
+        packed = secs[pw.SEC_W_F16 + li].reshape(cin // group, 9, group // 8, cout, 8)
+        # element (cg, tap, j, n, e) == folded weight [n][cg*G + j*8 + e][kh][kw]
+        for (cg, t, j, nn, e) in ((0, 0, 0, 0, 0), (cin // group - 1, 8, group // 8 - 1, cout - 1, 7), (0, 4, 1, 5, 3)):
+            want = np.float16(wf[nn, cg * group + j * 8 + e, t // 3, t % 3])
+            assert packed[cg, t, j, nn, e] == want
+        assert np.array_equal(secs[pw.SEC_W_F32 + li].reshape(9, cin, cout)[4, 1, 2], wf[2, 1, 1, 1])
+        bias_op = secs[pw.SEC_BIAS_MMA + li].reshape(2, cout, 8).astype(np.float32)
+        fused = secs[pw.SEC_BIAS_FUSED + li]
+        assert np.abs(bias_op[0, :, 0] + bias_op[0, :, 1] - fused).max() < 1e-6  # hi + lo split is ~fp32 exact
+        assert not bias_op[1].any() and not bias_op[0, :, 2:].any()
+        if sc >= 0:
+            assert secs[pw.SEC_SC_W_F16 + sc].size == table[li - 1][1] * cout
+    # 'params' wrapper and 'module.' prefixes (model2torchScript.py:23-32) are accepted
+    wrapped = {"params": {"module." + k: v for k, v in sd.items()}}
+    assert pw.pack(wrapped) == pw.pack(sd)
+    assert secs[pw.SEC_CONV1_F32].reshape(9, 2, 32)[5, 1, 7] == sd["conv1.weight"][7, 1, 1, 2]
+
+
+# ------------------------------------------------------------------------------------------- C ABI surface
+
+
+def test_library_exports_every_declared_symbol():
+    from fastintercu_vvc_b200 import capi
+
+    hdr = open(os.path.join(ROOT, "include", "mltcnn.h")).read()
+    declared = set(re.findall(r"MLT_API[^;(]*?\b(mlt_[a-z_]+)\s*\(", hdr))
+    assert len(declared) >= 18, declared
+    lib = capi.load_library()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in mltcnn.h but not exported"
+    assert declared == set(capi.EXPORTS), declared ^ set(capi.EXPORTS)
+    out = subprocess.run(["nm", "-D", "--defined-only", capi.lib_path()], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (mlt_[a-z_]+)", out))
+    assert exported == declared, exported ^ declared  # nothing else leaks out of the library
+    assert lib.mlt_abi_version() == 1
+    assert b"batch" in lib.mlt_strerror(-7)
+    import ctypes as C
+
+    assert C.sizeof(capi.MltResult) == 88 and C.sizeof(capi.CtuDesc) == 32
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from fastintercu_vvc_b200 import MltError, MltPredictor
+
+    with pytest.raises(MltError) as e:
+        MltPredictor("/nonexistent.mltw")
+    assert e.value.rc == -6  # MLT_E_NODEVICE: fails loudly, never computes on the CPU
+
+
+def test_product_code_never_touches_the_oracle():
+    for base, _, files in os.walk(os.path.join(ROOT, "fastintercu_vvc_b200")):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(base, fn)).read()
+                for pat in ("import oracle", "from oracle", "oracle/", "oracle.", "mlto_", "libmltcnn_oracle"):
+                    assert pat not in src, f"{fn} references the oracle ({pat})"
+
+
+# ------------------------------------------------------------------------------------------- hook mirror (C++)
+
+
+def test_hook_mirror_cpp():
+    hook = os.path.join(ROOT, "fastintercu_vvc_b200", "hook")
+    subprocess.check_call(["make", "-s", "-C", hook])
+    r = subprocess.run([os.path.join(hook, "test_hook.bin")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "test_hook: OK" in r.stdout
+    assert "Hello" in r.stdout  # the reference's pred < 0 branch (EncModeCtrl.cpp:147-148)
+
+
+# ------------------------------------------------------------------------------------------- sharding
+
+
+def test_shard_range_and_lpt():
+    for n in (0, 1, 7, 8, 120, 121):
+        for w in (1, 2, 3, 8):
+            parts = [list(shard.shard_range(n, w, r)) for r in range(w)]
+            assert sum(parts, []) == list(range(n))
+            assert max(map(len, parts)) - min(map(len, parts)) <= 1
+    costs = [416 * 240, 832 * 480, 1280 * 720, 1920 * 1080] * 2
+    for w in (1, 2, 4, 8):
+        plan = shard.assign_encodes(costs, w)
+        assert sorted(sum(plan, [])) == list(range(8))
+        loads = [sum(costs[i] for i in p) for p in plan]
+        assert max(loads) <= sum(costs) / w + max(costs)
+
+
+_WORKER = r"""
+import os, sys
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from fastintercu_vvc_b200 import shard
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+n = 37
+rows = np.array([[i, (i * 2654435761) % 4] for i in shard.shard_range(n, world, rank)], np.int64)  # stand-in "decisions"
+allrows = shard.gather_rows(rows, world, rank)
+assert allrows.shape == (n, 2) and np.array_equal(allrows[:, 0], np.arange(n))
+assert np.array_equal(allrows[:, 1], (np.arange(n) * 2654435761) % 4)
+dist.barrier()
+if rank == 0:
+    print("GLOO_OK", world)
+dist.destroy_process_group()
+"""
+
+
+def test_two_rank_gloo_sharding(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+         "--master-port", "29541", str(script), ROOT],
+        capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "GLOO_OK 2" in r.stdout
