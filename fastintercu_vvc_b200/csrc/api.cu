@@ -16,8 +16,8 @@ namespace {
 
 constexpr uint32_t MLTW_MAGIC = 0x57544C4Du;
 enum : uint32_t {
-    SEC_CONV1_F32 = 0x001, SEC_W_F16 = 0x100, SEC_BIAS_FUSED = 0x200, SEC_W_F32 = 0x300, SEC_BIAS = 0x400,
-    SEC_SC_W_F16 = 0x500, SEC_SC_W_F32 = 0x600, SEC_SC_BIAS = 0x700, SEC_FC_W = 0x800, SEC_FC_B = 0x900, SEC_BIAS_MMA = 0xA00
+    SEC_CONV1_F32 = 0x001, SEC_CONV1_UMMA = 0x002, SEC_W_F16 = 0x100, SEC_BIAS_FUSED = 0x200, SEC_W_F32 = 0x300, SEC_BIAS = 0x400,
+    SEC_SC_W_F16 = 0x500, SEC_SC_W_F32 = 0x600, SEC_SC_BIAS = 0x700, SEC_FC_W = 0x800, SEC_FC_B = 0x900, SEC_BIAS_MMA = 0xA00, SEC_X_W_F16 = 0xB00
 };
 
 constexpr int NCONV = 16, NACT = 17, CTU = MLT_CTU_SIZE;
@@ -44,11 +44,9 @@ inline size_t act_elems(int a)
     act_shape(a, h, c);
     return (size_t)h * h * c;
 }
-inline size_t act_elems_haloed(int a) // fp16 product-path layout: [h+2][h+2][c] per image (conv_umma.cuh)
+inline ActLayout act_layout(int a) // fp16 product-path layout of activation a (conv_umma.cuh)
 {
-    int h, c;
-    act_shape(a, h, c);
-    return (size_t)(h + 2) * (h + 2) * c;
+    return a == 0 ? ActLayout{128, 32, 1, 0} : conv_umma_out_layout(a - 1);
 }
 
 struct Section { const uint8_t *dev = nullptr; size_t bytes = 0; };
@@ -62,6 +60,7 @@ struct mlt_ctx {
     size_t blob_bytes = 0;
     Section sec[0x1000];
     __half *act_h[NACT] = {};
+    ConvParams conv_p[NCONV]; // tensor maps + weight pointers of every tcgen05 conv, built once at create
     float *act_f[NACT] = {};
     float *scratch_f = nullptr; // shortcut-conv output of the fp32 engine
     int16_t *d_in = nullptr, *h_in = nullptr; // dense [max_batch][2][128][128]
@@ -75,8 +74,6 @@ struct mlt_ctx {
     bool pic_valid = false;
     int last_n = 0;
     uint64_t launches = 0;
-    int trace_layer = -1;
-    long long *d_trace = nullptr;
     bool profiling = false;
     cudaEvent_t prof_ev[NCONV + 3] = {}; // boundaries of: stage+conv1, 16 convs, head
     cudaStream_t prof_stream = nullptr;
@@ -120,8 +117,8 @@ int load_blob(mlt_ctx *c, const char *path)
     uint64_t total;
     memcpy(hdr, raw.data(), 16);
     memcpy(&total, raw.data() + 16, 8);
-    if (hdr[0] != MLTW_MAGIC || hdr[1] != 1 || hdr[2] != 128 || total != raw.size() || 32 + (size_t)hdr[3] * 24 > raw.size())
-        return fail(c, MLT_E_FORMAT, "'%s' is not an MLTW v1 blob for the 128x128 CTU model", path);
+    if (hdr[0] != MLTW_MAGIC || hdr[1] != 2 || hdr[2] != 128 || total != raw.size() || 32 + (size_t)hdr[3] * 24 > raw.size())
+        return fail(c, MLT_E_FORMAT, "'%s' is not an MLTW v2 blob for the 128x128 CTU model", path);
     CU(cudaMalloc(&c->d_blob, raw.size()));
     c->blob_bytes = raw.size();
     CU(cudaMemcpy(c->d_blob, raw.data(), raw.size(), cudaMemcpyHostToDevice));
@@ -136,16 +133,19 @@ int load_blob(mlt_ctx *c, const char *path)
     }
     // every section this architecture needs must be present with the exact size
     auto need = [&](uint32_t id, size_t bytes) { return c->sec[id].dev != nullptr && c->sec[id].bytes == bytes; };
-    bool ok = need(SEC_CONV1_F32, 9 * 2 * 32 * 4);
+    bool ok = need(SEC_CONV1_F32, 9 * 2 * 32 * 4) && need(SEC_CONV1_UMMA, 2 * 4 * 32 * 16);
     for (int li = 0; li < NCONV && ok; li++) {
         const LayerDesc &L = kLayers[li];
         ok = need(SEC_W_F16 + li, (size_t)9 * L.cin * L.cout * 2) && need(SEC_W_F32 + li, (size_t)9 * L.cin * L.cout * 4) &&
              need(SEC_BIAS + li, (size_t)L.cout * 4) && need(SEC_BIAS_FUSED + li, (size_t)L.cout * 4) &&
              need(SEC_BIAS_MMA + li, (size_t)L.cout * 32);
+        if (ok && (li & 1)) { // second conv of a block: extra operand = shortcut conv (first block) or identity
+            const int xc = L.sc >= 0 ? kLayers[li - 1].cin : L.cout;
+            ok = need(SEC_X_W_F16 + li, (size_t)xc * L.cout * 2);
+        }
         if (ok && L.sc >= 0) {
             const int csc = kLayers[li - 1].cin;
-            ok = need(SEC_SC_W_F16 + L.sc, (size_t)csc * L.cout * 2) && need(SEC_SC_W_F32 + L.sc, (size_t)csc * L.cout * 4) &&
-                 need(SEC_SC_BIAS + L.sc, (size_t)L.cout * 4);
+            ok = need(SEC_SC_W_F32 + L.sc, (size_t)csc * L.cout * 4) && need(SEC_SC_BIAS + L.sc, (size_t)L.cout * 4);
         }
     }
     static const int fin[3] = {66, 130, 258}, fout[3] = {2, 3, 4};
@@ -200,27 +200,13 @@ int run_network(mlt_ctx *c, const CtuDev *ctus, int n, mlt_result *out, cudaStre
         const bool prof = c->profiling;
         int ev = 0;
         if (prof) { CU(cudaEventRecord(c->prof_ev[ev++], s)); c->prof_stream = s; c->prof_valid = false; }
-        CU(launch_stage_conv1_h(ctus, n, secp<float>(c, SEC_CONV1_F32), c->act_h[0], s));
+        CU(launch_conv1_umma(ctus, n, secp<__half>(c, SEC_CONV1_UMMA), c->act_h[0], s));
         c->launches++;
         if (prof) CU(cudaEventRecord(c->prof_ev[ev++], s));
         for (int li = 0; li < NCONV; li++) {
-            const LayerDesc &L = kLayers[li];
-            const bool conv2 = (li & 1) != 0;
-            const __half *x_block = c->act_h[li & ~1]; // input of the BasicBlock this conv belongs to
-            const __half *in = c->act_h[li];
-            const __half *sc_in = nullptr, *sc_w = nullptr, *res = nullptr;
-            if (conv2) {
-                if (L.sc >= 0) { sc_in = x_block; sc_w = secp<__half>(c, SEC_SC_W_F16 + L.sc); }
-                else res = x_block;
-            }
-            long long *trace = nullptr;
-            if (c->trace_layer == li) { // debug: MLT_TRACE_LAYER=<li> MLT_TRACE_FILE=<path>
-                if (!c->d_trace) CU(cudaMalloc(&c->d_trace, 4 * 64 * 4 * sizeof(long long)));
-                CU(cudaMemsetAsync(c->d_trace, 0, 4 * 64 * 4 * sizeof(long long), s));
-                trace = c->d_trace;
-            }
-            CU(launch_conv_umma(li, in, secp<__half>(c, SEC_W_F16 + li), secp<__half>(c, SEC_BIAS_MMA + li), sc_in, sc_w, res,
-                                c->act_h[li + 1], n, 1, c->num_sms, s, trace));
+            ConvParams &p = c->conv_p[li];
+            p.nimg = n;
+            CU(launch_conv_umma(li, p, c->num_sms, s));
             c->launches++;
             if (prof) CU(cudaEventRecord(c->prof_ev[ev++], s));
         }
@@ -257,18 +243,6 @@ int run_network(mlt_ctx *c, const CtuDev *ctus, int n, mlt_result *out, cudaStre
         c->launches++;
     }
     c->last_n = n;
-    if (c->trace_layer >= 0 && c->d_trace && getenv("MLT_TRACE_FILE")) {
-        std::vector<long long> h(4 * 64 * 4);
-        CU(cudaStreamSynchronize(s));
-        CU(cudaMemcpy(h.data(), c->d_trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-        if (FILE *f = fopen(getenv("MLT_TRACE_FILE"), "w")) {
-            fprintf(f, "# layer %d n %d: role tile t0 t1 t2 t3 (clock64 of CTA 0; role 0 producer, 1 mma, 2/3 epilogue groups)\n", c->trace_layer, n);
-            for (int r = 0; r < 4; r++)
-                for (int t = 0; t < 64; t++)
-                    fprintf(f, "%d %d %lld %lld %lld %lld\n", r, t, h[(r * 64 + t) * 4], h[(r * 64 + t) * 4 + 1], h[(r * 64 + t) * 4 + 2], h[(r * 64 + t) * 4 + 3]);
-            fclose(f);
-        }
-    }
     return MLT_OK;
 }
 
@@ -348,7 +322,7 @@ void mlt_destroy(mlt_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (int a = 0; a < NACT; a++) { cudaFree(c->act_h[a]); cudaFree(c->act_f[a]); }
     cudaFree(c->scratch_f); cudaFree(c->d_blob); cudaFree(c->d_in); cudaFree(c->d_ctus); cudaFree(c->d_out);
-    cudaFree(c->d_dbg); cudaFree(c->d_pic); cudaFree(c->d_trace);
+    cudaFree(c->d_dbg); cudaFree(c->d_pic);
     cudaFreeHost(c->h_in); cudaFreeHost(c->h_ctus); cudaFreeHost(c->h_out);
     for (cudaEvent_t e : c->prof_ev) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -371,7 +345,6 @@ int mlt_create_ex(mlt_ctx **out, const char *weights_path, int cuda_device, int 
     c->device = cuda_device;
     c->max_batch = max_batch;
     c->num_sms = prop.multiProcessorCount;
-    if (const char *tl = getenv("MLT_TRACE_LAYER")) c->trace_layer = atoi(tl);
     int rc = MLT_OK;
     auto body = [&]() -> int {
         CU(cudaSetDevice(cuda_device));
@@ -380,10 +353,26 @@ int mlt_create_ex(mlt_ctx **out, const char *weights_path, int cuda_device, int 
         if (r) return r;
         CU(conv_umma_init());
         for (int a = 0; a < NACT; a++) {
-            // +1 image: spare for the tile that pairs the last image of an odd batch; halos are zeroed once, here
-            const size_t bytes = act_elems_haloed(a) * ((size_t)max_batch + 1) * sizeof(__half);
+            // zeroed once: the unused half of the last image pair of an odd batch must stay finite
+            const ActLayout L = act_layout(a);
+            const size_t bytes = L.unit_elems() * L.units_for(max_batch) * sizeof(__half);
             CU(cudaMalloc(&c->act_h[a], bytes));
             CU(cudaMemsetAsync(c->act_h[a], 0, bytes, c->stream));
+        }
+        for (int li = 0; li < NCONV; li++) {
+            const LayerDesc &L = kLayers[li];
+            ConvParams &p = c->conv_p[li];
+            memset(&p, 0, sizeof p);
+            const bool conv2 = (li & 1) != 0;
+            const int xa = li & ~1; // input of the BasicBlock this conv belongs to
+            const ActLayout in_l = act_layout(li), x_l = act_layout(xa);
+            CU(conv_umma_prepare(li, &p, c->act_h[li], in_l, conv2 ? c->act_h[xa] : nullptr, conv2 ? &x_l : nullptr, (size_t)max_batch));
+            p.w = secp<__half>(c, SEC_W_F16 + li);
+            p.bias = secp<__half>(c, SEC_BIAS_MMA + li);
+            p.x_w = conv2 ? secp<__half>(c, SEC_X_W_F16 + li) : nullptr;
+            p.out = c->act_h[li + 1];
+            p.relu = 1;
+            (void)L;
         }
         CU(cudaStreamSynchronize(c->stream));
         CU(cudaMalloc(&c->d_in, (size_t)max_batch * CTU_IN_ELEMS * sizeof(int16_t)));
@@ -575,9 +564,7 @@ int64_t mlt_debug_activation(mlt_ctx *c, int layer, float *out, int64_t capacity
     if (c->engine == 0) {
         rc = ensure_dbg(c, elems * sizeof(float));
         if (rc) return rc;
-        int h, ch;
-        act_shape(layer, h, ch);
-        CU(launch_unhalo_to_float(c->act_h[layer], c->d_dbg, c->last_n, h, ch, s));
+        CU(launch_unpack_act(c->act_h[layer], c->d_dbg, c->last_n, act_layout(layer), s));
         CU(cudaMemcpyAsync(out, c->d_dbg, elems * sizeof(float), cudaMemcpyDeviceToHost, s));
     } else {
         if (!c->act_f[layer]) return fail(c, MLT_E_STATE, "fp32 engine has not run");

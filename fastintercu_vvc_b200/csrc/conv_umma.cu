@@ -1,4 +1,4 @@
-// conv_umma.cu -- instantiations + launcher of the tcgen05 implicit-GEMM conv kernel for the 16
+// conv_umma.cu -- instantiations, TMA tensor maps and launcher of the tcgen05 implicit-GEMM conv kernel for the 16
 // 3x3 convolutions of the MLT-CNN residual stack (shapes: SURVEY.md section 8a / arch.py:247-254).
 #include <cstdlib>
 
@@ -7,10 +7,113 @@
 
 namespace mlt {
 
-template <class C>
-static cudaError_t init_one()
+//            CIN  COUT S  HOUT XC  OUT_PAR
+using L0a = ConvCfg<32, 32, 2, 64, 0, 0>;     // layer0.0.conv1
+using L0b = ConvCfg<32, 32, 1, 64, 32, 0>;    // layer0.0.conv2 + shortcut(conv1 out)
+using L0c = ConvCfg<32, 32, 1, 64, 0, 0>;     // layer0.1.conv1
+using L0d = ConvCfg<32, 32, 1, 64, 32, 1>;    // layer0.1.conv2 + identity; output feeds a stride-2 block
+using L1a = ConvCfg<32, 64, 2, 32, 0, 0>;     // layer1.0.conv1
+using L1b = ConvCfg<64, 64, 1, 32, 32, 0>;    // layer1.0.conv2 + shortcut
+using L1c = ConvCfg<64, 64, 1, 32, 0, 0>;     // layer1.1.conv1
+using L1d = ConvCfg<64, 64, 1, 32, 64, 1>;    // layer1.1.conv2 + identity
+using L2a = ConvCfg<64, 128, 2, 16, 0, 0>;    // layer2.0.conv1
+using L2b = ConvCfg<128, 128, 1, 16, 64, 0>;  // layer2.0.conv2 + shortcut
+using L2c = ConvCfg<128, 128, 1, 16, 0, 0>;   // layer2.1.conv1
+using L2d = ConvCfg<128, 128, 1, 16, 128, 1>; // layer2.1.conv2 + identity
+using L3a = ConvCfg<128, 256, 2, 8, 0, 0>;    // layer3.0.conv1
+using L3b = ConvCfg<256, 256, 1, 8, 128, 0>;  // layer3.0.conv2 + shortcut
+using L3c = ConvCfg<256, 256, 1, 8, 0, 0>;    // layer3.1.conv1
+using L3d = ConvCfg<256, 256, 1, 8, 256, 0>;  // layer3.1.conv2 + identity
+
+#define MLT_FOR_LAYER(li, F)                                                                                            \
+    switch (li) {                                                                                                       \
+    case 0: F(L0a); break;  case 1: F(L0b); break;  case 2: F(L0c); break;  case 3: F(L0d); break;                      \
+    case 4: F(L1a); break;  case 5: F(L1b); break;  case 6: F(L1c); break;  case 7: F(L1d); break;                      \
+    case 8: F(L2a); break;  case 9: F(L2b); break;  case 10: F(L2c); break; case 11: F(L2d); break;                     \
+    case 12: F(L3a); break; case 13: F(L3b); break; case 14: F(L3c); break; case 15: F(L3d); break;                     \
+    default: return cudaErrorInvalidValue;                                                                              \
+    }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn g_encode = nullptr;
+
+cudaError_t conv_umma_init()
 {
-    return cudaFuncSetAttribute(conv_umma_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    cudaError_t e;
+#define MLT_INIT(C) if ((e = cudaFuncSetAttribute(conv_umma_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES)) != cudaSuccess) return e
+    for (int li = 0; li < 16; li++) { MLT_FOR_LAYER(li, MLT_INIT) }
+#undef MLT_INIT
+    if (!g_encode) {
+        cudaDriverEntryPointQueryResult q;
+        void *fn = nullptr;
+        e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+        if (e != cudaSuccess) return e;
+        if (!fn || q != cudaDriverEntryPointSuccess) return cudaErrorNotSupported;
+        g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    return cudaSuccess;
+}
+
+// 5-D tiled map over a chunk-planar activation tensor: dims (x*8, img, row, chunk, unit*plane), fp16, no swizzle.
+cudaError_t make_act_map(CUtensorMap *tm, const __half *base, const ActLayout &L, size_t units, int box_px, int box_img,
+                         int box_rows, int box_chunks)
+{
+    if (!g_encode) return cudaErrorNotReady;
+    const cuuint64_t hp = (cuuint64_t)L.hp(), ni = (cuuint64_t)L.nimg();
+    cuuint64_t dims[5] = {hp * 8, ni, hp, (cuuint64_t)(L.C / 8), (cuuint64_t)units * L.npl()};
+    cuuint64_t strides[4] = {hp * 16, ni * hp * 16, hp * ni * hp * 16, (cuuint64_t)(L.C / 8) * hp * ni * hp * 16};
+    cuuint32_t box[5] = {(cuuint32_t)box_px * 8, (cuuint32_t)box_img, (cuuint32_t)box_rows, (cuuint32_t)box_chunks, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    const CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<__half *>(base), dims, strides, box, es,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+template <class C>
+static cudaError_t prepare_one(ConvParams &p, const __half *in, const ActLayout &in_l, const __half *x, const ActLayout *x_l, size_t images)
+{
+    // the layouts the kernel template assumes must be the layouts the buffers were allocated with
+    if (in_l.C != C::CIN || in_l.H != C::HOUT * C::STRIDE || in_l.par != (C::STRIDE == 2) || in_l.pair != C::IN_PAIR) return cudaErrorInvalidValue;
+    cudaError_t e = make_act_map(&p.in_map, in, in_l, in_l.units_for((int)images), C::BLKW, C::NB, C::PROWS, C::CH);
+    if (e != cudaSuccess) return e;
+    if constexpr (C::XC > 0) {
+        if (!x || !x_l || x_l->C != C::XC || x_l->hp() != C::HOUT || x_l->pair != C::IN_PAIR) return cudaErrorInvalidValue;
+        e = make_act_map(&p.x_map, x, *x_l, x_l->units_for((int)images), 8, C::NB, C::TR, C::GX / 8);
+        if (e != cudaSuccess) return e;
+        p.x_unit_mul = x_l->npl();
+    } else {
+        p.x_map = p.in_map;
+        p.x_unit_mul = 1;
+    }
+    return cudaSuccess;
+}
+
+cudaError_t conv_umma_prepare(int layer, ConvParams *p, const __half *in, const ActLayout &in_l, const __half *x, const ActLayout *x_l,
+                              size_t images)
+{
+#define MLT_PREP(C) return prepare_one<C>(*p, in, in_l, x, x_l, images)
+    MLT_FOR_LAYER(layer, MLT_PREP)
+#undef MLT_PREP
+    return cudaSuccess;
+}
+
+ActLayout conv_umma_out_layout(int layer)
+{
+    ActLayout l{0, 0, 0, 0};
+#define MLT_OUT(C) l = ActLayout{C::HOUT, C::COUT, C::OUT_PAR, C::OUT_PAIR}
+    switch (layer) {
+    case 0: MLT_OUT(L0a); break;  case 1: MLT_OUT(L0b); break;  case 2: MLT_OUT(L0c); break;  case 3: MLT_OUT(L0d); break;
+    case 4: MLT_OUT(L1a); break;  case 5: MLT_OUT(L1b); break;  case 6: MLT_OUT(L1c); break;  case 7: MLT_OUT(L1d); break;
+    case 8: MLT_OUT(L2a); break;  case 9: MLT_OUT(L2b); break;  case 10: MLT_OUT(L2c); break; case 11: MLT_OUT(L2d); break;
+    case 12: MLT_OUT(L3a); break; case 13: MLT_OUT(L3b); break; case 14: MLT_OUT(L3c); break; case 15: MLT_OUT(L3d); break;
+    default: break;
+    }
+#undef MLT_OUT
+    return l;
 }
 
 template <class C>
@@ -23,54 +126,12 @@ static cudaError_t launch_one(const ConvParams &p, int num_sms, cudaStream_t s)
     return cudaGetLastError();
 }
 
-//            CIN  COUT S  HOUT CSC
-using L0a = ConvCfg<32, 32, 2, 64, 0>;    // layer0.0.conv1
-using L0b = ConvCfg<32, 32, 1, 64, 32>;   // layer0.0.conv2 + shortcut(conv1 out)
-using L0c = ConvCfg<32, 32, 1, 64, 0>;    // layer0.1.conv1 / conv2
-using L1a = ConvCfg<32, 64, 2, 32, 0>;    // layer1.0.conv1
-using L1b = ConvCfg<64, 64, 1, 32, 32>;   // layer1.0.conv2 + shortcut
-using L1c = ConvCfg<64, 64, 1, 32, 0>;    // layer1.1.*
-using L2a = ConvCfg<64, 128, 2, 16, 0>;   // layer2.0.conv1
-using L2b = ConvCfg<128, 128, 1, 16, 64>; // layer2.0.conv2 + shortcut
-using L2c = ConvCfg<128, 128, 1, 16, 0>;  // layer2.1.*
-using L3a = ConvCfg<128, 256, 2, 8, 0>;   // layer3.0.conv1
-using L3b = ConvCfg<256, 256, 1, 8, 128>; // layer3.0.conv2 + shortcut
-using L3c = ConvCfg<256, 256, 1, 8, 0>;   // layer3.1.*
-
-cudaError_t conv_umma_init()
+cudaError_t launch_conv_umma(int layer, const ConvParams &p, int num_sms, cudaStream_t s)
 {
-    cudaError_t e;
-#define MLT_INIT(C) if ((e = init_one<C>()) != cudaSuccess) return e;
-    MLT_INIT(L0a) MLT_INIT(L0b) MLT_INIT(L0c) MLT_INIT(L1a) MLT_INIT(L1b) MLT_INIT(L1c)
-    MLT_INIT(L2a) MLT_INIT(L2b) MLT_INIT(L2c) MLT_INIT(L3a) MLT_INIT(L3b) MLT_INIT(L3c)
-#undef MLT_INIT
+#define MLT_LAUNCH(C) return launch_one<C>(p, num_sms, s)
+    MLT_FOR_LAYER(layer, MLT_LAUNCH)
+#undef MLT_LAUNCH
     return cudaSuccess;
-}
-
-cudaError_t launch_conv_umma(int layer, const __half *in, const __half *w, const __half *bias, const __half *sc_in,
-                             const __half *sc_w, const __half *res, __half *out, int nimg, int relu, int num_sms,
-                             cudaStream_t s, long long *trace)
-{
-    ConvParams p;
-    p.in = in; p.w = w; p.bias = bias; p.sc_in = sc_in; p.sc_w = sc_w; p.res = res; p.out = out;
-    p.nimg = nimg; p.relu = relu; p.trace = trace;
-    static const int dbg = getenv("MLT_DEBUG_FLAGS") ? atoi(getenv("MLT_DEBUG_FLAGS")) : 0;
-    p.dbg = dbg;
-    switch (layer) {
-    case 0: return launch_one<L0a>(p, num_sms, s);
-    case 1: return launch_one<L0b>(p, num_sms, s);
-    case 2: case 3: return launch_one<L0c>(p, num_sms, s);
-    case 4: return launch_one<L1a>(p, num_sms, s);
-    case 5: return launch_one<L1b>(p, num_sms, s);
-    case 6: case 7: return launch_one<L1c>(p, num_sms, s);
-    case 8: return launch_one<L2a>(p, num_sms, s);
-    case 9: return launch_one<L2b>(p, num_sms, s);
-    case 10: case 11: return launch_one<L2c>(p, num_sms, s);
-    case 12: return launch_one<L3a>(p, num_sms, s);
-    case 13: return launch_one<L3b>(p, num_sms, s);
-    case 14: case 15: return launch_one<L3c>(p, num_sms, s);
-    default: return cudaErrorInvalidValue;
-    }
 }
 
 } // namespace mlt

@@ -28,18 +28,18 @@ __device__ __forceinline__ void load8<float>(const float *p, float (&f)[8])
     f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
 }
 
-// mean over the H x H pixels of an NHWC map -> feat[C]; 256 threads, deterministic.  The fp16 maps carry a
-// one-pixel zero halo ([H+2][H+2][C]); summing over it is harmless, so the whole buffer is read linearly.
-template <typename T, int H, int C>
-__device__ __forceinline__ void gap(const T *act, float *partial /*[256/(C/8)][C]*/, float *feat)
+// mean over the H x H pixels of one image -> feat[C]; 256 threads, deterministic (fixed summation order).
+// fp32 cross-check engine: dense NHWC.  Product path: chunk-planar fp16 (conv_umma.cuh ActLayout) -- the thread
+// group of one 8-channel chunk walks that chunk's pixels (16 B apart) in order.
+template <int H, int C>
+__device__ __forceinline__ void gap_nhwc(const float *act, float *partial /*[256/(C/8)][C]*/, float *feat)
 {
-    constexpr int HP = sizeof(T) == 2 ? H + 2 : H, P = HP * HP;
-    constexpr int CH = C / 8, PH = 256 / CH;
+    constexpr int P = H * H, CH = C / 8, PH = 256 / CH;
     const int cj = threadIdx.x % CH, pp = threadIdx.x / CH;
     float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int p = pp; p < P; p += PH) {
         float f[8];
-        load8<T>(act + (size_t)p * C + cj * 8, f);
+        load8<float>(act + (size_t)p * C + cj * 8, f);
 #pragma unroll
         for (int e = 0; e < 8; e++) s[e] += f[e];
     }
@@ -54,6 +54,34 @@ __device__ __forceinline__ void gap(const T *act, float *partial /*[256/(C/8)][C
     __syncthreads();
 }
 
+template <int H, int C, int PAR, int PAIR>
+__device__ __forceinline__ void gap_planar(const __half *act, int img, float *partial /*[256/(C/8)][C]*/, float *feat)
+{
+    constexpr int HP = PAR ? H / 2 : H, NPL = PAR ? 4 : 1, NIMG = PAIR ? 2 : 1;
+    constexpr int CH = C / 8, TPC = 256 / CH; // threads per chunk
+    constexpr size_t CHUNK = (size_t)HP * NIMG * HP * 8;
+    const int cj = threadIdx.x / TPC, pp = threadIdx.x % TPC;
+    const size_t unit = PAIR ? img >> 1 : img;
+    const int sub = PAIR ? img & 1 : 0;
+    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int p = pp; p < NPL * HP * HP; p += TPC) {
+        const int plane = p / (HP * HP), yy = (p / HP) % HP, xx = p % HP;
+        float f[8];
+        load8<__half>(act + ((unit * NPL + plane) * CH + cj) * CHUNK + (size_t)((yy * NIMG + sub) * HP + xx) * 8, f);
+#pragma unroll
+        for (int e = 0; e < 8; e++) s[e] += f[e];
+    }
+#pragma unroll
+    for (int e = 0; e < 8; e++) partial[pp * C + cj * 8 + e] = s[e];
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+        float t = 0.0f;
+        for (int k = 0; k < TPC; k++) t += partial[k * C + c];
+        feat[c] = t * (1.0f / (float)(H * H));
+    }
+    __syncthreads();
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) head_kernel(const HeadParams p)
 {
@@ -61,10 +89,15 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadParams p)
     __shared__ float feat[64 + 128 + 256];
     __shared__ float logits[9];
     const int n = blockIdx.x;
-    constexpr int E = sizeof(T) == 2 ? 2 : 0; // halo
-    gap<T, 32, 64>(static_cast<const T *>(p.act[0]) + (size_t)n * (32 + E) * (32 + E) * 64, partial, feat);
-    gap<T, 16, 128>(static_cast<const T *>(p.act[1]) + (size_t)n * (16 + E) * (16 + E) * 128, partial, feat + 64);
-    gap<T, 8, 256>(static_cast<const T *>(p.act[2]) + (size_t)n * (8 + E) * (8 + E) * 256, partial, feat + 192);
+    if constexpr (sizeof(T) == 2) { // layouts of activations 8 / 12 / 16 (conv_umma.cu L1d / L2d / L3d outputs)
+        gap_planar<32, 64, 1, 0>(static_cast<const __half *>(p.act[0]), n, partial, feat);
+        gap_planar<16, 128, 1, 1>(static_cast<const __half *>(p.act[1]), n, partial, feat + 64);
+        gap_planar<8, 256, 0, 1>(static_cast<const __half *>(p.act[2]), n, partial, feat + 192);
+    } else {
+        gap_nhwc<32, 64>(static_cast<const float *>(p.act[0]) + (size_t)n * 32 * 32 * 64, partial, feat);
+        gap_nhwc<16, 128>(static_cast<const float *>(p.act[1]) + (size_t)n * 16 * 16 * 128, partial, feat + 64);
+        gap_nhwc<8, 256>(static_cast<const float *>(p.act[2]) + (size_t)n * 8 * 8 * 256, partial, feat + 192);
+    }
 
     const float poc = (float)p.ctus[n].poc, qp = (float)p.ctus[n].qp; // raw ints promoted by torch.cat (arch.py:274-275)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -1,5 +1,6 @@
 // mlt_internal.h -- declarations shared by the kernels and the C-ABI layer of libmltcnn.so.
 #pragma once
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -29,9 +30,10 @@ struct LayerDesc { // one 3x3 conv of the residual stack (forward order, after c
 // ---- stage_conv1.cu
 // fp32 normalised input tensor [n][2][128][128] (bit-exactness probe of EncCu.cpp:810-867)
 cudaError_t launch_stage(const CtuDev *ctus, int n, float *out, cudaStream_t s);
-// fused staging + conv1 (2->32, 3x3, no BN / ReLU; arch.py:278) -> NHWC [n][128][128][32]
-cudaError_t launch_stage_conv1_h(const CtuDev *ctus, int n, const float *w /*[9][2][32]*/, __half *out, cudaStream_t s);
-cudaError_t launch_stage_conv1_f(const CtuDev *ctus, int n, const float *w, float *out, cudaStream_t s);
+// product path: staging + conv1 (2->32, 3x3, no BN / ReLU; arch.py:278) on tcgen05 -> activation 0, parity-planar fp16
+cudaError_t launch_conv1_umma(const CtuDev *ctus, int n, const __half *wop /*[hi,lo][4][32][8]*/, __half *out, cudaStream_t s);
+// fp32 cross-check engine: fused staging + conv1 on CUDA cores -> NHWC fp32 [n][128][128][32]
+cudaError_t launch_stage_conv1_f(const CtuDev *ctus, int n, const float *w /*[9][2][32]*/, float *out, cudaStream_t s);
 
 // ---- conv_simt.cu : fp32 CUDA-core cross-check engine (tests only; never a fallback)
 cudaError_t launch_conv_simt(const float *in, const float *w /*[k*k][cin][cout]*/, const float *bias, const float *res,
@@ -39,15 +41,43 @@ cudaError_t launch_conv_simt(const float *in, const float *w /*[k*k][cin][cout]*
                              cudaStream_t s);
 
 // ---- conv_umma.cu : tcgen05 implicit-GEMM engine
-struct ConvParams;
-cudaError_t launch_conv_umma(int layer, const __half *in, const __half *w, const __half *bias, const __half *sc_in,
-                             const __half *sc_w, const __half *res, __half *out, int nimg, int relu, int num_sms,
-                             cudaStream_t s, long long *trace = nullptr);
-cudaError_t conv_umma_init(); // opt in to large dynamic shared memory for every instantiation
+// Chunk-planar activation layout.  Element offset of (unit u, plane p, chunk k, row y, sub-image s, column x, e):
+//   (((((u * NPL + p) * (C/8) + k) * HP + y) * NIMG + s) * HP + x) * 8 + e
+// PAR : four parity planes, plane = (row & 1) * 2 + (col & 1), (y, x) = (row >> 1, col >> 1), HP = H / 2
+// PAIR: two images per unit (row-interleaved), image i = unit i >> 1, sub-image i & 1
+struct ActLayout {
+    int H, C, par, pair;
+    __host__ __device__ int hp() const { return par ? H / 2 : H; }
+    __host__ __device__ int npl() const { return par ? 4 : 1; }
+    __host__ __device__ int nimg() const { return pair ? 2 : 1; }
+    __host__ __device__ size_t chunk_stride() const { return (size_t)hp() * nimg() * hp() * 8; }
+    __host__ __device__ size_t unit_elems() const { return chunk_stride() * (C / 8) * npl(); }
+    __host__ __device__ size_t units_for(int images) const { return pair ? (size_t)(images + 1) / 2 : (size_t)images; }
+};
+
+struct ConvParams {
+    CUtensorMap in_map; // main operand: 5-D (x*8, img, row, chunk, unit*plane) over the layer input
+    CUtensorMap x_map;  // extra operand (block input: shortcut conv / identity residual); unused when XC == 0
+    const __half *w;    // packed [CIN/G][9][G/8][COUT][8]
+    const __half *bias; // tcgen05 bias operand [2][COUT][8] fp16: k=0 -> hi(b), k=1 -> lo(b), rest 0 (pack_weights.py)
+    const __half *x_w;  // packed [XC/GX][GX/8][COUT][8] (folded shortcut weights, or the identity)
+    __half *out;
+    int nimg;
+    int relu;
+    int x_unit_mul; // 4 when the extra operand tensor is parity-planar (plane 0 = even rows, even columns), else 1
+};
+
+cudaError_t conv_umma_init(); // opt in to large dynamic shared memory for every instantiation; resolve cuTensorMapEncodeTiled
+ActLayout conv_umma_out_layout(int layer); // layout of the activation conv `layer` (0..15) writes
+// fill p->in_map / x_map / x_unit_mul for conv `layer` reading `in` (and the block input `x` for the second conv of a block);
+// `images` = capacity of the buffers in images
+cudaError_t conv_umma_prepare(int layer, ConvParams *p, const __half *in, const ActLayout &in_l, const __half *x, const ActLayout *x_l,
+                              size_t images);
+cudaError_t launch_conv_umma(int layer, const ConvParams &p, int num_sms, cudaStream_t s);
 
 // ---- head.cu : global average pools + FC heads + softmax + argmax + flags (arch.py:281-297, EncCu.cpp:913-921)
 struct HeadParams {
-    const void *act[3];   // layer1 / layer2 / layer3 outputs: haloed NHWC fp16 (product) or dense NHWC fp32 (cross-check)
+    const void *act[3];   // layer1 / layer2 / layer3 outputs: chunk-planar fp16 (product) or dense NHWC fp32 (cross-check)
     const float *fc_w[3]; // [out][in]
     const float *fc_b[3];
     const CtuDev *ctus;   // poc / qp
@@ -58,6 +88,6 @@ cudaError_t launch_head_h(const HeadParams &p, cudaStream_t s);
 cudaError_t launch_head_f(const HeadParams &p, cudaStream_t s);
 
 // ---- misc
-cudaError_t launch_unhalo_to_float(const __half *in, float *out, int nimg, int h, int c, cudaStream_t s);
+cudaError_t launch_unpack_act(const __half *in, float *out, int nimg, const ActLayout &L, cudaStream_t s);
 
 } // namespace mlt

@@ -87,6 +87,18 @@ __device__ __forceinline__ void bulk_g2s(uint32_t smem_dst, const void *gsrc, ui
                  : "memory");
 }
 
+// ------------------------------------------------------------------ TMA tiled tensor load global -> smem (UTMALDG), 5-D
+// Box written densely in dimension order (c0 innermost); out-of-range elements (negative or past the extent) are
+// zero-filled and still counted in the mbarrier's transaction bytes.
+__device__ __forceinline__ void tma_load_5d(uint32_t smem_dst, const void *tmap, int c0, int c1, int c2, int c3, int c4, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(smem_dst),
+        "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void *tmap) { asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory"); }
+
 // ------------------------------------------------------------------ TMEM allocation
 __device__ __forceinline__ void tmem_alloc(uint32_t *smem_slot, uint32_t ncols)
 {

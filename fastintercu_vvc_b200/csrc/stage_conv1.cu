@@ -4,9 +4,14 @@
 //   conv1   : 3x3, 2 -> 32 channels, stride 1, pad 1, no BN, no activation
 //
 // The product path never materialises the fp32 [2][128][128] tensor the reference ships to the GPU
-// (128 KiB H2D per CTU, EncCu.cpp:875): `stage_conv1_kernel` reads the int16 samples with 128-bit
-// loads, normalises them in registers with exactly the reference's fp32 arithmetic and feeds conv1
-// directly.  `stage_kernel` writes that tensor out only for the bit-exactness probe (mlt_debug_stage).
+// (128 KiB H2D per CTU, EncCu.cpp:875):
+//   * `conv1_umma_kernel` (product) reads the int16 samples with 128-bit loads, does the integer part of the
+//     staging exactly (uint16 cast, |org - pred|, clamp at 1023 == clamp of v/1023 to [0,1]) and runs conv1 on the
+//     tensor cores: A = v * 2^-10 (exact in fp16), B = hi/lo fp16 split of w * (float)(1/1023) * 2^10, fp32
+//     accumulation in TMEM -- i.e. conv1 at ~fp32 weight precision on exact inputs, output fp16 chunk-planar.
+//   * `stage_kernel` writes the normalised fp32 tensor out for the bit-exactness probe (mlt_debug_stage) with
+//     exactly the reference's fp32 arithmetic; `stage_conv1_kernel` is the fp32 CUDA-core cross-check engine's conv1.
+#include "conv_umma.cuh"
 #include "mlt_internal.h"
 
 namespace mlt {
@@ -124,24 +129,14 @@ __global__ void __launch_bounds__(256) stage_conv1_kernel(const CtuDev *__restri
         }
     }
 
-    // fp16 product path: haloed NHWC [n+1][130][130][32] (conv_umma.cuh); fp32 cross-check path: dense NHWC
-    const size_t pix0 = sizeof(OutT) == 2 ? ((size_t)ctu * 130 + (y0 + row + 1)) * 130 + (x0 + sx + 1)
-                                          : ((size_t)ctu * 128 + (y0 + row)) * 128 + (x0 + sx);
+    // dense NHWC fp32 (cross-check engine only)
+    const size_t pix0 = ((size_t)ctu * 128 + (y0 + row)) * 128 + (x0 + sx);
 #pragma unroll
     for (int px = 0; px < 4; px++) {
         OutT *o = out + (pix0 + px) * 32 + half * 16;
-        if constexpr (sizeof(OutT) == 2) {
-            uint4 v[2];
-            __half2 *h2 = reinterpret_cast<__half2 *>(v);
 #pragma unroll
-            for (int e = 0; e < 8; e++) h2[e] = __floats2half2_rn(acc[px][2 * e], acc[px][2 * e + 1]);
-            reinterpret_cast<uint4 *>(o)[0] = v[0];
-            reinterpret_cast<uint4 *>(o)[1] = v[1];
-        } else {
-#pragma unroll
-            for (int q = 0; q < 4; q++)
-                reinterpret_cast<float4 *>(o)[q] = make_float4(acc[px][4 * q], acc[px][4 * q + 1], acc[px][4 * q + 2], acc[px][4 * q + 3]);
-        }
+        for (int q = 0; q < 4; q++)
+            reinterpret_cast<float4 *>(o)[q] = make_float4(acc[px][4 * q], acc[px][4 * q + 1], acc[px][4 * q + 2], acc[px][4 * q + 3]);
     }
 }
 
@@ -150,33 +145,159 @@ cudaError_t launch_stage(const CtuDev *ctus, int n, float *out, cudaStream_t s)
     stage_kernel<<<n, 256, 0, s>>>(ctus, out);
     return cudaGetLastError();
 }
-cudaError_t launch_stage_conv1_h(const CtuDev *ctus, int n, const float *w, __half *out, cudaStream_t s)
-{
-    stage_conv1_kernel<__half><<<n * 32, 256, 0, s>>>(ctus, w, out);
-    return cudaGetLastError();
-}
 cudaError_t launch_stage_conv1_f(const CtuDev *ctus, int n, const float *w, float *out, cudaStream_t s)
 {
     stage_conv1_kernel<float><<<n * 32, 256, 0, s>>>(ctus, w, out);
     return cudaGetLastError();
 }
 
-// debug: haloed NHWC fp16 [nimg][h+2][h+2][c] -> dense NHWC fp32 [nimg][h][h][c]
-__global__ void unhalo_to_float_kernel(const __half *__restrict__ in, float *__restrict__ out, int h, int c, size_t n)
+// ---------------------------------------------------------------------------------------------------
+// Product path: staging + conv1 on tcgen05.  One CTA = a 16-row x 64-column strip of one CTU = 8 MMA tiles of
+// 16 x 8 pixels (M = 128), all 8 accumulators (8 x 32 columns) live in TMEM at once.
+//   K layout per tile (K = 32, two K=16 MMAs): chunk kh (kh = 0..2) = 8 fp16 = (org, res) of input pixels
+//   x-1 .. x+2 of input row y+kh-1 (the 4th pixel has zero weights); chunk 3 = zero weights.
+//   The expanded patch E[19 rows][64 px][8] sits in shared memory once; the three vertical taps are row-shifted
+//   windows of it (operand descriptor start address), LBO = one patch row.
+// Output: activation 0 in the parity-planar layout (conv_umma.cuh), no bias / BN / ReLU (arch.py:278).
+constexpr int C1_SW = 64, C1_ROWS = 19, C1_IN_COLS = 80; // staged input columns x0-8 .. x0+71 (16-byte aligned loads)
+
+__global__ void __launch_bounds__(256) conv1_umma_kernel(const CtuDev *__restrict__ ctus, const __half *__restrict__ wop,
+                                                        __half *__restrict__ out)
 {
+    __shared__ __align__(128) uint8_t s_e[C1_ROWS * C1_SW * 16];
+    __shared__ __align__(128) uint8_t s_w[2 * 4 * 32 * 16]; // [hi, lo][4 chunks][32 cout][8]
+    __shared__ __align__(16) int16_t s_in[2][18][C1_IN_COLS];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ctu = blockIdx.x >> 4, t = blockIdx.x & 15;
+    const int y0 = (t >> 1) * 16, x0 = (t & 1) * C1_SW;
+    const CtuDev d = ctus[ctu];
+
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    if (warp == 0) { tmem_alloc(&tmem_slot, 256); tmem_relinquish(); }
+    reinterpret_cast<uint4 *>(s_w)[tid] = __ldg(reinterpret_cast<const uint4 *>(wop) + tid); // 256 x 16 B
+    // raw samples: 2 planes x 18 rows x 10 vectors of 8 int16; outside the CTU = conv zero padding (org = pred = 0)
+    for (int i = tid; i < 2 * 18 * 10; i += 256) {
+        const int plane = i / 180, rem = i % 180, row = rem / 10, v = rem % 10;
+        const int y = y0 - 1 + row, x = x0 - 8 + v * 8;
+        uint4 val = make_uint4(0, 0, 0, 0);
+        if (y >= 0 && y < 128 && x >= 0 && x < 128) {
+            const int16_t *src = plane ? d.pred + (size_t)y * d.pred_stride : d.org + (size_t)y * d.org_stride;
+            val = __ldg(reinterpret_cast<const uint4 *>(src + x));
+        }
+        *reinterpret_cast<uint4 *>(&s_in[plane][row][v * 8]) = val;
+    }
+    __syncthreads();
+    // expanded patch: entry (row i, px x) = fp16 {org, res} of input pixels x-1 .. x+2 of input row y0-1+i; row 18 = 0
+    for (int i = tid; i < C1_ROWS * (C1_SW / 4); i += 256) {
+        const int row = i / (C1_SW / 4), xq = (i % (C1_SW / 4)) * 4;
+        uint4 *dst = reinterpret_cast<uint4 *>(s_e + ((size_t)row * C1_SW + xq) * 16);
+        if (row == 18) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) dst[j] = make_uint4(0, 0, 0, 0);
+            continue;
+        }
+        __half2 px[7]; // (org, res) * 2^-10 of input columns x0+xq-1 .. x0+xq+5
+#pragma unroll
+        for (int j = 0; j < 7; j++) {
+            const uint32_t o = (uint16_t)s_in[0][row][8 + xq - 1 + j], pp = (uint16_t)s_in[1][row][8 + xq - 1 + j];
+            const uint32_t vo = o < 1023u ? o : 1023u;        // clamp(v / 1023, 0, 1) == min(v, 1023) / 1023 (EncCu.cpp:848-867)
+            const uint32_t ad = absdiff_u16(o, pp);
+            const uint32_t vr = ad < 1023u ? ad : 1023u;
+            px[j] = __floats2half2_rn((float)vo * 0.0009765625f, (float)vr * 0.0009765625f); // exact: <= 10 significant bits
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uint4 v;
+            __half2 *h2 = reinterpret_cast<__half2 *>(&v);
+            h2[0] = px[j]; h2[1] = px[j + 1]; h2[2] = px[j + 2]; h2[3] = px[j + 3];
+            dst[j] = v;
+        }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    if (warp == 0) {
+        if (elect_one_sync()) {
+            constexpr uint32_t idesc = umma_idesc_f16(128, 32);
+            constexpr uint32_t a_hi = umma_desc_hi(C1_SW * 16), b_hi = umma_desc_hi(128);
+            const uint32_t sE = smem_u32(s_e), sW = smem_u32(s_w);
+#pragma unroll
+            for (int tile = 0; tile < 8; tile++) {
+                const uint32_t a0 = umma_desc_lo(sE + tile * 128, C1_SW * 16);                    // chunks kh = 0, 1
+                const uint32_t a2 = umma_desc_lo(sE + 2 * C1_SW * 16 + tile * 128, C1_SW * 16);   // chunks kh = 2, (3: zero weights)
+#pragma unroll
+                for (int part = 0; part < 2; part++) { // hi, lo halves of the weights
+                    const uint32_t b0 = umma_desc_lo(sW + part * 2048, 32 * 16), b2 = umma_desc_lo(sW + part * 2048 + 1024, 32 * 16);
+                    umma_f16(tmem + tile * 32, umma_desc_pack(a0, a_hi), umma_desc_pack(b0, b_hi), idesc, part);
+                    umma_f16(tmem + tile * 32, umma_desc_pack(a2, a_hi), umma_desc_pack(b2, b_hi), idesc, 1);
+                }
+            }
+            umma_commit(&bar);
+        }
+        __syncwarp();
+    }
+    mbar_wait(&bar, 0);
+    tc_fence_after();
+    // epilogue: warp w reads TMEM lane quadrant w % 4 (pixels), tiles (w / 4) * 4 .. + 3
+    {
+        const int wq = warp & 3, m = wq * 32 + lane, r = m >> 3, c = m & 7;
+        const int oy = y0 + r;
+        constexpr size_t CHUNK = 64 * 64 * 8, PLANE = CHUNK * 4, UNIT = PLANE * 4; // a0: [ctu][4 planes][4 chunks][64][64][8]
+#pragma unroll 1
+        for (int tile = (warp >> 2) * 4; tile < (warp >> 2) * 4 + 4; tile++) {
+            uint32_t v[32];
+            tmem_ld32(tmem + ((uint32_t)(wq * 32) << 16) + tile * 32, v);
+            tmem_ld_wait();
+            const int ox = x0 + tile * 8 + c;
+            __half *op = out + (size_t)ctu * UNIT + (size_t)((oy & 1) * 2 + (ox & 1)) * PLANE + (size_t)((oy >> 1) * 64 + (ox >> 1)) * 8;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                uint4 ov;
+                __half2 *h2 = reinterpret_cast<__half2 *>(&ov);
+#pragma unroll
+                for (int e = 0; e < 4; e++) h2[e] = __floats2half2_rn(__uint_as_float(v[q * 8 + e * 2]), __uint_as_float(v[q * 8 + e * 2 + 1]));
+                *reinterpret_cast<uint4 *>(op + (size_t)q * CHUNK) = ov;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 256); }
+}
+
+cudaError_t launch_conv1_umma(const CtuDev *ctus, int n, const __half *wop, __half *out, cudaStream_t s)
+{
+    conv1_umma_kernel<<<n * 16, 256, 0, s>>>(ctus, wop, out);
+    return cudaGetLastError();
+}
+
+// debug: chunk-planar fp16 activation (conv_umma.cuh ActLayout) -> dense NHWC fp32 [nimg][h][h][c]
+__global__ void unpack_act_kernel(const __half *__restrict__ in, float *__restrict__ out, ActLayout L, size_t n)
+{
+    const int h = L.H, c = L.C;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const int ch = (int)(i % c);
         const size_t pix = i / c;
         const int x = (int)(pix % h), y = (int)((pix / h) % h);
         const size_t img = pix / ((size_t)h * h);
-        out[i] = __half2float(in[((img * (h + 2) + y + 1) * (h + 2) + x + 1) * c + ch]);
+        const size_t unit = L.pair ? img >> 1 : img;
+        const int sub = L.pair ? (int)(img & 1) : 0, plane = L.par ? (y & 1) * 2 + (x & 1) : 0;
+        const int yy = L.par ? y >> 1 : y, xx = L.par ? x >> 1 : x, hp = L.hp();
+        const size_t off = (unit * L.npl() + plane) * (size_t)(c / 8) * L.chunk_stride() + (size_t)(ch / 8) * L.chunk_stride() +
+                           (size_t)((yy * L.nimg() + sub) * hp + xx) * 8 + (ch & 7);
+        out[i] = __half2float(in[off]);
     }
 }
-cudaError_t launch_unhalo_to_float(const __half *in, float *out, int nimg, int h, int c, cudaStream_t s)
+cudaError_t launch_unpack_act(const __half *in, float *out, int nimg, const ActLayout &L, cudaStream_t s)
 {
-    const size_t n = (size_t)nimg * h * h * c;
+    const size_t n = (size_t)nimg * L.H * L.H * L.C;
     const int blocks = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
-    unhalo_to_float_kernel<<<blocks > 0 ? blocks : 1, 256, 0, s>>>(in, out, h, c, n);
+    unpack_act_kernel<<<blocks > 0 ? blocks : 1, 256, 0, s>>>(in, out, L, n);
     return cudaGetLastError();
 }
 

@@ -11,6 +11,9 @@ What it does
   * writes the folded 3x3 / 1x1 conv weights as fp16 in the tcgen05 shared-memory operand layout used by
     csrc/conv_umma.cuh: K-major, no-swizzle core matrices, [cin_group][tap][G/8][Cout][8] so that every
     (cin_group, tap) slab is one contiguous bulk copy;
+  * writes, for the second conv of every BasicBlock, the extra K-slab operand [xc/gx][gx/8][Cout][8]: the folded
+    1x1 stride-2 shortcut weights, or the identity matrix for an identity residual;
+  * writes conv1 as a tcgen05 operand with the staging scale folded in (conv1_operand);
   * writes each conv's (shortcut-fused) bias as a K=16 fp16 operand (hi/lo split) that one extra MMA adds
     into the accumulator;
   * writes fp32 copies ([tap][Cin][Cout]) for the fp32 CUDA-core cross-check engine, the fp32 biases, the
@@ -26,22 +29,24 @@ import sys
 import numpy as np
 
 MAGIC = 0x57544C4D  # "MLTW"
-VERSION = 1
+VERSION = 2
 ARCH_CTU128 = 128
 BN_EPS = 1e-5
 PLANES = (32, 64, 128, 256)
 
 SEC_CONV1_F32 = 0x001
+SEC_CONV1_UMMA = 0x002
 SEC_W_F16 = 0x100
 SEC_BIAS_FUSED = 0x200
 SEC_W_F32 = 0x300
 SEC_BIAS = 0x400
-SEC_SC_W_F16 = 0x500
 SEC_SC_W_F32 = 0x600
 SEC_SC_BIAS = 0x700
 SEC_BIAS_MMA = 0xA00
 SEC_FC_W = 0x800
 SEC_FC_B = 0x900
+SEC_X_W_F16 = 0xB00
+ALPHA = np.float32(1.0 / 1023)  # (float)(1.0/1023), bits 0x3A802008: cv::Mat::convertTo's alpha at EncCu.cpp:835-838
 
 
 def conv_table():
@@ -106,6 +111,31 @@ def bias_operand(b: np.ndarray) -> np.ndarray:
     return out
 
 
+def conv1_operand(w: np.ndarray) -> np.ndarray:
+    """conv1 OIHW fp32 [32][2][3][3] -> fp16 tcgen05 B operand [hi, lo][4 chunks][32 cout][8] (csrc/stage_conv1.cu).
+
+    chunk kh (0..2), element dx*2 + ch = w[cout][ch][kh][dx] * alpha * 2^10 for dx < 3, else 0; chunk 3 = 0.
+    The A operand is the integer sample * 2^-10 (exact in fp16), so A x (hi + lo) reproduces
+    w * (v * (float)(1/1023)) to ~2^-22 relative -- the staging multiply is folded into the weights."""
+    ws = w.astype(np.float64) * float(ALPHA) * 1024.0
+    op = np.zeros((4, 32, 8), np.float64)
+    for kh in range(3):
+        for dx in range(3):
+            for ch in range(2):
+                op[kh, :, dx * 2 + ch] = ws[:, ch, kh, dx]
+    hi = op.astype(np.float16)
+    lo = (op - hi.astype(np.float64)).astype(np.float16)
+    return np.stack([hi, lo], 0)
+
+
+def extra_operand(ws: np.ndarray, gx: int) -> np.ndarray:
+    """[cout][xc] fp32 (folded 1x1 shortcut weights, or the identity) -> fp16 [xc/gx][gx/8][cout][8]."""
+    cout, xc = ws.shape
+    assert xc % gx == 0 and gx % 16 == 0
+    t = ws.reshape(cout, xc // gx, gx // 8, 8).transpose(1, 2, 0, 3)
+    return np.ascontiguousarray(t).astype(np.float16)
+
+
 def build_sections(sd: dict) -> list:
     sd = normalise_state_dict(sd)
     secs = []
@@ -115,6 +145,7 @@ def build_sections(sd: dict) -> list:
 
     w = sd["conv1.weight"].astype(np.float32)  # [32][2][3][3], no BN / bias
     add(SEC_CONV1_F32, w.transpose(2, 3, 1, 0).reshape(9, 2, 32), np.float32)
+    add(SEC_CONV1_UMMA, conv1_operand(w), np.float16)
     for li, (prefix, cin, cout, stride, hout, group, sc) in enumerate(conv_table()):
         bn = prefix.replace("conv", "bn")
         wf, bf = fold_bn(sd[f"{prefix}.weight"], sd, bn)
@@ -127,10 +158,13 @@ def build_sections(sd: dict) -> list:
             sp = prefix.rsplit(".", 1)[0] + ".shortcut"
             ws, bs = fold_bn(sd[f"{sp}.0.weight"], sd, f"{sp}.1")
             csc = ws.shape[1]
-            add(SEC_SC_W_F16 + sc, pack_umma_b(ws, csc), np.float16)
+            add(SEC_X_W_F16 + li, extra_operand(ws.reshape(cout, csc), min(csc, group)), np.float16)
             add(SEC_SC_W_F32 + sc, ws.reshape(cout, csc).T, np.float32)
             add(SEC_SC_BIAS + sc, bs, np.float32)
             fused = (bf.astype(np.float32) + bs.astype(np.float32)).astype(np.float32)
+        elif li & 1:
+            # identity residual of the second block (arch.py:44-57): one more K-slab with Wx = I, exact in fp16
+            add(SEC_X_W_F16 + li, extra_operand(np.eye(cout, dtype=np.float32), min(cout, group)), np.float16)
         add(SEC_BIAS_FUSED + li, fused, np.float32)
         add(SEC_BIAS_MMA + li, bias_operand(fused), np.float16)
     for i in range(3):
@@ -170,7 +204,7 @@ def read_sections(path: str) -> dict:
     raw = open(path, "rb").read()
     magic, ver, arch, nsec, total, _ = struct.unpack_from("<IIIIQQ", raw, 0)
     if magic != MAGIC or ver != VERSION or arch != ARCH_CTU128 or total != len(raw):
-        raise ValueError("not an MLTW v1 blob for the 128x128 CTU model")
+        raise ValueError("not an MLTW v2 blob for the 128x128 CTU model")
     out = {}
     for i in range(nsec):
         sid, dt, off, nb = struct.unpack_from("<IIQQ", raw, 32 + 24 * i)

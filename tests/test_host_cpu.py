@@ -56,8 +56,28 @@ def test_blob_roundtrip_and_operand_layout(sd):
         fused = secs[pw.SEC_BIAS_FUSED + li]
         assert np.abs(bias_op[0, :, 0] + bias_op[0, :, 1] - fused).max() < 1e-6  # hi + lo split is ~fp32 exact
         assert not bias_op[1].any() and not bias_op[0, :, 2:].any()
-        if sc >= 0:
-            assert secs[pw.SEC_SC_W_F16 + sc].size == table[li - 1][1] * cout
+        if li & 1:  # second conv of a block: extra K-slab operand = folded shortcut weights, or the identity
+            xc = table[li - 1][1] if sc >= 0 else cout
+            gx = min(xc, group)
+            xop = secs[pw.SEC_X_W_F16 + li].reshape(xc // gx, gx // 8, cout, 8).astype(np.float32)
+            dense = xop.transpose(2, 0, 1, 3).reshape(cout, xc)  # [cout][xc]
+            if sc >= 0:
+                sp = prefix.rsplit(".", 1)[0] + ".shortcut"
+                ws, _ = pw.fold_bn(sd[f"{sp}.0.weight"], sd, f"{sp}.1")
+                assert np.array_equal(dense, ws.reshape(cout, xc).astype(np.float16).astype(np.float32))
+            else:
+                assert np.array_equal(dense, np.eye(cout, dtype=np.float32))
+        else:
+            assert (pw.SEC_X_W_F16 + li) not in secs
+    # conv1 as a tcgen05 operand: hi + lo reproduces w * (float)(1/1023) * 2^10; 4th pixel and 4th chunk are zero
+    c1 = secs[pw.SEC_CONV1_UMMA].reshape(2, 4, 32, 8).astype(np.float64)
+    w1 = sd["conv1.weight"].astype(np.float64) * float(np.float32(1.0 / 1023)) * 1024.0
+    for kh in range(3):
+        for dx in range(3):
+            for ch in range(2):
+                got = c1[0, kh, :, dx * 2 + ch] + c1[1, kh, :, dx * 2 + ch]
+                assert np.abs(got - w1[:, ch, kh, dx]).max() <= np.abs(w1).max() * 2.0 ** -20
+    assert not c1[:, 3].any() and not c1[:, :, :, 6:].any()
     # 'params' wrapper and 'module.' prefixes (model2torchScript.py:23-32) are accepted
     wrapped = {"params": {"module." + k: v for k, v in sd.items()}}
     assert pw.pack(wrapped) == pw.pack(sd)
