@@ -8,7 +8,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["api.cu", "conv_umma.cu", "conv_simt.cu", "stage_conv1.cu", "head.cu"]
+SOURCES = ["api.cu", "conv_umma.cu", "stem_umma.cu", "conv_simt.cu", "stage_conv1.cu", "head.cu"]
 LIB = os.path.join(HERE, "libmltcnn.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -16,7 +16,7 @@ namespace {
 
 constexpr uint32_t MLTW_MAGIC = 0x57544C4Du;
 enum : uint32_t {
-    SEC_CONV1_F32 = 0x001, SEC_CONV1_UMMA = 0x002, SEC_W_F16 = 0x100, SEC_BIAS_FUSED = 0x200, SEC_W_F32 = 0x300, SEC_BIAS = 0x400,
+    SEC_CONV1_F32 = 0x001, SEC_CONV1_UMMA = 0x002, SEC_STEM_CONV1 = 0x003, SEC_W_F16 = 0x100, SEC_BIAS_FUSED = 0x200, SEC_W_F32 = 0x300, SEC_BIAS = 0x400,
     SEC_SC_W_F16 = 0x500, SEC_SC_W_F32 = 0x600, SEC_SC_BIAS = 0x700, SEC_FC_W = 0x800, SEC_FC_B = 0x900, SEC_BIAS_MMA = 0xA00, SEC_X_W_F16 = 0xB00
 };
 
@@ -55,11 +55,14 @@ struct Section { const uint8_t *dev = nullptr; size_t bytes = 0; };
 
 struct mlt_ctx {
     int device = 0, max_batch = 0, engine = 0, num_sms = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    static constexpr int MAX_CHUNKS = 8;
+    cudaEvent_t ev_in[MAX_CHUNKS] = {}; // "chunk i of the input batch has landed in HBM"
     uint8_t *d_blob = nullptr;
     size_t blob_bytes = 0;
     Section sec[0x1000];
-    __half *act_h[NACT] = {};
+    __half *act_h[NACT] = {}; // [0] (conv1's full output, parity-planar) exists only for the unfused engine / debug reads
+    __half *act0q = nullptr;  // conv1's output at even rows / columns (input of layer0.0's shortcut), dense [n][4][64][64][8]
     ConvParams conv_p[NCONV]; // tensor maps + weight pointers of every tcgen05 conv, built once at create
     float *act_f[NACT] = {};
     float *scratch_f = nullptr; // shortcut-conv output of the fp32 engine
@@ -133,7 +136,7 @@ int load_blob(mlt_ctx *c, const char *path)
     }
     // every section this architecture needs must be present with the exact size
     auto need = [&](uint32_t id, size_t bytes) { return c->sec[id].dev != nullptr && c->sec[id].bytes == bytes; };
-    bool ok = need(SEC_CONV1_F32, 9 * 2 * 32 * 4) && need(SEC_CONV1_UMMA, 2 * 4 * 32 * 16);
+    bool ok = need(SEC_CONV1_F32, 9 * 2 * 32 * 4) && need(SEC_CONV1_UMMA, 2 * 4 * 32 * 16) && need(SEC_STEM_CONV1, 8 * 1024);
     for (int li = 0; li < NCONV && ok; li++) {
         const LayerDesc &L = kLayers[li];
         ok = need(SEC_W_F16 + li, (size_t)9 * L.cin * L.cout * 2) && need(SEC_W_F32 + li, (size_t)9 * L.cin * L.cout * 4) &&
@@ -176,6 +179,25 @@ int ensure_dbg(mlt_ctx *c, size_t bytes)
     return MLT_OK;
 }
 
+int ensure_act0(mlt_ctx *c) // conv1's full output: only the unfused engine and debug reads materialise it
+{
+    if (c->act_h[0]) return MLT_OK;
+    const ActLayout L = act_layout(0);
+    const size_t bytes = L.unit_elems() * L.units_for(c->max_batch) * sizeof(__half);
+    CU(cudaMalloc(&c->act_h[0], bytes));
+    CU(cudaMemset(c->act_h[0], 0, bytes));
+    if (c->conv_p[0].out == nullptr) {
+        ConvParams &p = c->conv_p[0];
+        CU(conv_umma_prepare(0, &p, c->act_h[0], L, nullptr, nullptr, (size_t)c->max_batch));
+        p.w = secp<__half>(c, SEC_W_F16 + 0);
+        p.bias = secp<__half>(c, SEC_BIAS_MMA + 0);
+        p.x_w = nullptr;
+        p.out = c->act_h[1];
+        p.relu = 1;
+    }
+    return MLT_OK;
+}
+
 __global__ void dense_descs_kernel(CtuDev *ctus, const int16_t *orgpred, const int32_t *pocqp, int n)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -195,15 +217,30 @@ int run_network(mlt_ctx *c, const CtuDev *ctus, int n, mlt_result *out, cudaStre
     HeadParams hp;
     hp.ctus = ctus; hp.out = out; hp.n = n;
     for (int i = 0; i < 3; i++) { hp.fc_w[i] = secp<float>(c, SEC_FC_W + i); hp.fc_b[i] = secp<float>(c, SEC_FC_B + i); }
-    if (c->engine == 0) {
-        // ---- product path: fused staging+conv1, 16 tcgen05 implicit-GEMM convs, head
+    if (c->engine != 1) {
+        // ---- product path: fused stem (staging + conv1 + layer0.0.conv1), 15 tcgen05 implicit-GEMM convs, head
         const bool prof = c->profiling;
         int ev = 0;
         if (prof) { CU(cudaEventRecord(c->prof_ev[ev++], s)); c->prof_stream = s; c->prof_valid = false; }
-        CU(launch_conv1_umma(ctus, n, secp<__half>(c, SEC_CONV1_UMMA), c->act_h[0], s));
-        c->launches++;
-        if (prof) CU(cudaEventRecord(c->prof_ev[ev++], s));
-        for (int li = 0; li < NCONV; li++) {
+        int first = 0;
+        if (c->engine == 0) {
+            // fused stem: staging + conv1 + layer0.0.conv1; conv1's 1 MiB / CTU output never reaches HBM
+            CU(launch_stem_umma(ctus, n, secp<__half>(c, SEC_STEM_CONV1), secp<__half>(c, SEC_W_F16 + 0), secp<__half>(c, SEC_BIAS_MMA + 0),
+                                c->act0q, c->act_h[1], c->num_sms, s));
+            c->launches++;
+            if (prof) { CU(cudaEventRecord(c->prof_ev[ev++], s)); CU(cudaEventRecord(c->prof_ev[ev++], s)); }
+            first = 1;
+        } else {
+            // unfused tcgen05 engine (cross-check of the stem): standalone conv1, its even/even quarter copied out
+            int rc = ensure_act0(c);
+            if (rc) return rc;
+            CU(launch_conv1_umma(ctus, n, secp<__half>(c, SEC_CONV1_UMMA), c->act_h[0], s));
+            c->launches++;
+            const size_t q = (size_t)4 * 64 * 64 * 8 * sizeof(__half);
+            CU(cudaMemcpy2DAsync(c->act0q, q, c->act_h[0], 4 * q, q, n, cudaMemcpyDeviceToDevice, s));
+            if (prof) CU(cudaEventRecord(c->prof_ev[ev++], s));
+        }
+        for (int li = first; li < NCONV; li++) {
             ConvParams &p = c->conv_p[li];
             p.nimg = n;
             CU(launch_conv_umma(li, p, c->num_sms, s));
@@ -280,6 +317,36 @@ int run_host_batch(mlt_ctx *c, int n, mlt_result *out, bool upload_in)
     return MLT_OK;
 }
 
+// Host batch of n CTUs, pipelined: chunk i+1 is staged / copied (copy stream) while chunk i computes (compute stream).
+// `src` != nullptr: dense caller buffer, copied straight from it (pinned or pageable, no intermediate host copy);
+// otherwise `descs` are gathered chunk by chunk into the pinned staging buffer first.
+int run_host_batch_chunked(mlt_ctx *c, int n, const int16_t *src, const mlt_ctu_desc *descs, const int32_t *pocqp, mlt_result *out)
+{
+    cudaStream_t s = c->stream;
+    dense_descs(c, n, pocqp, descs);
+    CU(cudaMemcpyAsync(c->d_ctus, c->h_ctus, (size_t)n * sizeof(CtuDev), cudaMemcpyHostToDevice, s));
+    const int nchunks = n >= 1024 ? (n / 512 < mlt_ctx::MAX_CHUNKS ? n / 512 : mlt_ctx::MAX_CHUNKS) : 1;
+    const int per = (n + nchunks - 1) / nchunks;
+    for (int i = 0, off = 0; off < n; i++, off += per) {
+        const int m = n - off < per ? n - off : per;
+        const int16_t *from = src ? src + (size_t)off * CTU_IN_ELEMS : c->h_in + (size_t)off * CTU_IN_ELEMS;
+        if (!src)
+            for (int k = off; k < off + m; k++)
+                gather_ctu(c->h_in + (size_t)k * CTU_IN_ELEMS, descs[k].org, descs[k].org_stride, descs[k].pred, descs[k].pred_stride);
+        CU(cudaMemcpyAsync(c->d_in + (size_t)off * CTU_IN_ELEMS, from, (size_t)m * CTU_IN_ELEMS * sizeof(int16_t),
+                           cudaMemcpyHostToDevice, c->copy_stream));
+        CU(cudaEventRecord(c->ev_in[i], c->copy_stream));
+        CU(cudaStreamWaitEvent(s, c->ev_in[i], 0));
+        const int rc = run_network(c, c->d_ctus + off, m, c->d_out + off, s);
+        if (rc) { cudaStreamSynchronize(c->copy_stream); return rc; }
+    }
+    c->last_n = n <= per ? n : 0; // debug_activation only sees a whole batch when it ran as one chunk
+    CU(cudaMemcpyAsync(c->h_out, c->d_out, (size_t)n * sizeof(mlt_result), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    memcpy(out, c->h_out, (size_t)n * sizeof(mlt_result));
+    return MLT_OK;
+}
+
 int check_ctx(mlt_ctx *c)
 {
     if (!c) return MLT_E_INVAL;
@@ -322,9 +389,11 @@ void mlt_destroy(mlt_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (int a = 0; a < NACT; a++) { cudaFree(c->act_h[a]); cudaFree(c->act_f[a]); }
     cudaFree(c->scratch_f); cudaFree(c->d_blob); cudaFree(c->d_in); cudaFree(c->d_ctus); cudaFree(c->d_out);
-    cudaFree(c->d_dbg); cudaFree(c->d_pic);
+    cudaFree(c->d_dbg); cudaFree(c->d_pic); cudaFree(c->act0q);
     cudaFreeHost(c->h_in); cudaFreeHost(c->h_ctus); cudaFreeHost(c->h_out);
     for (cudaEvent_t e : c->prof_ev) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->ev_in) if (e) cudaEventDestroy(e);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -349,30 +418,34 @@ int mlt_create_ex(mlt_ctx **out, const char *weights_path, int cuda_device, int 
     auto body = [&]() -> int {
         CU(cudaSetDevice(cuda_device));
         CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (cudaEvent_t &e : c->ev_in) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         int r = load_blob(c, weights_path);
         if (r) return r;
         CU(conv_umma_init());
-        for (int a = 0; a < NACT; a++) {
+        CU(stem_umma_init());
+        for (int a = 1; a < NACT; a++) {
             // zeroed once: the unused half of the last image pair of an odd batch must stay finite
             const ActLayout L = act_layout(a);
             const size_t bytes = L.unit_elems() * L.units_for(max_batch) * sizeof(__half);
             CU(cudaMalloc(&c->act_h[a], bytes));
             CU(cudaMemsetAsync(c->act_h[a], 0, bytes, c->stream));
         }
-        for (int li = 0; li < NCONV; li++) {
-            const LayerDesc &L = kLayers[li];
+        const ActLayout l0q{64, 32, 0, 0};
+        CU(cudaMalloc(&c->act0q, l0q.unit_elems() * (size_t)max_batch * sizeof(__half)));
+        memset(c->conv_p, 0, sizeof c->conv_p);
+        for (int li = 1; li < NCONV; li++) { // conv 0 runs inside the stem kernel (ensure_act0 prepares it for the unfused engine)
             ConvParams &p = c->conv_p[li];
-            memset(&p, 0, sizeof p);
             const bool conv2 = (li & 1) != 0;
             const int xa = li & ~1; // input of the BasicBlock this conv belongs to
-            const ActLayout in_l = act_layout(li), x_l = act_layout(xa);
-            CU(conv_umma_prepare(li, &p, c->act_h[li], in_l, conv2 ? c->act_h[xa] : nullptr, conv2 ? &x_l : nullptr, (size_t)max_batch));
+            const ActLayout in_l = act_layout(li), x_l = xa == 0 ? l0q : act_layout(xa);
+            const __half *xp = xa == 0 ? c->act0q : c->act_h[xa];
+            CU(conv_umma_prepare(li, &p, c->act_h[li], in_l, conv2 ? xp : nullptr, conv2 ? &x_l : nullptr, (size_t)max_batch));
             p.w = secp<__half>(c, SEC_W_F16 + li);
             p.bias = secp<__half>(c, SEC_BIAS_MMA + li);
             p.x_w = conv2 ? secp<__half>(c, SEC_X_W_F16 + li) : nullptr;
             p.out = c->act_h[li + 1];
             p.relu = 1;
-            (void)L;
         }
         CU(cudaStreamSynchronize(c->stream));
         CU(cudaMalloc(&c->d_in, (size_t)max_batch * CTU_IN_ELEMS * sizeof(int16_t)));
@@ -402,7 +475,7 @@ int mlt_set_engine(mlt_ctx *c, int engine)
 {
     int rc = check_ctx(c);
     if (rc) return rc;
-    if (engine != 0 && engine != 1) return fail(c, MLT_E_INVAL, "engine must be 0 (tcgen05) or 1 (fp32 cross-check)");
+    if (engine < 0 || engine > 2) return fail(c, MLT_E_INVAL, "engine must be 0 (tcgen05), 1 (fp32 cross-check) or 2 (tcgen05, unfused stem)");
     c->engine = engine;
     return MLT_OK;
 }
@@ -439,12 +512,9 @@ int mlt_predict_batch(mlt_ctx *c, int n, const mlt_ctu_desc *descs, mlt_result *
     if (n < 0 || (n > 0 && (!descs || !out))) return fail(c, MLT_E_INVAL, "null argument");
     if (n > c->max_batch) return fail(c, MLT_E_BATCH, "n=%d > max_batch=%d", n, c->max_batch);
     if (n == 0) return MLT_OK;
-    for (int i = 0; i < n; i++) {
+    for (int i = 0; i < n; i++)
         if (!descs[i].org || !descs[i].pred) return fail(c, MLT_E_INVAL, "descs[%d]: null org/pred", i);
-        gather_ctu(c->h_in + (size_t)i * CTU_IN_ELEMS, descs[i].org, descs[i].org_stride, descs[i].pred, descs[i].pred_stride);
-    }
-    dense_descs(c, n, nullptr, descs);
-    return run_host_batch(c, n, out, true);
+    return run_host_batch_chunked(c, n, nullptr, descs, nullptr, out);
 }
 
 int mlt_predict_ctu(mlt_ctx *c, const int16_t *org, int org_stride, const int16_t *pred, int pred_stride, int poc, int qp,
@@ -462,11 +532,7 @@ int mlt_predict_batch_dense(mlt_ctx *c, int n, const int16_t *orgpred, const int
     if (n < 0 || (n > 0 && (!orgpred || !pocqp || !out))) return fail(c, MLT_E_INVAL, "null argument");
     if (n > c->max_batch) return fail(c, MLT_E_BATCH, "n=%d > max_batch=%d", n, c->max_batch);
     if (n == 0) return MLT_OK;
-    cudaStream_t s = c->stream;
-    // straight from the caller's buffer (pinned or pageable): no intermediate host copy
-    CU(cudaMemcpyAsync(c->d_in, orgpred, (size_t)n * CTU_IN_ELEMS * sizeof(int16_t), cudaMemcpyHostToDevice, s));
-    dense_descs(c, n, pocqp, nullptr);
-    return run_host_batch(c, n, out, false);
+    return run_host_batch_chunked(c, n, orgpred, nullptr, pocqp, out);
 }
 
 int mlt_predict_batch_device(mlt_ctx *c, int n, const int16_t *d_orgpred, const int32_t *d_pocqp, mlt_result *d_out,
@@ -561,9 +627,15 @@ int64_t mlt_debug_activation(mlt_ctx *c, int layer, float *out, int64_t capacity
     const size_t elems = act_elems(layer) * c->last_n;
     if ((int64_t)elems > capacity) return fail(c, MLT_E_INVAL, "capacity %lld < %zu", (long long)capacity, elems);
     cudaStream_t s = c->stream;
-    if (c->engine == 0) {
+    if (c->engine != 1) {
         rc = ensure_dbg(c, elems * sizeof(float));
         if (rc) return rc;
+        if (layer == 0 && c->engine == 0) {
+            // the fused stem never materialises conv1's output: recompute it for the last batch with the standalone kernel
+            rc = ensure_act0(c);
+            if (rc) return rc;
+            CU(launch_conv1_umma(c->d_ctus, c->last_n, secp<__half>(c, SEC_CONV1_UMMA), c->act_h[0], s));
+        }
         CU(launch_unpack_act(c->act_h[layer], c->d_dbg, c->last_n, act_layout(layer), s));
         CU(cudaMemcpyAsync(out, c->d_dbg, elems * sizeof(float), cudaMemcpyDeviceToHost, s));
     } else {

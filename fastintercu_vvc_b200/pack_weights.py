@@ -36,6 +36,7 @@ PLANES = (32, 64, 128, 256)
 
 SEC_CONV1_F32 = 0x001
 SEC_CONV1_UMMA = 0x002
+SEC_STEM_CONV1 = 0x003
 SEC_W_F16 = 0x100
 SEC_BIAS_FUSED = 0x200
 SEC_W_F32 = 0x300
@@ -128,6 +129,23 @@ def conv1_operand(w: np.ndarray) -> np.ndarray:
     return np.stack([hi, lo], 0)
 
 
+def stem_conv1_operand(w: np.ndarray) -> np.ndarray:
+    """conv1 for the fused stem kernel (csrc/stem_umma.cu): fp16 [py][hi, lo][a, b][2 chunks][32 cout][8].
+
+    Same chunks as conv1_operand (chunk kh = one kernel row, scale folded in), arranged as the two K=16 MMAs the
+    stem issues per output row parity py:  py = 0: a = [kh0 | 0], b = [kh1 | kh2];  py = 1: a = [kh0 | kh1], b = [kh2 | 0]."""
+    c = conv1_operand(w)  # [hi, lo][4 chunks][32][8]; chunk 3 = 0
+    z = 3
+    order = (((0, z), (1, 2)), ((0, 1), (2, z)))
+    out = np.zeros((2, 2, 2, 2, 32, 8), np.float16)
+    for py in range(2):
+        for part in range(2):
+            for ab in range(2):
+                for k in range(2):
+                    out[py, part, ab, k] = c[part, order[py][ab][k]]
+    return out
+
+
 def extra_operand(ws: np.ndarray, gx: int) -> np.ndarray:
     """[cout][xc] fp32 (folded 1x1 shortcut weights, or the identity) -> fp16 [xc/gx][gx/8][cout][8]."""
     cout, xc = ws.shape
@@ -146,6 +164,7 @@ def build_sections(sd: dict) -> list:
     w = sd["conv1.weight"].astype(np.float32)  # [32][2][3][3], no BN / bias
     add(SEC_CONV1_F32, w.transpose(2, 3, 1, 0).reshape(9, 2, 32), np.float32)
     add(SEC_CONV1_UMMA, conv1_operand(w), np.float16)
+    add(SEC_STEM_CONV1, stem_conv1_operand(w), np.float16)
     for li, (prefix, cin, cout, stride, hout, group, sc) in enumerate(conv_table()):
         bn = prefix.replace("conv", "bn")
         wf, bf = fold_bn(sd[f"{prefix}.weight"], sd, bn)

@@ -161,6 +161,32 @@ def test_tcgen05_layers_vs_fp32_engine(pred, ctus):
     assert worst > 0  # the two engines really are different arithmetic
 
 
+def test_fused_stem_matches_unfused_tcgen05_engine(pred, ctus):
+    """Product path (staging + conv1 + layer0.0.conv1 fused in one kernel, conv1 output kept on chip) vs the unfused
+    tcgen05 engine (standalone conv1 kernel + the generic conv kernel): same arithmetic up to fp32 summation order."""
+    orgpred, pocqp = ctus
+    n = 5
+    batch = as_list(orgpred[:n], pocqp[:n])
+    pred.set_engine(2)
+    try:
+        ref = pred.predict_batch(batch)
+        ref_act1 = pred.debug_activation(1, n)
+        ref_act2 = pred.debug_activation(2, n)
+    finally:
+        pred.set_engine(0)
+    got = pred.predict_batch(batch)
+    act1 = pred.debug_activation(1, n)
+    act2 = pred.debug_activation(2, n)
+    e1 = np.abs(act1 - ref_act1).max() / np.abs(ref_act1).max()
+    e2 = np.abs(act2 - ref_act2).max() / np.abs(ref_act2).max()
+    dl = np.abs(got["logits"] - ref["logits"]).max()
+    print(f"fused vs unfused stem: act1 {e1:.2e}, act2 (uses the shortcut quarter of conv1) {e2:.2e}, max|dlogit| {dl:.2e}")
+    assert e1 < 2e-3 and e2 < 2e-3  # at most an fp16 ulp here and there
+    assert (act1 != ref_act1).mean() < 0.02
+    assert dl < 2e-3
+    assert np.array_equal(got["split_l3"], ref["split_l3"])
+
+
 def test_tcgen05_matches_reference_golden(pred, ctus):
     """Product path vs logits of the reference's own arch file (tests/golden/logits_seed10.npz)."""
     gold = np.load(os.path.join(GOLD, "logits_seed10.npz"))
