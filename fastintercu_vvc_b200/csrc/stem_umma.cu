@@ -38,7 +38,7 @@ constexpr int EP_BYTES = 4 * EP_ARR;                       // 19,584
 constexpr int RAW_COLS = 48, RAW_ROWS = 35;
 constexpr int RAW_BYTES = RAW_ROWS * RAW_COLS * 4;         // 6,720: fp16 {org, res} pair per pixel of the input window
 constexpr int W0_BYTES = 9 * 32 * 32 * 2;                  // layer0.0.conv1 weights, resident
-constexpr int W1_BYTES = 8 * 1024;                         // conv1 operand variants [py][hi,lo][a,b][2 chunks][32][8]
+constexpr int W1_BYTES = 6 * 1024;                         // conv1 operand variants [py][3 MMAs][2 chunks][32][8]
 constexpr int BIAS_BYTES = 32 * 32, ONES_BYTES = 2 * 128 * 16;
 constexpr int OFF_PATCH = 0;
 constexpr int OFF_EP = OFF_PATCH + 2 * PATCH_BYTES;
@@ -48,7 +48,7 @@ constexpr int OFF_W1 = OFF_W0 + W0_BYTES;
 constexpr int OFF_BIAS = OFF_W1 + W1_BYTES;
 constexpr int OFF_ONES = OFF_BIAS + BIAS_BYTES;
 constexpr int OFF_BAR = OFF_ONES + ONES_BYTES;
-constexpr int NBAR = 2 + 2 + 12 + 12 + 2 + 2 + 2 + 2;
+constexpr int NBAR = 2 + 2 + 12 + 4 + 2 + 2 + 2 + 2;
 constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16;
 constexpr int TM_C1 = 0, TM_D = 384; // TMEM columns
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(stem::NTHREADS, 1) stem_umma_kernel(const Stem
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + OFF_BAR);
     uint64_t *ep_full = bars, *ep_empty = bars + 2, *c1_full = bars + 4, *c1_empty = bars + 16;
-    uint64_t *patch_full = bars + 28, *patch_empty = bars + 30, *d_full = bars + 32, *d_empty = bars + 34;
+    uint64_t *patch_full = bars + 20, *patch_empty = bars + 22, *d_full = bars + 24, *d_empty = bars + 26;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_TMEM);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -85,7 +85,8 @@ __global__ void __launch_bounds__(stem::NTHREADS, 1) stem_umma_kernel(const Stem
             mbar_init(&patch_full[i], 8); mbar_init(&patch_empty[i], 1);
             mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 4);
         }
-        for (int i = 0; i < 12; i++) { mbar_init(&c1_full[i], 1); mbar_init(&c1_empty[i], 4); }
+        for (int i = 0; i < 12; i++) mbar_init(&c1_full[i], 1);
+        for (int i = 0; i < 4; i++) mbar_init(&c1_empty[i], 12); // per parity plane: 3 tiles x 4 lane-quadrant warps
         mbar_fence_init();
     }
     for (int i = tid; i < W0_BYTES / 16; i += NTHREADS) reinterpret_cast<uint4 *>(smem + OFF_W0)[i] = __ldg(reinterpret_cast<const uint4 *>(p.w0) + i);
@@ -194,25 +195,26 @@ __global__ void __launch_bounds__(stem::NTHREADS, 1) stem_umma_kernel(const Stem
                 mbar_wait(&ep_full[buf], (ul >> 1) & 1);
                 tc_fence_after();
                 const uint32_t ep = sEP + buf * EP_BYTES;
-#pragma unroll 1
+                // Per tile THREE K=16 MMAs cover the six (kernel row, hi/lo) products; the two chunks of each MMA are two
+                // kernel rows whose EP addresses differ by a positive constant (LBO):
+                //   py = 0: rows kh0 @ R1+0, kh1 @ R0+17, kh2 @ R1+17   (R0 / R1 = row-parity arrays, entries)
+                //           [kh1 | kh0] x [w1hi | w0hi],  [kh1 | kh2] x [w1lo | w2hi],  [kh0 | kh2] x [w0lo | w2lo]
+                //   py = 1: rows kh0 @ R0+0, kh1 @ R1+0, kh2 @ R0+17
+                //           [kh0 | kh1] x [w0hi | w1hi],  [kh0 | kh2] x [w0lo | w2hi],  [kh2 | kh1] x [w2lo | w1lo]
+#pragma unroll
                 for (int k = 0; k < 12; k++) {
                     const int plane = k / 3, t = k % 3, py = plane >> 1, px = plane & 1;
-                    mbar_wait(&c1_empty[k], (ul & 1) ^ 1);
-                    tc_fence_after();
+                    if (t == 0) { mbar_wait(&c1_empty[plane], (ul & 1) ^ 1); tc_fence_after(); }
                     if (elect_one_sync()) {
-                        // arrays of column parity 1 - px: row parity 0 at +0, row parity 1 at +EP_ARR
-                        const uint32_t a0 = ep + (1 - px) * 2 * EP_ARR + t * 128 * 16;
-                        // py = 0: a = [kh0 @ (rpar 1, +0 rows) | zero-weight chunk], b = [kh1 @ (rpar 0, +1 row) | kh2 @ (rpar 1, +1 row)]
-                        // py = 1: a = [kh0 @ (rpar 0, +0)     | kh1 @ (rpar 1, +0)], b = [kh2 @ (rpar 0, +1 row) | zero-weight chunk]
-                        const uint32_t da = py ? umma_desc_lo(a0, EP_ARR) : umma_desc_lo(a0 + EP_ARR, PE * 16);
-                        const uint32_t db = umma_desc_lo(a0 + PE * 16, EP_ARR);
+                        const uint32_t a0 = ep + (1 - px) * 2 * EP_ARR + t * 128 * 16; // row-parity-0 array of column parity 1 - px
                         const uint32_t d_tmem = tmem + TM_C1 + k * 32;
-                        const uint32_t wb = sW1 + py * 4096;
-#pragma unroll
-                        for (int part = 0; part < 2; part++) { // hi, lo halves of the weights
-                            umma_f16(d_tmem, umma_desc_pack(da, e_hi), umma_desc_pack(umma_desc_lo(wb + part * 2048, 32 * 16), b_hi), idesc, part);
-                            umma_f16(d_tmem, umma_desc_pack(db, e_hi), umma_desc_pack(umma_desc_lo(wb + part * 2048 + 1024, 32 * 16), b_hi), idesc, 1);
-                        }
+                        const uint32_t wb = sW1 + py * 3072;
+                        constexpr uint32_t ROW = PE * 16, L289 = (EP_ARR - PE * 16);
+                        const uint32_t s0 = py ? a0 : a0 + ROW, s1 = py ? a0 : a0 + ROW, s2 = py ? a0 + ROW : a0 + EP_ARR;
+                        const uint32_t l0 = py ? EP_ARR : L289, l1 = py ? ROW : EP_ARR, l2 = py ? L289 : ROW;
+                        umma_f16(d_tmem, umma_desc_pack(umma_desc_lo(s0, l0), e_hi), umma_desc_pack(umma_desc_lo(wb, 32 * 16), b_hi), idesc, 0);
+                        umma_f16(d_tmem, umma_desc_pack(umma_desc_lo(s1, l1), e_hi), umma_desc_pack(umma_desc_lo(wb + 1024, 32 * 16), b_hi), idesc, 1);
+                        umma_f16(d_tmem, umma_desc_pack(umma_desc_lo(s2, l2), e_hi), umma_desc_pack(umma_desc_lo(wb + 2048, 32 * 16), b_hi), idesc, 1);
                         umma_commit(&c1_full[k]);
                     }
                     __syncwarp();
@@ -269,7 +271,7 @@ __global__ void __launch_bounds__(stem::NTHREADS, 1) stem_umma_kernel(const Stem
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&c1_empty[k]);
+                if (lane == 0) mbar_arrive(&c1_empty[plane]);
                 if (e < PLANE_ENT) {
                     // conv1 pixel (2*oy0 - py + 2*i, 2*ox0 - px + 2*j); outside the picture = zero padding of the stride-2 conv
                     const bool zero = (py && i == 0 && oy0 == 0) || (px && j == 0 && ox0 == 0);

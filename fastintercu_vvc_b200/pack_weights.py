@@ -130,19 +130,23 @@ def conv1_operand(w: np.ndarray) -> np.ndarray:
 
 
 def stem_conv1_operand(w: np.ndarray) -> np.ndarray:
-    """conv1 for the fused stem kernel (csrc/stem_umma.cu): fp16 [py][hi, lo][a, b][2 chunks][32 cout][8].
+    """conv1 for the fused stem kernel (csrc/stem_umma.cu): fp16 [py][3 MMAs][2 chunks][32 cout][8].
 
-    Same chunks as conv1_operand (chunk kh = one kernel row, scale folded in), arranged as the two K=16 MMAs the
-    stem issues per output row parity py:  py = 0: a = [kh0 | 0], b = [kh1 | kh2];  py = 1: a = [kh0 | kh1], b = [kh2 | 0]."""
-    c = conv1_operand(w)  # [hi, lo][4 chunks][32][8]; chunk 3 = 0
-    z = 3
-    order = (((0, z), (1, 2)), ((0, 1), (2, z)))
-    out = np.zeros((2, 2, 2, 2, 32, 8), np.float16)
+    Same chunks as conv1_operand (chunk kh = one kernel row, scale folded in, hi/lo fp16 split).  Per output-row parity
+    py the stem issues three K=16 MMAs whose two chunks pair kernel rows at a constant shared-memory distance:
+      py = 0: [kh1.hi | kh0.hi], [kh1.lo | kh2.hi], [kh0.lo | kh2.lo]
+      py = 1: [kh0.hi | kh1.hi], [kh0.lo | kh2.hi], [kh2.lo | kh1.lo]
+    so the six (kernel row, hi/lo) products are each covered exactly once."""
+    c = conv1_operand(w)  # [hi, lo][4 chunks][32][8]
+    H, L = 0, 1
+    order = ((((H, 1), (H, 0)), ((L, 1), (H, 2)), ((L, 0), (L, 2))),
+             (((H, 0), (H, 1)), ((L, 0), (H, 2)), ((L, 2), (L, 1))))
+    out = np.zeros((2, 3, 2, 32, 8), np.float16)
     for py in range(2):
-        for part in range(2):
-            for ab in range(2):
-                for k in range(2):
-                    out[py, part, ab, k] = c[part, order[py][ab][k]]
+        for m in range(3):
+            for k in range(2):
+                part, kh = order[py][m][k]
+                out[py, m, k] = c[part, kh]
     return out
 
 
