@@ -191,6 +191,7 @@ int ensure_act0(mlt_ctx *c) // conv1's full output: only the unfused engine and 
         CU(conv_umma_prepare(0, &p, c->act_h[0], L, nullptr, nullptr, (size_t)c->max_batch));
         p.w = secp<__half>(c, SEC_W_F16 + 0);
         p.bias = secp<__half>(c, SEC_BIAS_MMA + 0);
+        p.bias_f32 = secp<float>(c, SEC_BIAS_FUSED + 0);
         p.x_w = nullptr;
         p.out = c->act_h[1];
         p.relu = 1;
@@ -443,6 +444,7 @@ int mlt_create_ex(mlt_ctx **out, const char *weights_path, int cuda_device, int 
             CU(conv_umma_prepare(li, &p, c->act_h[li], in_l, conv2 ? xp : nullptr, conv2 ? &x_l : nullptr, (size_t)max_batch));
             p.w = secp<__half>(c, SEC_W_F16 + li);
             p.bias = secp<__half>(c, SEC_BIAS_MMA + li);
+            p.bias_f32 = secp<float>(c, SEC_BIAS_FUSED + li);
             p.x_w = conv2 ? secp<__half>(c, SEC_X_W_F16 + li) : nullptr;
             p.out = c->act_h[li + 1];
             p.relu = 1;

@@ -34,7 +34,9 @@ namespace mlt {
 template <int CIN_, int COUT_, int STRIDE_, int HOUT_, int XC_, int OUT_PAR_>
 struct ConvCfg {
     static constexpr int CIN = CIN_, COUT = COUT_, STRIDE = STRIDE_, HOUT = HOUT_, XC = XC_, OUT_PAR = OUT_PAR_;
-    static constexpr int G = (STRIDE == 2) ? 32 : (CIN < 64 ? CIN : 64); // input channels per A stage
+    // input channels per A stage / weight slab: 32 for the stride-2 convs (four parity planes per stage) and for the
+    // 256-channel layers (keeps the activation ring small so the streamed-weight ring can be deep)
+    static constexpr int G = (STRIDE == 2 && COUT >= 256) ? 16 : ((STRIDE == 2 || COUT >= 256) ? 32 : (CIN < 64 ? CIN : 64));
     static constexpr int NCG = CIN / G;
     static constexpr int CH = G / 8;               // 16-byte chunks per pixel per A stage
     static constexpr int NB = (HOUT == 8) ? 2 : 1; // images per tile (pair layouts)
@@ -61,13 +63,25 @@ struct ConvCfg {
     static constexpr int W_MAIN_BYTES = NCG * 9 * SLAB_BYTES;
     static constexpr int W_X_BYTES = XC * COUT * 2;
     static constexpr bool RESIDENT = (W_MAIN_BYTES + W_X_BYTES) <= 84 * 1024;
-    static constexpr int NBS = RESIDENT ? 0 : (SLAB_BYTES >= 16 * 1024 ? 4 : 6);
+    // weight-slab ring: deep enough that ring depth x MMA time per slab covers the ~2500-cycle L2 -> smem latency of a
+    // bulk copy (one slab feeds G/16 MMAs of max(N/2, 32 + N/4) cycles), leaving room for >= MIN_NAS activation stages
+    // streamed weights: the activation ring holds exactly two passes' worth of one step (MIN_NAS = 4: one stage per tile
+    // of the pair, double buffered); all remaining shared memory goes to the weight-slab ring, whose depth x MMA time per
+    // slab must cover the L2 -> smem latency of a bulk copy
+    static constexpr int TP = RESIDENT ? 1 : 2;     // tiles per pass: streamed weight slabs are shared by a pair of tiles
+    static constexpr int MIN_NAS = 4;
+    static constexpr int NBS_MAX = (231000 - MIN_NAS * A_STAGE_BYTES - COUT * 32 - 4096) / SLAB_BYTES;
+    static constexpr int NBS = RESIDENT ? 0 : (NBS_MAX > 12 ? 12 : NBS_MAX);
+    static_assert(RESIDENT || NBS >= 3, "weight ring too shallow");
     static constexpr int B_BYTES = RESIDENT ? (W_MAIN_BYTES + W_X_BYTES) : NBS * SLAB_BYTES;
     static constexpr int BIAS_BYTES = COUT * 32;    // bias as a K=16 B operand
     static constexpr int ONES_BYTES = 2 * 128 * 16; // matching A operand: k=0,1 -> 1.0, rest 0
     static constexpr int A_BUDGET = 231000 - B_BYTES - BIAS_BYTES - ONES_BYTES;
     static constexpr int NAS = (A_BUDGET / A_STAGE_BYTES) > 8 ? 8 : (A_BUDGET / A_STAGE_BYTES); // A ring depth
     static constexpr int NACC = (COUT <= 128) ? 4 : 2; // TMEM accumulator stages (NACC * COUT <= 512 columns)
+    // bias: for the smem-operand-bound 32/64-channel layers it is added in the epilogue from registers (an extra MMA
+    // would cost 5 % / 3 % of the tile); for 128/256 channels it enters the accumulator through one K=16 MMA
+    static constexpr bool BIAS_REG = COUT <= 64;
     static constexpr int NBAR = 2 * NAS + 2 * (RESIDENT ? 1 : NBS) + 2 * NACC;
     static constexpr int OFF_A = 0;
     static constexpr int OFF_B = OFF_A + NAS * A_STAGE_BYTES;
@@ -148,6 +162,11 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
         const int m = wq * 32 + lane; // accumulator row == TMEM lane == pixel of the tile
         const int r = m / (8 * C::NB), h = (m / 8) % C::NB, c = m % 8;
         uint32_t acc_it = grp;
+        float bias_r[C::BIAS_REG ? C::COUT : 1];
+        if constexpr (C::BIAS_REG) {
+#pragma unroll
+            for (int j = 0; j < C::COUT; j++) bias_r[j] = __ldg(p.bias_f32 + j);
+        }
         for (int tile = blockIdx.x + grp * gridDim.x; tile < ntiles; tile += 2 * gridDim.x, acc_it += 2) {
             int img, oy, ox;
             if (C::NB == 2) { img = tile * 2 + h; oy = r; ox = c; }
@@ -166,11 +185,15 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
             const uint32_t acc = acc_it % C::NACC;
             mbar_wait(&accFull[acc], (acc_it / C::NACC) & 1);
             tc_fence_after();
-#pragma unroll 1
+#pragma unroll(C::BIAS_REG ? 2 : 1)
             for (int c0 = 0; c0 < C::COUT; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + acc * C::COUT + c0, v);
                 tmem_ld_wait();
+                if constexpr (C::BIAS_REG) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) v[j] = __float_as_uint(__uint_as_float(v[j]) + bias_r[c0 + j]);
+                }
                 if (valid) {
                     const __half2 zero2 = __float2half2_rn(0.0f);
                     __half *op = p.out + off + (size_t)(c0 / 8) * C::OCHUNK;
@@ -199,32 +222,56 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
         const uint32_t bias_lo = umma_desc_lo(smem_u32(smem + C::OFF_BIAS), C::COUT * 16);
         uint32_t a_it = 0, b_it = 0, acc_it = 0;
         if constexpr (C::RESIDENT) { mbar_wait(&fullB[0], 0); tc_fence_after(); }
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, acc_it++) {
-            const uint32_t acc = acc_it % C::NACC;
-            mbar_wait(&accEmpty[acc], ((acc_it / C::NACC) & 1) ^ 1);
+        // One pass = TP tiles (a PAIR when the weights are streamed): every weight slab fetched from L2 feeds the MMAs of
+        // both tiles, which halves the L2 -> smem weight traffic that otherwise bounds the 128/256-channel layers.
+        for (int tile = blockIdx.x; tile < ntiles; tile += C::TP * gridDim.x) {
+            const int np = (C::TP == 2 && tile + (int)gridDim.x < ntiles) ? 2 : 1;
+            uint32_t d_tmem[C::TP];
+#pragma unroll
+            for (int h = 0; h < C::TP; h++) {
+                if (h < np) {
+                    const uint32_t acc = (acc_it + h) % C::NACC;
+                    mbar_wait(&accEmpty[acc], (((acc_it + h) / C::NACC) & 1) ^ 1);
+                    d_tmem[h] = tmem_base + acc * C::COUT;
+                }
+            }
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * C::COUT;
             // accumulator := bias  (ones[128 x 16] x biasB[COUT x 16]^T, hi + lo fp16 split => ~fp32-exact bias)
-            if (elect_one_sync()) umma_f16(d_tmem, umma_desc_pack(ones_lo, b_hi), umma_desc_pack(bias_lo, b_hi), idesc, 0);
+            if constexpr (!C::BIAS_REG) {
+                if (elect_one_sync()) {
+#pragma unroll
+                    for (int h = 0; h < C::TP; h++)
+                        if (h < np) umma_f16(d_tmem[h], umma_desc_pack(ones_lo, b_hi), umma_desc_pack(bias_lo, b_hi), idesc, 0);
+                }
+            }
 #pragma unroll 1
-            for (int cg = 0; cg < C::NCG; cg++, a_it++) {
-                const uint32_t st = a_it % C::NAS;
-                mbar_wait(&fullA[st], (a_it / C::NAS) & 1); // TMA complete_tx: data visible to the async proxy
+            for (int cg = 0; cg < C::NCG; cg++, a_it += np) {
+                uint32_t a_lo0[C::TP];
+#pragma unroll
+                for (int h = 0; h < C::TP; h++) {
+                    if (h < np) {
+                        const uint32_t st = (a_it + h) % C::NAS;
+                        mbar_wait(&fullA[st], ((a_it + h) / C::NAS) & 1); // TMA complete_tx: data visible to the async proxy
+                        a_lo0[h] = umma_desc_lo(sA + st * C::A_STAGE_BYTES, C::A_LBO);
+                    }
+                }
                 tc_fence_after();
-                const uint32_t a_lo0 = umma_desc_lo(sA + st * C::A_STAGE_BYTES, C::A_LBO);
                 if constexpr (C::RESIDENT) {
+                    // weights resident: one elected thread streams all taps of this stage back to back (TP == 1)
                     if (elect_one_sync()) {
 #pragma unroll
                         for (int tap = 0; tap < 9; tap++) {
                             const uint32_t b_lo0 = umma_desc_lo(sB + (cg * 9 + tap) * C::SLAB_BYTES, C::COUT * 16);
-                            const uint32_t a_tap = a_lo0 + tap_offset16<C>(tap / 3, tap % 3);
+                            const uint32_t a_tap = a_lo0[0] + tap_offset16<C>(tap / 3, tap % 3);
 #pragma unroll
                             for (int ks = 0; ks < C::G / 16; ks++)
-                                umma_f16(d_tmem, umma_desc_pack(a_tap + ks * (2 * C::A_LBO / 16), a_hi),
-                                         umma_desc_pack(b_lo0 + ks * (2 * C::COUT), b_hi), idesc, 1);
+                                umma_f16(d_tmem[0], umma_desc_pack(a_tap + ks * (2 * C::A_LBO / 16), a_hi),
+                                         umma_desc_pack(b_lo0 + ks * (2 * C::COUT), b_hi), idesc,
+                                         (C::BIAS_REG && tap == 0 && ks == 0) ? (uint32_t)(cg != 0) : 1u);
                         }
-                        umma_commit(&emptyA[st]);
+                        umma_commit(&emptyA[a_it % C::NAS]);
                     }
+                    __syncwarp();
                 } else {
 #pragma unroll
                     for (int tap = 0; tap < 9; tap++, b_it++) {
@@ -233,45 +280,75 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
                         tc_fence_after();
                         if (elect_one_sync()) {
                             const uint32_t b_lo0 = umma_desc_lo(sB + bs * C::SLAB_BYTES, C::COUT * 16);
-                            const uint32_t a_tap = a_lo0 + tap_offset16<C>(tap / 3, tap % 3);
 #pragma unroll
-                            for (int ks = 0; ks < C::G / 16; ks++)
-                                umma_f16(d_tmem, umma_desc_pack(a_tap + ks * (2 * C::A_LBO / 16), a_hi),
-                                         umma_desc_pack(b_lo0 + ks * (2 * C::COUT), b_hi), idesc, 1);
+                            for (int h = 0; h < C::TP; h++) {
+                                if (h < np) {
+                                    const uint32_t a_tap = a_lo0[h] + tap_offset16<C>(tap / 3, tap % 3);
+#pragma unroll
+                                    for (int ks = 0; ks < C::G / 16; ks++)
+                                        umma_f16(d_tmem[h], umma_desc_pack(a_tap + ks * (2 * C::A_LBO / 16), a_hi),
+                                                 umma_desc_pack(b_lo0 + ks * (2 * C::COUT), b_hi), idesc,
+                                                 (C::BIAS_REG && tap == 0 && ks == 0) ? (uint32_t)(cg != 0) : 1u);
+                                }
+                            }
                             umma_commit(&emptyB[bs]);
-                            if (tap == 8) umma_commit(&emptyA[st]);
+                            if (tap == 8) {
+#pragma unroll
+                                for (int h = 0; h < C::TP; h++)
+                                    if (h < np) umma_commit(&emptyA[(a_it + h) % C::NAS]);
+                            }
                         }
+                        __syncwarp();
                     }
                 }
             }
             if constexpr (C::XC > 0) {
                 // extra operand: block input (1x1 stride-2 shortcut conv, or identity residual), GX channels per stage
 #pragma unroll 1
-                for (int xs = 0; xs < C::NXS; xs++, a_it++) {
-                    const uint32_t st = a_it % C::NAS;
-                    mbar_wait(&fullA[st], (a_it / C::NAS) & 1);
-                    tc_fence_after();
-                    const uint32_t a_lo0 = umma_desc_lo(sA + st * C::A_STAGE_BYTES, C::X_LBO);
+                for (int xs = 0; xs < C::NXS; xs++, a_it += np) {
+                    uint32_t a_lo0[C::TP];
+#pragma unroll
+                    for (int h = 0; h < C::TP; h++) {
+                        if (h < np) {
+                            const uint32_t st = (a_it + h) % C::NAS;
+                            mbar_wait(&fullA[st], ((a_it + h) / C::NAS) & 1);
+                            a_lo0[h] = umma_desc_lo(sA + st * C::A_STAGE_BYTES, C::X_LBO);
+                        }
+                    }
                     uint32_t bs = 0;
                     if constexpr (!C::RESIDENT) {
                         bs = b_it % C::NBS;
                         mbar_wait(&fullB[bs], (b_it / C::NBS) & 1);
-                        tc_fence_after();
                         b_it++;
                     }
+                    tc_fence_after();
                     if (elect_one_sync()) {
                         const uint32_t b_lo0 = C::RESIDENT ? umma_desc_lo(sB + C::W_MAIN_BYTES + xs * C::X_SLAB_BYTES, C::COUT * 16)
                                                            : umma_desc_lo(sB + bs * C::SLAB_BYTES, C::COUT * 16);
 #pragma unroll
-                        for (int ks = 0; ks < C::GX / 16; ks++)
-                            umma_f16(d_tmem, umma_desc_pack(a_lo0 + ks * (2 * C::X_LBO / 16), x_hi),
-                                     umma_desc_pack(b_lo0 + ks * (2 * C::COUT), b_hi), idesc, 1);
+                        for (int h = 0; h < C::TP; h++) {
+                            if (h < np) {
+#pragma unroll
+                                for (int ks = 0; ks < C::GX / 16; ks++)
+                                    umma_f16(d_tmem[h], umma_desc_pack(a_lo0[h] + ks * (2 * C::X_LBO / 16), x_hi),
+                                             umma_desc_pack(b_lo0 + ks * (2 * C::COUT), b_hi), idesc, 1);
+                            }
+                        }
                         if constexpr (!C::RESIDENT) umma_commit(&emptyB[bs]);
-                        umma_commit(&emptyA[st]);
+#pragma unroll
+                        for (int h = 0; h < C::TP; h++)
+                            if (h < np) umma_commit(&emptyA[(a_it + h) % C::NAS]);
                     }
+                    __syncwarp();
                 }
             }
-            if (elect_one_sync()) umma_commit(&accFull[acc]);
+            if (elect_one_sync()) {
+#pragma unroll
+                for (int h = 0; h < C::TP; h++)
+                    if (h < np) umma_commit(&accFull[(acc_it + h) % C::NACC]);
+            }
+            __syncwarp();
+            acc_it += np;
         }
     } else if (warp == C::W_BLOAD) {
         // ======================= weight loader (bulk copies on the TMA engine), one elected lane issues
@@ -288,7 +365,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
             }
         } else {
             uint32_t b_it = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            for (int tile = blockIdx.x; tile < ntiles; tile += C::TP * gridDim.x) { // once per pass (pair of tiles)
 #pragma unroll 1
                 for (int s = 0; s < C::NCG * 9 + C::NXS; s++, b_it++) {
                     const uint32_t bs = b_it % C::NBS;
@@ -308,35 +385,42 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
         // stride-2 conv]; the halo / zero padding comes from the TMA out-of-bounds fill
         if (lane == 0) { tma_prefetch_desc(&p.in_map); if (C::XC > 0) tma_prefetch_desc(&p.x_map); }
         uint32_t a_it = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            int unit, oy0, ox0;
-            if (C::NB == 2) { unit = tile; oy0 = 0; ox0 = 0; }
-            else {
-                unit = tile / C::TILES_PER_IMG;
-                const int rem = tile % C::TILES_PER_IMG;
-                oy0 = (rem / (C::HOUT / 8)) * 16;
-                ox0 = (rem % (C::HOUT / 8)) * 8;
-            }
+        for (int tile0 = blockIdx.x; tile0 < ntiles; tile0 += C::TP * gridDim.x) {
+            const int np = (C::TP == 2 && tile0 + (int)gridDim.x < ntiles) ? 2 : 1;
+            // stage order of a pass: (step 0, tile 0), (step 0, tile 1), (step 1, tile 0), ... -- what the MMA issuer consumes
 #pragma unroll 1
-            for (int it = 0; it < C::NCG + C::NXS; it++, a_it++) {
-                const uint32_t st = a_it % C::NAS;
-                mbar_wait(&emptyA[st], ((a_it / C::NAS) & 1) ^ 1);
-                if (elect_one_sync()) {
-                    const uint32_t abase = sA + st * C::A_STAGE_BYTES;
-                    if (it < C::NCG) {
-                        mbar_arrive_expect_tx(&fullA[st], C::A_TX_BYTES);
-                        if constexpr (C::STRIDE == 1) {
-                            tma_load_5d(abase, &p.in_map, (ox0 - 1) * 8, 0, oy0 - 1, it * C::CH, unit, &fullA[st]);
-                        } else {
-#pragma unroll
-                            for (int pl = 0; pl < 4; pl++)
-                                tma_load_5d(abase + pl * C::PLANE_STRIDE, &p.in_map, (ox0 - (pl & 1)) * 8, 0, oy0 - (pl >> 1),
-                                            it * C::CH, unit * 4 + pl, &fullA[st]);
-                        }
-                    } else {
-                        mbar_arrive_expect_tx(&fullA[st], C::X_STAGE_BYTES);
-                        tma_load_5d(abase, &p.x_map, ox0 * 8, 0, oy0, (it - C::NCG) * (C::GX / 8), unit * p.x_unit_mul, &fullA[st]);
+            for (int it = 0; it < C::NCG + C::NXS; it++) {
+#pragma unroll 1
+                for (int h = 0; h < np; h++, a_it++) {
+                    const int tile = tile0 + h * (int)gridDim.x;
+                    int unit, oy0, ox0;
+                    if (C::NB == 2) { unit = tile; oy0 = 0; ox0 = 0; }
+                    else {
+                        unit = tile / C::TILES_PER_IMG;
+                        const int rem = tile % C::TILES_PER_IMG;
+                        oy0 = (rem / (C::HOUT / 8)) * 16;
+                        ox0 = (rem % (C::HOUT / 8)) * 8;
                     }
+                    const uint32_t st = a_it % C::NAS;
+                    mbar_wait(&emptyA[st], ((a_it / C::NAS) & 1) ^ 1);
+                    if (elect_one_sync()) {
+                        const uint32_t abase = sA + st * C::A_STAGE_BYTES;
+                        if (it < C::NCG) {
+                            mbar_arrive_expect_tx(&fullA[st], C::A_TX_BYTES);
+                            if constexpr (C::STRIDE == 1) {
+                                tma_load_5d(abase, &p.in_map, (ox0 - 1) * 8, 0, oy0 - 1, it * C::CH, unit, &fullA[st]);
+                            } else {
+#pragma unroll
+                                for (int pl = 0; pl < 4; pl++)
+                                    tma_load_5d(abase + pl * C::PLANE_STRIDE, &p.in_map, (ox0 - (pl & 1)) * 8, 0, oy0 - (pl >> 1),
+                                                it * C::CH, unit * 4 + pl, &fullA[st]);
+                            }
+                        } else {
+                            mbar_arrive_expect_tx(&fullA[st], C::X_STAGE_BYTES);
+                            tma_load_5d(abase, &p.x_map, ox0 * 8, 0, oy0, (it - C::NCG) * (C::GX / 8), unit * p.x_unit_mul, &fullA[st]);
+                        }
+                    }
+                    __syncwarp();
                 }
             }
         }

@@ -66,6 +66,7 @@ struct ConvParams {
     const __half *w;    // packed [CIN/G][9][G/8][COUT][8]
     const __half *bias; // tcgen05 bias operand [2][COUT][8] fp16: k=0 -> hi(b), k=1 -> lo(b), rest 0 (pack_weights.py)
     const __half *x_w;  // packed [XC/GX][GX/8][COUT][8] (folded shortcut weights, or the identity)
+    const float *bias_f32; // the same (shortcut-fused) bias as fp32 [COUT], added in the epilogue by the 32/64-channel layers
     __half *out;
     int nimg;
     int relu;

@@ -57,10 +57,11 @@ def conv_table():
     for L, planes in enumerate(PLANES):
         hout = hin // 2
         p = f"layer{L}"
-        rows.append((f"{p}.0.conv1", cin, planes, 2, hout, 32, -1))
-        rows.append((f"{p}.0.conv2", planes, planes, 1, hout, min(planes, 64), L))
-        rows.append((f"{p}.1.conv1", planes, planes, 1, hout, min(planes, 64), -1))
-        rows.append((f"{p}.1.conv2", planes, planes, 1, hout, min(planes, 64), -1))
+        g = 32 if planes >= 256 else min(planes, 64)  # = ConvCfg::G of csrc/conv_umma.cuh
+        rows.append((f"{p}.0.conv1", cin, planes, 2, hout, 16 if planes >= 256 else 32, -1))
+        rows.append((f"{p}.0.conv2", planes, planes, 1, hout, g, L))
+        rows.append((f"{p}.1.conv1", planes, planes, 1, hout, g, -1))
+        rows.append((f"{p}.1.conv2", planes, planes, 1, hout, g, -1))
         cin, hin = planes, hout
     return rows
 
