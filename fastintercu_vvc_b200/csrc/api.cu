@@ -61,9 +61,17 @@ struct mlt_ctx {
     uint8_t *d_blob = nullptr;
     size_t blob_bytes = 0;
     Section sec[0x1000];
-    __half *act_h[NACT] = {}; // [0] (conv1's full output, parity-planar) exists only for the unfused engine / debug reads
-    __half *act0q = nullptr;  // conv1's output at even rows / columns (input of layer0.0's shortcut), dense [n][4][64][64][8]
-    ConvParams conv_p[NCONV]; // tensor maps + weight pointers of every tcgen05 conv, built once at create
+    // Two sets of activation buffers (+ the tensor maps over them): large batches are cut in two slices that run on two
+    // streams, so the drain / launch / prologue gap between the 17 kernels of one slice is filled by kernels of the other.
+    // Set 0 holds max_batch images (every single-slice call and all debug reads use it), set 1 half of that.
+    struct ActSet {
+        __half *act_h[NACT] = {}; // [0] (conv1's full output, parity-planar) exists only for the unfused engine / debug reads
+        __half *act0q = nullptr;  // conv1's output at even rows / columns (input of layer0.0's shortcut), dense [n][4][64][64][8]
+        ConvParams conv_p[NCONV]; // tensor maps + weight pointers of every tcgen05 conv, built once at create
+        int cap = 0;              // images
+    } set[2];
+    cudaStream_t stream2 = nullptr;            // second compute stream (slice 1)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     float *act_f[NACT] = {};
     float *scratch_f = nullptr; // shortcut-conv output of the fp32 engine
     int16_t *d_in = nullptr, *h_in = nullptr; // dense [max_batch][2][128][128]
@@ -179,23 +187,21 @@ int ensure_dbg(mlt_ctx *c, size_t bytes)
     return MLT_OK;
 }
 
-int ensure_act0(mlt_ctx *c) // conv1's full output: only the unfused engine and debug reads materialise it
+int ensure_act0(mlt_ctx *c, mlt_ctx::ActSet &S) // conv1's full output: only the unfused engine and debug reads materialise it
 {
-    if (c->act_h[0]) return MLT_OK;
+    if (S.act_h[0]) return MLT_OK;
     const ActLayout L = act_layout(0);
-    const size_t bytes = L.unit_elems() * L.units_for(c->max_batch) * sizeof(__half);
-    CU(cudaMalloc(&c->act_h[0], bytes));
-    CU(cudaMemset(c->act_h[0], 0, bytes));
-    if (c->conv_p[0].out == nullptr) {
-        ConvParams &p = c->conv_p[0];
-        CU(conv_umma_prepare(0, &p, c->act_h[0], L, nullptr, nullptr, (size_t)c->max_batch));
-        p.w = secp<__half>(c, SEC_W_F16 + 0);
-        p.bias = secp<__half>(c, SEC_BIAS_MMA + 0);
-        p.bias_f32 = secp<float>(c, SEC_BIAS_FUSED + 0);
-        p.x_w = nullptr;
-        p.out = c->act_h[1];
-        p.relu = 1;
-    }
+    const size_t bytes = L.unit_elems() * L.units_for(S.cap) * sizeof(__half);
+    CU(cudaMalloc(&S.act_h[0], bytes));
+    CU(cudaMemset(S.act_h[0], 0, bytes));
+    ConvParams &p = S.conv_p[0];
+    CU(conv_umma_prepare(0, &p, S.act_h[0], L, nullptr, nullptr, (size_t)S.cap));
+    p.w = secp<__half>(c, SEC_W_F16 + 0);
+    p.bias = secp<__half>(c, SEC_BIAS_MMA + 0);
+    p.bias_f32 = secp<float>(c, SEC_BIAS_FUSED + 0);
+    p.x_w = nullptr;
+    p.out = S.act_h[1];
+    p.relu = 1;
     return MLT_OK;
 }
 
@@ -213,42 +219,44 @@ __global__ void dense_descs_kernel(CtuDev *ctus, const int16_t *orgpred, const i
 }
 
 // The whole network on `n` CTUs described by device array `ctus`; results to device array `out`.
-int run_network(mlt_ctx *c, const CtuDev *ctus, int n, mlt_result *out, cudaStream_t s)
+int run_network(mlt_ctx *c, const CtuDev *ctus, int n, mlt_result *out, cudaStream_t s, int set_idx = 0)
 {
+    mlt_ctx::ActSet &S = c->set[set_idx];
+    if (n > S.cap) return fail(c, MLT_E_BATCH, "slice of %d CTUs exceeds activation set %d (%d)", n, set_idx, S.cap);
     HeadParams hp;
     hp.ctus = ctus; hp.out = out; hp.n = n;
     for (int i = 0; i < 3; i++) { hp.fc_w[i] = secp<float>(c, SEC_FC_W + i); hp.fc_b[i] = secp<float>(c, SEC_FC_B + i); }
     if (c->engine != 1) {
         // ---- product path: fused stem (staging + conv1 + layer0.0.conv1), 15 tcgen05 implicit-GEMM convs, head
-        const bool prof = c->profiling;
+        const bool prof = c->profiling && set_idx == 0;
         int ev = 0;
         if (prof) { CU(cudaEventRecord(c->prof_ev[ev++], s)); c->prof_stream = s; c->prof_valid = false; }
         int first = 0;
         if (c->engine == 0) {
             // fused stem: staging + conv1 + layer0.0.conv1; conv1's 1 MiB / CTU output never reaches HBM
             CU(launch_stem_umma(ctus, n, secp<__half>(c, SEC_STEM_CONV1), secp<__half>(c, SEC_W_F16 + 0), secp<__half>(c, SEC_BIAS_MMA + 0),
-                                c->act0q, c->act_h[1], c->num_sms, s));
+                                S.act0q, S.act_h[1], c->num_sms, s));
             c->launches++;
             if (prof) { CU(cudaEventRecord(c->prof_ev[ev++], s)); CU(cudaEventRecord(c->prof_ev[ev++], s)); }
             first = 1;
         } else {
             // unfused tcgen05 engine (cross-check of the stem): standalone conv1, its even/even quarter copied out
-            int rc = ensure_act0(c);
+            int rc = ensure_act0(c, S);
             if (rc) return rc;
-            CU(launch_conv1_umma(ctus, n, secp<__half>(c, SEC_CONV1_UMMA), c->act_h[0], s));
+            CU(launch_conv1_umma(ctus, n, secp<__half>(c, SEC_CONV1_UMMA), S.act_h[0], s));
             c->launches++;
             const size_t q = (size_t)4 * 64 * 64 * 8 * sizeof(__half);
-            CU(cudaMemcpy2DAsync(c->act0q, q, c->act_h[0], 4 * q, q, n, cudaMemcpyDeviceToDevice, s));
+            CU(cudaMemcpy2DAsync(S.act0q, q, S.act_h[0], 4 * q, q, n, cudaMemcpyDeviceToDevice, s));
             if (prof) CU(cudaEventRecord(c->prof_ev[ev++], s));
         }
         for (int li = first; li < NCONV; li++) {
-            ConvParams &p = c->conv_p[li];
+            ConvParams &p = S.conv_p[li];
             p.nimg = n;
             CU(launch_conv_umma(li, p, c->num_sms, s));
             c->launches++;
             if (prof) CU(cudaEventRecord(c->prof_ev[ev++], s));
         }
-        hp.act[0] = c->act_h[8]; hp.act[1] = c->act_h[12]; hp.act[2] = c->act_h[16];
+        hp.act[0] = S.act_h[8]; hp.act[1] = S.act_h[12]; hp.act[2] = S.act_h[16];
         CU(launch_head_h(hp, s));
         c->launches++;
         if (prof) { CU(cudaEventRecord(c->prof_ev[ev++], s)); c->prof_valid = true; }
@@ -328,6 +336,8 @@ int run_host_batch_chunked(mlt_ctx *c, int n, const int16_t *src, const mlt_ctu_
     CU(cudaMemcpyAsync(c->d_ctus, c->h_ctus, (size_t)n * sizeof(CtuDev), cudaMemcpyHostToDevice, s));
     const int nchunks = n >= 1024 ? (n / 512 < mlt_ctx::MAX_CHUNKS ? n / 512 : mlt_ctx::MAX_CHUNKS) : 1;
     const int per = (n + nchunks - 1) / nchunks;
+    const bool two = nchunks > 1 && !c->profiling; // chunks alternate between the two activation sets / compute streams
+    if (two) { CU(cudaEventRecord(c->ev_fork, s)); CU(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0)); } // descriptors uploaded
     for (int i = 0, off = 0; off < n; i++, off += per) {
         const int m = n - off < per ? n - off : per;
         const int16_t *from = src ? src + (size_t)off * CTU_IN_ELEMS : c->h_in + (size_t)off * CTU_IN_ELEMS;
@@ -337,10 +347,13 @@ int run_host_batch_chunked(mlt_ctx *c, int n, const int16_t *src, const mlt_ctu_
         CU(cudaMemcpyAsync(c->d_in + (size_t)off * CTU_IN_ELEMS, from, (size_t)m * CTU_IN_ELEMS * sizeof(int16_t),
                            cudaMemcpyHostToDevice, c->copy_stream));
         CU(cudaEventRecord(c->ev_in[i], c->copy_stream));
-        CU(cudaStreamWaitEvent(s, c->ev_in[i], 0));
-        const int rc = run_network(c, c->d_ctus + off, m, c->d_out + off, s);
-        if (rc) { cudaStreamSynchronize(c->copy_stream); return rc; }
+        const int si = two ? (i & 1) : 0;
+        cudaStream_t cs = si ? c->stream2 : s;
+        CU(cudaStreamWaitEvent(cs, c->ev_in[i], 0));
+        const int rc = run_network(c, c->d_ctus + off, m, c->d_out + off, cs, si);
+        if (rc) { cudaStreamSynchronize(c->copy_stream); cudaStreamSynchronize(c->stream2); return rc; }
     }
+    if (two) { CU(cudaEventRecord(c->ev_join, c->stream2)); CU(cudaStreamWaitEvent(s, c->ev_join, 0)); }
     c->last_n = n <= per ? n : 0; // debug_activation only sees a whole batch when it ran as one chunk
     CU(cudaMemcpyAsync(c->h_out, c->d_out, (size_t)n * sizeof(mlt_result), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
@@ -388,9 +401,13 @@ void mlt_destroy(mlt_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    for (int a = 0; a < NACT; a++) { cudaFree(c->act_h[a]); cudaFree(c->act_f[a]); }
+    for (auto &S : c->set) { for (int a = 0; a < NACT; a++) cudaFree(S.act_h[a]); cudaFree(S.act0q); }
+    for (int a = 0; a < NACT; a++) cudaFree(c->act_f[a]);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
     cudaFree(c->scratch_f); cudaFree(c->d_blob); cudaFree(c->d_in); cudaFree(c->d_ctus); cudaFree(c->d_out);
-    cudaFree(c->d_dbg); cudaFree(c->d_pic); cudaFree(c->act0q);
+    cudaFree(c->d_dbg); cudaFree(c->d_pic);
     cudaFreeHost(c->h_in); cudaFreeHost(c->h_ctus); cudaFreeHost(c->h_out);
     for (cudaEvent_t e : c->prof_ev) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : c->ev_in) if (e) cudaEventDestroy(e);
@@ -425,29 +442,36 @@ int mlt_create_ex(mlt_ctx **out, const char *weights_path, int cuda_device, int 
         if (r) return r;
         CU(conv_umma_init());
         CU(stem_umma_init());
-        for (int a = 1; a < NACT; a++) {
-            // zeroed once: the unused half of the last image pair of an odd batch must stay finite
-            const ActLayout L = act_layout(a);
-            const size_t bytes = L.unit_elems() * L.units_for(max_batch) * sizeof(__half);
-            CU(cudaMalloc(&c->act_h[a], bytes));
-            CU(cudaMemsetAsync(c->act_h[a], 0, bytes, c->stream));
-        }
+        CU(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
         const ActLayout l0q{64, 32, 0, 0};
-        CU(cudaMalloc(&c->act0q, l0q.unit_elems() * (size_t)max_batch * sizeof(__half)));
-        memset(c->conv_p, 0, sizeof c->conv_p);
-        for (int li = 1; li < NCONV; li++) { // conv 0 runs inside the stem kernel (ensure_act0 prepares it for the unfused engine)
-            ConvParams &p = c->conv_p[li];
-            const bool conv2 = (li & 1) != 0;
-            const int xa = li & ~1; // input of the BasicBlock this conv belongs to
-            const ActLayout in_l = act_layout(li), x_l = xa == 0 ? l0q : act_layout(xa);
-            const __half *xp = xa == 0 ? c->act0q : c->act_h[xa];
-            CU(conv_umma_prepare(li, &p, c->act_h[li], in_l, conv2 ? xp : nullptr, conv2 ? &x_l : nullptr, (size_t)max_batch));
-            p.w = secp<__half>(c, SEC_W_F16 + li);
-            p.bias = secp<__half>(c, SEC_BIAS_MMA + li);
-            p.bias_f32 = secp<float>(c, SEC_BIAS_FUSED + li);
-            p.x_w = conv2 ? secp<__half>(c, SEC_X_W_F16 + li) : nullptr;
-            p.out = c->act_h[li + 1];
-            p.relu = 1;
+        for (int si = 0; si < 2; si++) {
+            mlt_ctx::ActSet &S = c->set[si];
+            S.cap = si == 0 ? max_batch : (max_batch + 1) / 2;
+            for (int a = 1; a < NACT; a++) {
+                // zeroed once: the unused half of the last image pair of an odd batch must stay finite
+                const ActLayout L = act_layout(a);
+                const size_t bytes = L.unit_elems() * L.units_for(S.cap) * sizeof(__half);
+                CU(cudaMalloc(&S.act_h[a], bytes));
+                CU(cudaMemsetAsync(S.act_h[a], 0, bytes, c->stream));
+            }
+            CU(cudaMalloc(&S.act0q, l0q.unit_elems() * (size_t)S.cap * sizeof(__half)));
+            memset(S.conv_p, 0, sizeof S.conv_p);
+            for (int li = 1; li < NCONV; li++) { // conv 0 runs inside the stem kernel (ensure_act0 prepares it for the unfused engine)
+                ConvParams &p = S.conv_p[li];
+                const bool conv2 = (li & 1) != 0;
+                const int xa = li & ~1; // input of the BasicBlock this conv belongs to
+                const ActLayout in_l = act_layout(li), x_l = xa == 0 ? l0q : act_layout(xa);
+                const __half *xp = xa == 0 ? S.act0q : S.act_h[xa];
+                CU(conv_umma_prepare(li, &p, S.act_h[li], in_l, conv2 ? xp : nullptr, conv2 ? &x_l : nullptr, (size_t)S.cap));
+                p.w = secp<__half>(c, SEC_W_F16 + li);
+                p.bias = secp<__half>(c, SEC_BIAS_MMA + li);
+                p.bias_f32 = secp<float>(c, SEC_BIAS_FUSED + li);
+                p.x_w = conv2 ? secp<__half>(c, SEC_X_W_F16 + li) : nullptr;
+                p.out = S.act_h[li + 1];
+                p.relu = 1;
+            }
         }
         CU(cudaStreamSynchronize(c->stream));
         CU(cudaMalloc(&c->d_in, (size_t)max_batch * CTU_IN_ELEMS * sizeof(int16_t)));
@@ -551,7 +575,20 @@ int mlt_predict_batch_device(mlt_ctx *c, int n, const int16_t *d_orgpred, const 
     dense_descs_kernel<<<(n + 255) / 256, 256, 0, s>>>(c->d_ctus, d_orgpred, d_pocqp, n);
     CU(cudaGetLastError());
     c->launches++;
-    return run_network(c, c->d_ctus, n, d_out, s);
+    static const bool no_slice = getenv("MLT_NO_SLICE") != nullptr; // A/B switch for measurements
+    if (n < 2 * 240 || c->profiling || c->engine != 0 || no_slice) return run_network(c, c->d_ctus, n, d_out, s);
+    // two slices on two streams: the inter-kernel gaps of one slice are filled by the other slice's kernels
+    const int n0 = (n + 1) / 2;
+    CU(cudaEventRecord(c->ev_fork, s));
+    CU(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+    rc = run_network(c, c->d_ctus, n0, d_out, s, 0);
+    if (rc) return rc;
+    rc = run_network(c, c->d_ctus + n0, n - n0, d_out + n0, c->stream2, 1);
+    if (rc) return rc;
+    CU(cudaEventRecord(c->ev_join, c->stream2));
+    CU(cudaStreamWaitEvent(s, c->ev_join, 0));
+    c->last_n = 0; // debug_activation only sees single-slice batches
+    return MLT_OK;
 }
 
 int mlt_begin_picture(mlt_ctx *c, const int16_t *org_luma, int stride, int width, int height, int poc)
@@ -634,11 +671,11 @@ int64_t mlt_debug_activation(mlt_ctx *c, int layer, float *out, int64_t capacity
         if (rc) return rc;
         if (layer == 0 && c->engine == 0) {
             // the fused stem never materialises conv1's output: recompute it for the last batch with the standalone kernel
-            rc = ensure_act0(c);
+            rc = ensure_act0(c, c->set[0]);
             if (rc) return rc;
-            CU(launch_conv1_umma(c->d_ctus, c->last_n, secp<__half>(c, SEC_CONV1_UMMA), c->act_h[0], s));
+            CU(launch_conv1_umma(c->d_ctus, c->last_n, secp<__half>(c, SEC_CONV1_UMMA), c->set[0].act_h[0], s));
         }
-        CU(launch_unpack_act(c->act_h[layer], c->d_dbg, c->last_n, act_layout(layer), s));
+        CU(launch_unpack_act(c->set[0].act_h[layer], c->d_dbg, c->last_n, act_layout(layer), s));
         CU(cudaMemcpyAsync(out, c->d_dbg, elems * sizeof(float), cudaMemcpyDeviceToHost, s));
     } else {
         if (!c->act_f[layer]) return fail(c, MLT_E_STATE, "fp32 engine has not run");

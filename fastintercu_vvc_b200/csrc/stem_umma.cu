@@ -173,8 +173,13 @@ __global__ void __launch_bounds__(stem::NTHREADS, 1) stem_umma_kernel(const Stem
 #pragma unroll
             for (int k = 0; k < EPT; k++) {
                 if (src[k] >= 0) {
-                    const uint32_t *hp = H + src[k];
-                    *reinterpret_cast<uint4 *>(ep + (size_t)(st + k * 128) * 16) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+                    // three aligned 8-byte loads (conflict-free: consecutive lanes are 8 bytes apart) + a parity select,
+                    // instead of four 4-byte loads at an 8-byte lane stride (2..4-way bank conflicts)
+                    const uint2 *hp = reinterpret_cast<const uint2 *>(H + (src[k] & ~1));
+                    const uint2 w0 = hp[0], w1 = hp[1], w2 = hp[2];
+                    const bool odd = src[k] & 1;
+                    *reinterpret_cast<uint4 *>(ep + (size_t)(st + k * 128) * 16) =
+                        odd ? make_uint4(w0.y, w1.x, w1.y, w2.x) : make_uint4(w0.x, w0.y, w1.x, w1.y);
                 }
             }
             fence_proxy_async_smem();
