@@ -305,6 +305,15 @@ def main():
         pred.predict_batch_dense(f_in, f_pq, f_out)
     frame_ms = (time.perf_counter() - t0) / 20 * 1e3
 
+    # ---- single-CTU latency: the in-encoder hook call (mlt_predict_ctu: 64 KiB H2D, 18 launches, 88 B D2H, synchronous)
+    o1, p1 = np.ascontiguousarray(orgpred_pinned[0, 0]), np.ascontiguousarray(orgpred_pinned[0, 1])
+    for _ in range(20):
+        pred.predict_ctu(o1, p1, int(pocqp_pinned[0, 0]), int(pocqp_pinned[0, 1]))
+    t0 = time.perf_counter()
+    for _ in range(200):
+        pred.predict_ctu(o1, p1, int(pocqp_pinned[0, 0]), int(pocqp_pinned[0, 1]))
+    ctu_us = (time.perf_counter() - t0) / 200 * 1e6
+
     if world > 1:
         t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -334,6 +343,7 @@ def main():
                          "peak_source": f"{how} bf16 sustained", "kernel_ms_per_step": umma_ms, "stem_ms": float(prof[0]),
                          "head_ms": float(prof[17]), "per_layer_ms": [round(float(x), 4) for x in prof[2:17]]},
             "frame_latency_ms": frame_ms,
+            "ctu_latency_us": ctu_us,
             "tflops_whole_net": value / world * FLOP_PER_CTU / 1e12,
         }
         if not args.no_cpu_baseline and world == 1:

@@ -122,8 +122,7 @@ static cudaError_t launch_one(const ConvParams &p, int num_sms, cudaStream_t s)
     const int ntiles = C::num_tiles(p.nimg);
     if (ntiles <= 0) return cudaSuccess;
     const int grid = ntiles < num_sms ? ntiles : num_sms; // persistent: one CTA per SM
-    conv_umma_kernel<C><<<grid, C::NTHREADS, C::SMEM_BYTES, s>>>(p);
-    return cudaGetLastError();
+    return launch_pdl(conv_umma_kernel<C>, dim3(grid), dim3(C::NTHREADS), C::SMEM_BYTES, s, p);
 }
 
 cudaError_t launch_conv_umma(int layer, const ConvParams &p, int num_sms, cudaStream_t s)

@@ -154,6 +154,10 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t sA = smem_u32(smem + C::OFF_A), sB = smem_u32(smem + C::OFF_B);
+    // PDL: let the next kernel of the stream start its prologue; everything that touches activations waits for the
+    // previous kernel here -- the weight loader does not (weights are constants), so its copies overlap that tail
+    griddep_launch_dependents();
+    if (warp != C::W_BLOAD) griddep_wait();
 
     if (warp < 8) {
         // ======================= epilogue: TMEM (bias, conv, shortcut / residual all accumulated) -> regs -> ReLU -> fp16

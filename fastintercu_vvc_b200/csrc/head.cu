@@ -3,6 +3,7 @@
 // per-level split flags.  One block per CTU; all reductions run in a fixed order (smem partials +
 // warp shuffles), so results are bit-reproducible run to run -- an encoder must be deterministic.
 #include "mlt_internal.h"
+#include "ptx.cuh"
 
 namespace mlt {
 
@@ -89,6 +90,8 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadParams p)
     __shared__ float feat[64 + 128 + 256];
     __shared__ float logits[9];
     const int n = blockIdx.x;
+    griddep_launch_dependents();
+    griddep_wait(); // PDL: activations come from the previous kernel
     if constexpr (sizeof(T) == 2) { // layouts of activations 8 / 12 / 16 (conv_umma.cu L1d / L2d / L3d outputs)
         gap_planar<32, 64, 1, 0>(static_cast<const __half *>(p.act[0]), n, partial, feat);
         gap_planar<16, 128, 1, 1>(static_cast<const __half *>(p.act[1]), n, partial, feat + 64);
@@ -151,8 +154,7 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadParams p)
 
 cudaError_t launch_head_h(const HeadParams &p, cudaStream_t s)
 {
-    head_kernel<__half><<<p.n, 256, 0, s>>>(p);
-    return cudaGetLastError();
+    return launch_pdl(head_kernel<__half>, dim3(p.n), dim3(256), 0, s, p);
 }
 cudaError_t launch_head_f(const HeadParams &p, cudaStream_t s)
 {

@@ -4,6 +4,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/mltcnn.h"
 
@@ -26,6 +27,25 @@ struct LayerDesc { // one 3x3 conv of the residual stack (forward order, after c
 
 // (float)(1.0/1023): the alpha OpenCV's convertTo uses at EncCu.cpp:835-838, bit pattern 0x3A802008
 #define MLT_ALPHA_BITS 0x3A802008u
+
+// Launch with programmatic stream serialization (PDL): the kernel's prologue may overlap the tail of the previous
+// kernel in the stream; the kernel itself orders its dependent accesses with griddepcontrol.wait (ptx.cuh).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static const bool no_pdl = getenv("MLT_NO_PDL") != nullptr; // A/B switch for measurements
+    cfg.attrs = attr;
+    cfg.numAttrs = no_pdl ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // ---- stage_conv1.cu
 // fp32 normalised input tensor [n][2][128][128] (bit-exactness probe of EncCu.cpp:810-867)

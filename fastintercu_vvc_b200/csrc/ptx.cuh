@@ -23,6 +23,13 @@ __device__ __forceinline__ bool elect_one_sync()
     return pred != 0;
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch (PDL)
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the
+// stream is still running: everything before griddep_wait() (barrier init, TMEM allocation, weight loads) overlaps the
+// predecessor's tail; griddep_wait() returns once the predecessor has completed and its writes are visible.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {

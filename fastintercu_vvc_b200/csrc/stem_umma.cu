@@ -103,6 +103,8 @@ __global__ void __launch_bounds__(stem::NTHREADS, 1) stem_umma_kernel(const Stem
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const uint32_t sPatch = smem_u32(smem + OFF_PATCH), sEP = smem_u32(smem + OFF_EP);
+    griddep_launch_dependents(); // PDL: the prologue above overlapped the previous kernel's tail
+    griddep_wait();
 
     if (warp >= W_STG) {
         // ======================= stagers: int16 window -> fp16 {org, res} pair plane H -> expanded, parity-split operand EP
@@ -351,8 +353,7 @@ cudaError_t launch_stem_umma(const CtuDev *ctus, int n, const __half *w1, const 
     if (n <= 0) return cudaSuccess;
     StemParams p{ctus, w1, w0, bias, act0q, act1, n};
     const int units = n * 16;
-    stem_umma_kernel<<<units < num_sms ? units : num_sms, stem::NTHREADS, stem::SMEM_BYTES, s>>>(p);
-    return cudaGetLastError();
+    return launch_pdl(stem_umma_kernel, dim3(units < num_sms ? units : num_sms), dim3(stem::NTHREADS), stem::SMEM_BYTES, s, p);
 }
 
 } // namespace mlt
