@@ -471,6 +471,7 @@ int mlt_create_ex(mlt_ctx **out, const char *weights_path, int cuda_device, int 
                 p.x_w = conv2 ? secp<__half>(c, SEC_X_W_F16 + li) : nullptr;
                 p.out = S.act_h[li + 1];
                 p.relu = 1;
+                p.reverse = getenv("MLT_NO_REVERSE") ? 0 : (li & 1); // the stem walks the images upwards, conv 1 downwards, conv 2 upwards, ...
             }
         }
         CU(cudaStreamSynchronize(c->stream));

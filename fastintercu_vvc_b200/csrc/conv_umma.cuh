@@ -172,11 +172,14 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
             for (int j = 0; j < C::COUT; j++) bias_r[j] = __ldg(p.bias_f32 + j);
         }
         for (int tile = blockIdx.x + grp * gridDim.x; tile < ntiles; tile += 2 * gridDim.x, acc_it += 2) {
+            // p.reverse: this layer walks the images in the opposite direction to the previous one, so that it starts on
+            // the activations the previous kernel wrote last (still in the 126 MB L2) -- consecutive layers zig-zag
+            const int ptile = p.reverse ? ntiles - 1 - tile : tile;
             int img, oy, ox;
-            if (C::NB == 2) { img = tile * 2 + h; oy = r; ox = c; }
+            if (C::NB == 2) { img = ptile * 2 + h; oy = r; ox = c; }
             else {
-                img = tile / C::TILES_PER_IMG;
-                const int rem = tile % C::TILES_PER_IMG;
+                img = ptile / C::TILES_PER_IMG;
+                const int rem = ptile % C::TILES_PER_IMG;
                 oy = (rem / (C::HOUT / 8)) * 16 + r;
                 ox = (rem % (C::HOUT / 8)) * 8 + c;
             }
@@ -396,7 +399,8 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
             for (int it = 0; it < C::NCG + C::NXS; it++) {
 #pragma unroll 1
                 for (int h = 0; h < np; h++, a_it++) {
-                    const int tile = tile0 + h * (int)gridDim.x;
+                    const int ltile = tile0 + h * (int)gridDim.x;
+                    const int tile = p.reverse ? ntiles - 1 - ltile : ltile;
                     int unit, oy0, ox0;
                     if (C::NB == 2) { unit = tile; oy0 = 0; ox0 = 0; }
                     else {

@@ -90,6 +90,7 @@ struct ConvParams {
     __half *out;
     int nimg;
     int relu;
+    int reverse;    // walk the tiles from the last image to the first (L2 reuse across consecutive layers)
     int x_unit_mul; // 4 when the extra operand tensor is parity-planar (plane 0 = even rows, even columns), else 1
 };
 
