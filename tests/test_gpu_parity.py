@@ -277,6 +277,32 @@ def test_device_resident_batch_via_torch(pred, ctus):
     assert dev.tobytes() == host.tobytes()
 
 
+def test_sliced_device_batch_matches_small_batches(blob, ctus):
+    """n >= 480 device-resident batches run as two slices on two streams / activation sets (odd split included):
+    every row must be bit-identical to the same CTU computed in a small single-slice batch."""
+    import torch
+
+    from fastintercu_vvc_b200 import MltPredictor
+    from fastintercu_vvc_b200.capi import RESULT_DTYPE
+
+    orgpred, pocqp = ctus
+    n = 601
+    idx = np.random.RandomState(7).randint(0, len(orgpred), n)
+    big, big_pq = np.ascontiguousarray(orgpred[idx]), np.ascontiguousarray(pocqp[idx])
+    with MltPredictor(blob, device=0, max_batch=640) as p:
+        base = p.predict_batch_dense(orgpred, pocqp)  # 24 CTUs, one slice
+        d_in, d_pq = torch.from_numpy(big).cuda(), torch.from_numpy(big_pq).cuda()
+        d_out = torch.zeros(n * RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+        st = torch.cuda.current_stream()
+        for _ in range(2):  # twice: the second pass reuses both activation sets
+            p.predict_batch_device(n, d_in.data_ptr(), d_pq.data_ptr(), d_out.data_ptr(), st.cuda_stream)
+        st.synchronize()
+        dev = np.frombuffer(d_out.cpu().numpy().tobytes(), RESULT_DTYPE)
+        host = p.predict_batch_dense(big, big_pq)  # n < 1024: one chunk, one slice
+    assert np.array_equal(dev["logits"].view(np.uint32), base["logits"][idx].view(np.uint32))
+    assert dev.tobytes() == host.tobytes()
+
+
 def test_errors(pred, blob, ctus):
     from fastintercu_vvc_b200 import MltError, MltPredictor
 
