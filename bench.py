@@ -132,8 +132,8 @@ def cpu_reference_rate(budget_s: float, threads: int | None = None):
 
     from oracle import ref_arch
 
-    if threads:
-        torch.set_num_threads(threads)
+    # all host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which would cripple the CPU arm)
+    torch.set_num_threads(threads or len(os.sched_getaffinity(0)))
     sd = ref_arch.make_state_dict(10)
     net = ref_arch.build_model(sd)
     ex = (torch.rand(1, 2, 128, 128), torch.rand(1), torch.rand(1))
