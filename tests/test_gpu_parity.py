@@ -260,6 +260,41 @@ def test_picture_staging_path(pred):
         pred.predict_ctu_in_picture(0, 128, p, 37)
 
 
+def test_cpp_hook_drives_the_library_like_the_encoder(pred, blob):
+    """The C++ hook mirror (what INTEGRATION.md patches into EncCu.cpp) run over a picture's CTU raster: gate, per-CTU
+    predict() with picture-strided pointers and the per-picture staging path give the ctypes binding's decisions."""
+    hook = os.path.join(ROOT, "fastintercu_vvc_b200", "hook")
+    exe = os.path.join(hook, "hook_encode_sim.bin")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", hook])
+    rng = np.random.RandomState(11)
+    w, h, stride, poc = 416, 240, 416 + 2 * 80 + 8, 9  # VTM-like margins; 3 eligible CTUs (EncCu.cpp:755)
+    base, _ = ref_arch.synth_ctus(3, 77)
+    org = rng.randint(0, 1024, (h, stride)).astype(np.int16)
+    for i in range(3):
+        org[0:128, 128 * i : 128 * i + 128] = base[i, 0]
+    preds = [base[i, 1] for i in range(3)]
+    qps = [37, 22, 41]
+    with tempfile.NamedTemporaryFile(suffix=".bin", delete=False) as f:
+        f.write(np.array([w, h, stride, poc, 3], np.int32).tobytes())
+        f.write(org.tobytes())
+        for q, p in zip(qps, preds):
+            f.write(np.array([q], np.int32).tobytes())
+            f.write(np.ascontiguousarray(p).tobytes())
+        path = f.name
+    try:
+        env = dict(os.environ, MLT_WEIGHTS=blob, MLT_DEVICE="0")
+        r = subprocess.run([exe, path], capture_output=True, text=True, timeout=120, env=env)
+    finally:
+        os.unlink(path)
+    assert r.returncode == 0, r.stdout + r.stderr
+    rows = [list(map(int, l.split())) for l in r.stdout.strip().splitlines()]
+    assert [(x, y) for x, y, _, _ in rows] == [(0, 0), (128, 0), (256, 0)]
+    for (x, y, a, b), q, p in zip(rows, qps, preds):
+        want = pred.predict_ctu(org[y : y + 128, x : x + 128], p, poc, q)["split_l3"]
+        assert a == want and b == want
+
+
 def test_device_resident_batch_via_torch(pred, ctus):
     import torch
 
