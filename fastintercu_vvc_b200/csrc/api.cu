@@ -252,7 +252,22 @@ int run_network(mlt_ctx *c, const CtuDev *ctus, int n, mlt_result *out, cudaStre
         for (int li = first; li < NCONV; li++) {
             ConvParams &p = S.conv_p[li];
             p.nimg = n;
+            static const int trace_layer = getenv("MLT_TRACE_LAYER") ? atoi(getenv("MLT_TRACE_LAYER")) : -1;
+            static long long *d_trace = nullptr;
+            if (li == trace_layer) { // debug: per-tile clock64 stamps of CTA 0's MMA warp -> stderr (last call wins)
+                if (!d_trace) CU(cudaMalloc(&d_trace, 1024 * sizeof(long long)));
+                CU(cudaMemsetAsync(d_trace, 0, 1024 * sizeof(long long), s));
+                p.trace = d_trace;
+            }
             CU(launch_conv_umma(li, p, c->num_sms, s));
+            if (li == trace_layer && getenv("MLT_TRACE_DUMP")) {
+                static long long h[1024];
+                CU(cudaStreamSynchronize(s));
+                CU(cudaMemcpy(h, d_trace, sizeof h, cudaMemcpyDeviceToHost));
+                fprintf(stderr, "trace layer %d:", li);
+                for (int k = 1; k < 1024 && h[k]; k++) fprintf(stderr, " %lld", h[k] - h[k - 1]);
+                fprintf(stderr, "\n");
+            }
             c->launches++;
             if (prof) CU(cudaEventRecord(c->prof_ev[ev++], s));
         }
@@ -471,6 +486,7 @@ int mlt_create_ex(mlt_ctx **out, const char *weights_path, int cuda_device, int 
                 p.x_w = conv2 ? secp<__half>(c, SEC_X_W_F16 + li) : nullptr;
                 p.out = S.act_h[li + 1];
                 p.relu = 1;
+                p.dbg = getenv("MLT_DEBUG_FLAGS") ? atoi(getenv("MLT_DEBUG_FLAGS")) : 0;
                 p.reverse = getenv("MLT_NO_REVERSE") ? 0 : (li & 1); // the stem walks the images upwards, conv 1 downwards, conv 2 upwards, ...
             }
         }

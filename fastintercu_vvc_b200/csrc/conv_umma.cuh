@@ -21,8 +21,9 @@
 //    epilogue therefore never loads anything: TMEM -> regs -> ReLU -> fp16 -> global.
 //  * Folded weights are pre-packed offline in exactly the smem operand layout; each (cin_group, tap) slab is one
 //    contiguous cp.async.bulk into a ring, or the whole layer is resident in smem for the 32/64-channel layers.
-//  * Warp-specialised persistent CTA (1 per SM, 11 warps): 2 x 4 epilogue warps taking alternate tiles, 1 MMA-issuer
-//    warp (one elected thread issues tcgen05.mma), 1 weight-copy warp, 1 activation-TMA warp.  2-4 TMEM accumulator
+//  * Warp-specialised persistent CTA (1 per SM, 12 warps): 2 x 4 epilogue warps taking alternate tiles, 1 MMA-issuer
+//    warp (one elected thread issues tcgen05.mma; 2 issuer warps on alternate tiles for the resident-weight layers,
+//    whose MMA stream is otherwise instruction-issue-bound), 1 weight-copy warp, 1 activation-TMA warp.  2-4 TMEM accumulator
 //    stages overlap the epilogue of tile i with the MMAs of tiles i+1...; the bias enters the accumulator through one
 //    extra K=16 MMA (ones x [hi(b), lo(b)]).
 #pragma once
@@ -92,8 +93,10 @@ struct ConvCfg {
     static constexpr int SMEM_BYTES = OFF_TMEM + 16;
     static constexpr int TMEM_COLS = (NACC * COUT <= 32) ? 32 : (NACC * COUT <= 64 ? 64 : (NACC * COUT <= 128 ? 128 : (NACC * COUT <= 256 ? 256 : 512)));
     // warp roles: 0-3 epilogue group 0, 4-7 epilogue group 1 (alternate tiles), 8 MMA issuer, 9 weight loader, 10 activation TMA
-    static constexpr int W_MMA = 8, W_BLOAD = 9, W_ALOAD = 10;
-    static constexpr int NTHREADS = 352;
+    // (resident-weight layers: a second issuer warp takes the odd tiles -- one warp cannot issue a tile's ~220 instructions
+    //  in the 750 cycles its 18 N=32 MMAs take, see profiles/r01/README.md)
+    static constexpr int W_MMA = 8, W_BLOAD = 9, W_ALOAD = 10, W_MMA2 = 11;
+    static constexpr int NTHREADS = 384;
     static constexpr int TILES_PER_IMG = (NB == 2) ? 1 : (HOUT / 16) * (HOUT / 8);
     // layouts of the tensors this conv touches
     static constexpr int IN_PAIR = (NB == 2);
@@ -171,7 +174,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
 #pragma unroll
             for (int j = 0; j < C::COUT; j++) bias_r[j] = __ldg(p.bias_f32 + j);
         }
-        for (int tile = blockIdx.x + grp * gridDim.x; tile < ntiles; tile += 2 * gridDim.x, acc_it += 2) {
+        for (int tile = blockIdx.x + grp * gridDim.x; tile < ((C::RESIDENT && (p.dbg & 8)) ? 0 : ntiles); tile += 2 * gridDim.x, acc_it += 2) {
             // p.reverse: this layer walks the images in the opposite direction to the previous one, so that it starts on
             // the activations the previous kernel wrote last (still in the 126 MB L2) -- consecutive layers zig-zag
             const int ptile = p.reverse ? ntiles - 1 - tile : tile;
@@ -183,7 +186,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
                 oy = (rem / (C::HOUT / 8)) * 16 + r;
                 ox = (rem % (C::HOUT / 8)) * 8 + c;
             }
-            const bool valid = img < p.nimg;
+            const bool valid = img < p.nimg && !(p.dbg & 2);
             const int unit = C::OUT_PAIR ? img >> 1 : img, sub = C::OUT_PAIR ? img & 1 : 0;
             const int plane = C::OUT_PAR ? (oy & 1) * 2 + (ox & 1) : 0;
             const int yy = C::OUT_PAR ? oy >> 1 : oy, xx = C::OUT_PAR ? ox >> 1 : ox;
@@ -193,7 +196,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
             mbar_wait(&accFull[acc], (acc_it / C::NACC) & 1);
             tc_fence_after();
 #pragma unroll(C::BIAS_REG ? 2 : 1)
-            for (int c0 = 0; c0 < C::COUT; c0 += 32) {
+            for (int c0 = 0; c0 < ((p.dbg & 4) ? 0 : C::COUT); c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + acc * C::COUT + c0, v);
                 tmem_ld_wait();
@@ -220,7 +223,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
             tc_fence_before();
             mbar_arrive(&accEmpty[acc]);
         }
-    } else if (warp == C::W_MMA) {
+    } else if (warp == C::W_MMA || (C::RESIDENT && warp == C::W_MMA2)) {
         // ======================= MMA issuer: the whole warp runs the (uniform) control flow and the waits,
         // one elected lane issues tcgen05.mma / tcgen05.commit
         constexpr uint32_t idesc = umma_idesc_f16(128, C::COUT);
@@ -228,7 +231,69 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
         const uint32_t ones_lo = umma_desc_lo(smem_u32(smem + C::OFF_ONES), 128 * 16);
         const uint32_t bias_lo = umma_desc_lo(smem_u32(smem + C::OFF_BIAS), C::COUT * 16);
         uint32_t a_it = 0, b_it = 0, acc_it = 0;
-        if constexpr (C::RESIDENT) { mbar_wait(&fullB[0], 0); tc_fence_after(); }
+        if constexpr (C::RESIDENT) {
+            // ---- weights resident (32/64-channel layers): one activation stage (+ one extra-operand stage) per tile.
+            // These layers are bound by the MMA stream itself (18 N=32 MMAs = 750 cycles per tile) and ONE warp needs
+            // ~930 cycles to issue a tile's ~220 instructions (measured: clock64 per tile, profiles/r01/README.md), so
+            // two issuer warps take alternate tiles.
+            static_assert(!C::RESIDENT || (C::NCG == 1 && C::NXS <= 1 && C::TP == 1 && C::BIAS_REG), "resident-weight path assumptions");
+            constexpr int SPT = 1 + C::NXS; // stages per tile
+            static_assert(!C::RESIDENT || C::NAS >= 3 * SPT, "A ring must hold the two tiles in flight plus one prefetched");
+            mbar_wait(&fullB[0], 0);
+            auto wait_tile = [&](uint32_t j) {
+                if (p.dbg & 8) return; // debug: free-running MMA stream, no handshakes
+                mbar_wait(&accEmpty[j % C::NACC], ((j / C::NACC) & 1) ^ 1);
+#pragma unroll
+                for (int sidx = 0; sidx < SPT; sidx++) {
+                    const uint32_t it = j * SPT + sidx;
+                    mbar_wait(&fullA[it % C::NAS], (it / C::NAS) & 1);
+                }
+            };
+            // two issuer warps: W_MMA takes the even local tiles, W_MMA2 the odd ones (different accumulators and stages;
+            // tcgen05.commit tracks the MMAs of the issuing thread, so each tile's barriers see exactly its own MMAs)
+            const uint32_t iss = warp == C::W_MMA ? 0u : 1u;
+            uint32_t j = iss;
+            for (int tile = blockIdx.x + iss * gridDim.x; tile < ntiles; tile += 2 * gridDim.x, j += 2) {
+                wait_tile(j); // each issuer has two tile-times per tile: the wait latency is off the critical path
+                if (p.trace != nullptr && blockIdx.x == 0 && j < 1024 && lane == 0) p.trace[j] = clock64();
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (j % C::NACC) * C::COUT;
+                const uint32_t st0 = (j * SPT) % C::NAS;
+                const uint32_t a_lo0 = umma_desc_lo(sA + st0 * C::A_STAGE_BYTES, C::A_LBO);
+                auto issue_taps = [&](int t0, int t1) {
+#pragma unroll
+                    for (int tap = t0; tap < t1; tap++) {
+                        const uint32_t b_lo0 = umma_desc_lo(sB + tap * C::SLAB_BYTES, C::COUT * 16);
+                        const uint32_t a_tap = a_lo0 + tap_offset16<C>(tap / 3, tap % 3);
+#pragma unroll
+                        for (int ks = 0; ks < C::G / 16; ks++)
+                            umma_f16(d_tmem, umma_desc_pack(a_tap + ks * (2 * C::A_LBO / 16), a_hi),
+                                     umma_desc_pack(b_lo0 + ks * (2 * C::COUT), b_hi), idesc, (tap == 0 && ks == 0) ? 0u : 1u);
+                    }
+                };
+                if (elect_one_sync()) {
+                    issue_taps(0, 9);
+                    if (!(p.dbg & 16)) umma_commit(&emptyA[st0]);
+                    if constexpr (C::XC > 0) {
+                        const uint32_t st1 = (j * SPT + 1) % C::NAS;
+                        const uint32_t x_lo0 = umma_desc_lo(sA + st1 * C::A_STAGE_BYTES, C::X_LBO);
+                        const uint32_t b_lo0 = umma_desc_lo(sB + C::W_MAIN_BYTES, C::COUT * 16);
+#pragma unroll
+                        for (int ks = 0; ks < C::GX / 16; ks++)
+                            umma_f16(d_tmem, umma_desc_pack(x_lo0 + ks * (2 * C::X_LBO / 16), x_hi),
+                                     umma_desc_pack(b_lo0 + ks * (2 * C::COUT), b_hi), idesc, 1);
+                        if (!(p.dbg & 16)) umma_commit(&emptyA[st1]);
+                    }
+                    if (!(p.dbg & 16)) umma_commit(&accFull[j % C::NACC]);
+                }
+                __syncwarp();
+            }
+            if (p.dbg & 8) { // drain before the TMEM is released
+                if (elect_one_sync()) umma_commit(&emptyB[0]);
+                __syncwarp();
+                mbar_wait(&emptyB[0], 0);
+            }
+        } else
         // One pass = TP tiles (a PAIR when the weights are streamed): every weight slab fetched from L2 feeds the MMAs of
         // both tiles, which halves the L2 -> smem weight traffic that otherwise bounds the 128/256-channel layers.
         for (int tile = blockIdx.x; tile < ntiles; tile += C::TP * gridDim.x) {
@@ -392,7 +457,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
         // stride-2 conv]; the halo / zero padding comes from the TMA out-of-bounds fill
         if (lane == 0) { tma_prefetch_desc(&p.in_map); if (C::XC > 0) tma_prefetch_desc(&p.x_map); }
         uint32_t a_it = 0;
-        for (int tile0 = blockIdx.x; tile0 < ntiles; tile0 += C::TP * gridDim.x) {
+        for (int tile0 = blockIdx.x; tile0 < ((C::RESIDENT && (p.dbg & 8)) ? 0 : ntiles); tile0 += C::TP * gridDim.x) {
             const int np = (C::TP == 2 && tile0 + (int)gridDim.x < ntiles) ? 2 : 1;
             // stage order of a pass: (step 0, tile 0), (step 0, tile 1), (step 1, tile 0), ... -- what the MMA issuer consumes
 #pragma unroll 1
@@ -411,7 +476,9 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
                     }
                     const uint32_t st = a_it % C::NAS;
                     mbar_wait(&emptyA[st], ((a_it / C::NAS) & 1) ^ 1);
-                    if (elect_one_sync()) {
+                    if ((p.dbg & 1) && a_it >= (uint32_t)C::NAS) { // debug: stale smem, no TMA traffic
+                        if (elect_one_sync()) mbar_arrive(&fullA[st]);
+                    } else if (elect_one_sync()) {
                         const uint32_t abase = sA + st * C::A_STAGE_BYTES;
                         if (it < C::NCG) {
                             mbar_arrive_expect_tx(&fullA[st], C::A_TX_BYTES);

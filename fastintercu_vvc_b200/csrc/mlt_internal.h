@@ -90,6 +90,8 @@ struct ConvParams {
     __half *out;
     int nimg;
     int relu;
+    long long *trace; // MLT_TRACE_LAYER debug: CTA 0's MMA warp stores clock64() at every tile start (<= 1024 entries), or nullptr
+    int dbg;        // MLT_DEBUG_FLAGS (timing experiments only, results invalid): 1 no activation TMA, 2 no stores, 4 no TMEM reads
     int reverse;    // walk the tiles from the last image to the first (L2 reuse across consecutive layers)
     int x_unit_mul; // 4 when the extra operand tensor is parity-planar (plane 0 = even rows, even columns), else 1
 };
