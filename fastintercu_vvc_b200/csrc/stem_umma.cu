@@ -27,8 +27,9 @@
 namespace mlt {
 
 namespace stem {
-constexpr int NTHREADS = 17 * 32;
-constexpr int W_E2 = 0, W_E1 = 4, W_MMA = 12, W_STG = 13; // warp roles (first warp of each group)
+constexpr int NE1 = 8;                                      // mid-epilogue warps (2 per TMEM lane quadrant; 16 measured no faster: the stem is smem-port-bound)
+constexpr int NTHREADS = (4 + NE1 + 1 + 4) * 32;           // 800
+constexpr int W_E2 = 0, W_E1 = 4, W_MMA = 4 + NE1, W_STG = W_MMA + 1; // warp roles (first warp of each group)
 constexpr int PE = 17, PLANE_ENT = PE * PE;                // 289 entries per parity plane
 constexpr int P_LBO = PLANE_ENT * 16;                      // bytes between 8-channel chunks of the patch
 constexpr int P_PLANE = 4 * P_LBO;                         // one parity plane (32 channels)
@@ -82,7 +83,7 @@ __global__ void __launch_bounds__(stem::NTHREADS, 1) stem_umma_kernel(const Stem
     if (tid == 0) {
         for (int i = 0; i < 2; i++) {
             mbar_init(&ep_full[i], 4); mbar_init(&ep_empty[i], 1);
-            mbar_init(&patch_full[i], 8); mbar_init(&patch_empty[i], 1);
+            mbar_init(&patch_full[i], NE1); mbar_init(&patch_empty[i], 1);
             mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 4);
         }
         for (int i = 0; i < 12; i++) mbar_init(&c1_full[i], 1);
@@ -260,7 +261,7 @@ __global__ void __launch_bounds__(stem::NTHREADS, 1) stem_umma_kernel(const Stem
         }
     } else if (warp >= W_E1) {
         // ======================= mid-epilogue: conv1 accumulators -> fp16 -> stride-2 conv's operand patch (+ even/even quarter to HBM)
-        const int wq = warp & 3, hsel = (warp - W_E1) >> 2; // TMEM lane quadrant; which half of the 12 tiles
+        const int wq = warp & 3, hsel = (warp - W_E1) >> 2; // TMEM lane quadrant; which of the NE1/4 tile subsets
         uint32_t ul = 0;
         for (int u = blockIdx.x; u < total_units; u += gridDim.x, ul++) {
             const int ctu = u >> 4, oy0 = ((u >> 2) & 3) * 16, ox0 = (u & 3) * 16;
@@ -268,7 +269,7 @@ __global__ void __launch_bounds__(stem::NTHREADS, 1) stem_umma_kernel(const Stem
             mbar_wait(&patch_empty[buf], ((ul >> 1) & 1) ^ 1);
             uint8_t *patch = smem + OFF_PATCH + buf * PATCH_BYTES;
 #pragma unroll 1
-            for (int k = hsel; k < 12; k += 2) {
+            for (int k = hsel; k < 12; k += NE1 / 4) {
                 const int plane = k / 3, t = k % 3, py = plane >> 1, px = plane & 1;
                 const int e = t * 128 + wq * 32 + lane, i = e / PE, j = e % PE;
                 mbar_wait(&c1_full[k], ul & 1);
