@@ -68,6 +68,7 @@ struct mlt_ctx {
         __half *act_h[NACT] = {}; // [0] (conv1's full output, parity-planar) exists only for the unfused engine / debug reads
         __half *act0q = nullptr;  // conv1's output at even rows / columns (input of layer0.0's shortcut), dense [n][4][64][64][8]
         ConvParams conv_p[NCONV]; // tensor maps + weight pointers of every tcgen05 conv, built once at create
+        float *gap_part[3] = {};  // pool partial sums written by convs 7 / 11 / 15: [cap][8 | 2 | 1 tiles][4][64 | 128 | 256]
         int cap = 0;              // images
     } set[2];
     cudaStream_t stream2 = nullptr;            // second compute stream (slice 1)
@@ -271,7 +272,7 @@ int run_network(mlt_ctx *c, const CtuDev *ctus, int n, mlt_result *out, cudaStre
             c->launches++;
             if (prof) CU(cudaEventRecord(c->prof_ev[ev++], s));
         }
-        hp.act[0] = S.act_h[8]; hp.act[1] = S.act_h[12]; hp.act[2] = S.act_h[16];
+        for (int i = 0; i < 3; i++) hp.gap_part[i] = S.gap_part[i];
         CU(launch_head_h(hp, s));
         c->launches++;
         if (prof) { CU(cudaEventRecord(c->prof_ev[ev++], s)); c->prof_valid = true; }
@@ -416,7 +417,7 @@ void mlt_destroy(mlt_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    for (auto &S : c->set) { for (int a = 0; a < NACT; a++) cudaFree(S.act_h[a]); cudaFree(S.act0q); }
+    for (auto &S : c->set) { for (int a = 0; a < NACT; a++) cudaFree(S.act_h[a]); cudaFree(S.act0q); for (float *g : S.gap_part) cudaFree(g); }
     for (int a = 0; a < NACT; a++) cudaFree(c->act_f[a]);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
@@ -472,6 +473,8 @@ int mlt_create_ex(mlt_ctx **out, const char *weights_path, int cuda_device, int 
                 CU(cudaMemsetAsync(S.act_h[a], 0, bytes, c->stream));
             }
             CU(cudaMalloc(&S.act0q, l0q.unit_elems() * (size_t)S.cap * sizeof(__half)));
+            static const int gp_per_img[3] = {8 * 4 * 64, 2 * 4 * 128, 4 * 256};
+            for (int i = 0; i < 3; i++) CU(cudaMalloc(&S.gap_part[i], ((size_t)S.cap + 1) * gp_per_img[i] * sizeof(float)));
             memset(S.conv_p, 0, sizeof S.conv_p);
             for (int li = 1; li < NCONV; li++) { // conv 0 runs inside the stem kernel (ensure_act0 prepares it for the unfused engine)
                 ConvParams &p = S.conv_p[li];
@@ -485,6 +488,7 @@ int mlt_create_ex(mlt_ctx **out, const char *weights_path, int cuda_device, int 
                 p.bias_f32 = secp<float>(c, SEC_BIAS_FUSED + li);
                 p.x_w = conv2 ? secp<__half>(c, SEC_X_W_F16 + li) : nullptr;
                 p.out = S.act_h[li + 1];
+                p.gap_part = li == 7 ? S.gap_part[0] : (li == 11 ? S.gap_part[1] : (li == 15 ? S.gap_part[2] : nullptr));
                 p.relu = 1;
                 p.dbg = getenv("MLT_DEBUG_FLAGS") ? atoi(getenv("MLT_DEBUG_FLAGS")) : 0;
                 p.reverse = getenv("MLT_NO_REVERSE") ? 0 : (li & 1); // the stem walks the images upwards, conv 1 downwards, conv 2 upwards, ...

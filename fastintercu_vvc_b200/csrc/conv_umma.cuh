@@ -83,6 +83,9 @@ struct ConvCfg {
     // bias: for the smem-operand-bound 32/64-channel layers it is added in the epilogue from registers (an extra MMA
     // would cost 5 % / 3 % of the tile); for 128/256 channels it enters the accumulator through one K=16 MMA
     static constexpr bool BIAS_REG = COUT <= 64;
+    // last conv of a stage whose output feeds a prediction head (layer1.1 / layer2.1 / layer3.1 conv2, arch.py:282,288,294):
+    // the epilogue also emits per-tile global-average-pool partial sums, so the head never re-reads the activation
+    static constexpr bool GAP = (XC == COUT) && COUT >= 64;
     static constexpr int NBAR = 2 * NAS + 2 * (RESIDENT ? 1 : NBS) + 2 * NACC;
     static constexpr int OFF_A = 0;
     static constexpr int OFF_B = OFF_A + NAS * A_STAGE_BYTES;
@@ -204,19 +207,50 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
 #pragma unroll
                     for (int j = 0; j < 32; j++) v[j] = __float_as_uint(__uint_as_float(v[j]) + bias_r[c0 + j]);
                 }
+                const __half2 zero2 = __float2half2_rn(0.0f);
+                __half2 hq[16]; // ReLU(fp16(x)) of this pixel's 32 channels: what is stored, and what the pool sums
+#pragma unroll
+                for (int e = 0; e < 16; e++) {
+                    const __half2 t = __floats2half2_rn(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
+                    hq[e] = p.relu ? __hmax2(t, zero2) : t; // max(round(x), 0) == round(max(x, 0))
+                }
                 if (valid) {
-                    const __half2 zero2 = __float2half2_rn(0.0f);
                     __half *op = p.out + off + (size_t)(c0 / 8) * C::OCHUNK;
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
                         uint4 ov;
                         __half2 *h2 = reinterpret_cast<__half2 *>(&ov);
 #pragma unroll
-                        for (int e = 0; e < 4; e++) {
-                            const __half2 t = __floats2half2_rn(__uint_as_float(v[q * 8 + e * 2]), __uint_as_float(v[q * 8 + e * 2 + 1]));
-                            h2[e] = p.relu ? __hmax2(t, zero2) : t; // max(round(x), 0) == round(max(x, 0))
-                        }
+                        for (int e = 0; e < 4; e++) h2[e] = hq[q * 4 + e];
                         *reinterpret_cast<uint4 *>(op + (size_t)q * C::OCHUNK) = ov;
+                    }
+                }
+                if constexpr (C::GAP) {
+                    // Global-average-pool partial sums of this tile (fixed shuffle tree => bit-reproducible): a transpose-
+                    // reduce over the warp's 32 pixels leaves lane l with the sum of channel c0 + l (pair tiles: 16 pixels per
+                    // image, two channels per lane); one partial per (tile, image, lane quadrant, channel) goes to HBM and the
+                    // head adds the few partials of an image in a fixed order.
+                    float gv[32];
+#pragma unroll
+                    for (int e = 0; e < 16; e++) { const float2 t = __half22float2(hq[e]); gv[2 * e] = t.x; gv[2 * e + 1] = t.y; }
+                    auto fold = [&](int off, int nkeep) { // lanes with bit `off` keep the upper half of the list
+                        const bool upper = (lane & off) != 0;
+#pragma unroll
+                        for (int i = 0; i < 16; i++) {
+                            if (i < nkeep) {
+                                const float send = upper ? gv[i] : gv[i + nkeep], keep = upper ? gv[i + nkeep] : gv[i];
+                                gv[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                            }
+                        }
+                    };
+                    float *gp = p.gap_part + ((size_t)(ptile * C::NB + h) * 4 + wq) * C::COUT + c0;
+                    if constexpr (C::NB == 1) {
+                        fold(16, 16); fold(8, 8); fold(4, 4); fold(2, 2); fold(1, 1);
+                        gp[lane] = gv[0]; // channel bits == lane bits
+                    } else {
+                        fold(16, 16); fold(4, 8); fold(2, 4); fold(1, 2); // lane bit 3 selects the image: not folded
+                        const int cb = ((lane >> 4) & 1) * 16 + (lane & 7) * 2;
+                        *reinterpret_cast<float2 *>(gp + cb) = make_float2(gv[0], gv[1]);
                     }
                 }
             }

@@ -55,34 +55,6 @@ __device__ __forceinline__ void gap_nhwc(const float *act, float *partial /*[256
     __syncthreads();
 }
 
-template <int H, int C, int PAR, int PAIR>
-__device__ __forceinline__ void gap_planar(const __half *act, int img, float *partial /*[256/(C/8)][C]*/, float *feat)
-{
-    constexpr int HP = PAR ? H / 2 : H, NPL = PAR ? 4 : 1, NIMG = PAIR ? 2 : 1;
-    constexpr int CH = C / 8, TPC = 256 / CH; // threads per chunk
-    constexpr size_t CHUNK = (size_t)HP * NIMG * HP * 8;
-    const int cj = threadIdx.x / TPC, pp = threadIdx.x % TPC;
-    const size_t unit = PAIR ? img >> 1 : img;
-    const int sub = PAIR ? img & 1 : 0;
-    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int p = pp; p < NPL * HP * HP; p += TPC) {
-        const int plane = p / (HP * HP), yy = (p / HP) % HP, xx = p % HP;
-        float f[8];
-        load8<__half>(act + ((unit * NPL + plane) * CH + cj) * CHUNK + (size_t)((yy * NIMG + sub) * HP + xx) * 8, f);
-#pragma unroll
-        for (int e = 0; e < 8; e++) s[e] += f[e];
-    }
-#pragma unroll
-    for (int e = 0; e < 8; e++) partial[pp * C + cj * 8 + e] = s[e];
-    __syncthreads();
-    for (int c = threadIdx.x; c < C; c += 256) {
-        float t = 0.0f;
-        for (int k = 0; k < TPC; k++) t += partial[k * C + c];
-        feat[c] = t * (1.0f / (float)(H * H));
-    }
-    __syncthreads();
-}
-
 template <typename T>
 __global__ void __launch_bounds__(256) head_kernel(const HeadParams p)
 {
@@ -92,10 +64,27 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadParams p)
     const int n = blockIdx.x;
     griddep_launch_dependents();
     griddep_wait(); // PDL: activations come from the previous kernel
-    if constexpr (sizeof(T) == 2) { // layouts of activations 8 / 12 / 16 (conv_umma.cu L1d / L2d / L3d outputs)
-        gap_planar<32, 64, 1, 0>(static_cast<const __half *>(p.act[0]), n, partial, feat);
-        gap_planar<16, 128, 1, 1>(static_cast<const __half *>(p.act[1]), n, partial, feat + 64);
-        gap_planar<8, 256, 0, 1>(static_cast<const __half *>(p.act[2]), n, partial, feat + 192);
+    if constexpr (sizeof(T) == 2) {
+        // product path: the epilogues of the last conv of each stage (conv_umma.cuh GAP) left per-tile partial sums
+        // [tile * NB + sub-image][4 lane quadrants][C]; add the few partials of this image in a fixed order
+        for (int c = threadIdx.x; c < 448; c += 256) {
+            float t = 0.0f;
+            if (c < 64) { // layer1: 32x32 = 8 tiles of 16x8 per image
+                const float *g = p.gap_part[0] + (size_t)n * 8 * 4 * 64 + c;
+                for (int k = 0; k < 32; k++) t += g[k * 64];
+                t *= 1.0f / (32 * 32);
+            } else if (c < 192) { // layer2: 16x16 = 2 tiles per image
+                const float *g = p.gap_part[1] + (size_t)n * 2 * 4 * 128 + (c - 64);
+                for (int k = 0; k < 8; k++) t += g[k * 128];
+                t *= 1.0f / (16 * 16);
+            } else { // layer3: one tile per image pair, sub-image n & 1
+                const float *g = p.gap_part[2] + (size_t)n * 4 * 256 + (c - 192);
+                for (int k = 0; k < 4; k++) t += g[k * 256];
+                t *= 1.0f / (8 * 8);
+            }
+            feat[c] = t;
+        }
+        __syncthreads();
     } else {
         gap_nhwc<32, 64>(static_cast<const float *>(p.act[0]) + (size_t)n * 32 * 32 * 64, partial, feat);
         gap_nhwc<16, 128>(static_cast<const float *>(p.act[1]) + (size_t)n * 16 * 16 * 128, partial, feat + 64);

@@ -88,6 +88,7 @@ struct ConvParams {
     const __half *x_w;  // packed [XC/GX][GX/8][COUT][8] (folded shortcut weights, or the identity)
     const float *bias_f32; // the same (shortcut-fused) bias as fp32 [COUT], added in the epilogue by the 32/64-channel layers
     __half *out;
+    float *gap_part; // GAP layers only: pool partial sums [tile * NB + sub-image][4 lane quadrants][COUT] of this layer's output
     int nimg;
     int relu;
     long long *trace; // MLT_TRACE_LAYER debug: CTA 0's MMA warp stores clock64() at every tile start (<= 1024 entries), or nullptr
@@ -106,7 +107,8 @@ cudaError_t launch_conv_umma(int layer, const ConvParams &p, int num_sms, cudaSt
 
 // ---- head.cu : global average pools + FC heads + softmax + argmax + flags (arch.py:281-297, EncCu.cpp:913-921)
 struct HeadParams {
-    const void *act[3];   // layer1 / layer2 / layer3 outputs: chunk-planar fp16 (product) or dense NHWC fp32 (cross-check)
+    const void *act[3];   // fp32 cross-check engine: layer1 / layer2 / layer3 outputs, dense NHWC fp32
+    const float *gap_part[3]; // product path: per-tile pool partial sums written by the epilogues of convs 7 / 11 / 15
     const float *fc_w[3]; // [out][in]
     const float *fc_b[3];
     const CtuDev *ctus;   // poc / qp
