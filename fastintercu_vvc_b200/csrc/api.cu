@@ -235,7 +235,7 @@ int run_network(mlt_ctx *c, const CtuDev *ctus, int n, mlt_result *out, cudaStre
         int first = 0;
         if (c->engine == 0) {
             // fused stem: staging + conv1 + layer0.0.conv1; conv1's 1 MiB / CTU output never reaches HBM
-            CU(launch_stem_umma(ctus, n, secp<__half>(c, SEC_STEM_CONV1), secp<__half>(c, SEC_W_F16 + 0), secp<__half>(c, SEC_BIAS_MMA + 0),
+            CU(launch_stem_umma(ctus, n, secp<__half>(c, SEC_STEM_CONV1), secp<__half>(c, SEC_W_F16 + 0), secp<float>(c, SEC_BIAS_FUSED + 0),
                                 S.act0q, S.act_h[1], c->num_sms, s));
             c->launches++;
             if (prof) { CU(cudaEventRecord(c->prof_ev[ev++], s)); CU(cudaEventRecord(c->prof_ev[ev++], s)); }

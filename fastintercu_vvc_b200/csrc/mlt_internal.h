@@ -57,7 +57,7 @@ cudaError_t launch_stage_conv1_f(const CtuDev *ctus, int n, const float *w /*[9]
 
 // ---- stem_umma.cu : staging + conv1 + layer0.0.conv1 fused (product path); conv1's full output never reaches HBM
 cudaError_t stem_umma_init();
-cudaError_t launch_stem_umma(const CtuDev *ctus, int n, const __half *w1 /*SEC_STEM_CONV1*/, const __half *w0, const __half *bias,
+cudaError_t launch_stem_umma(const CtuDev *ctus, int n, const __half *w1 /*SEC_STEM_CONV1*/, const __half *w0, const float *bias /*fp32*/,
                              __half *act0q /*conv1 at even rows/cols [n][4][64][64][8]*/, __half *act1, int num_sms, cudaStream_t s);
 
 // ---- conv_simt.cu : fp32 CUDA-core cross-check engine (tests only; never a fallback)

@@ -28,8 +28,8 @@ namespace mlt {
 
 namespace stem {
 constexpr int NE1 = 8;                                      // mid-epilogue warps (2 per TMEM lane quadrant; 16 measured no faster: the stem is smem-port-bound)
-constexpr int NTHREADS = (4 + NE1 + 1 + 4) * 32;           // 800
-constexpr int W_E2 = 0, W_E1 = 4, W_MMA = 4 + NE1, W_STG = W_MMA + 1; // warp roles (first warp of each group)
+constexpr int NTHREADS = (4 + NE1 + 2 + 4) * 32;           // 576
+constexpr int W_E2 = 0, W_E1 = 4, W_MMA = 4 + NE1, W_MMA2 = W_MMA + 1, W_STG = W_MMA + 2; // warp roles (first warp of each group)
 constexpr int PE = 17, PLANE_ENT = PE * PE;                // 289 entries per parity plane
 constexpr int P_LBO = PLANE_ENT * 16;                      // bytes between 8-channel chunks of the patch
 constexpr int P_PLANE = 4 * P_LBO;                         // one parity plane (32 channels)
@@ -40,15 +40,12 @@ constexpr int RAW_COLS = 48, RAW_ROWS = 35;
 constexpr int RAW_BYTES = RAW_ROWS * RAW_COLS * 4;         // 6,720: fp16 {org, res} pair per pixel of the input window
 constexpr int W0_BYTES = 9 * 32 * 32 * 2;                  // layer0.0.conv1 weights, resident
 constexpr int W1_BYTES = 6 * 1024;                         // conv1 operand variants [py][3 MMAs][2 chunks][32][8]
-constexpr int BIAS_BYTES = 32 * 32, ONES_BYTES = 2 * 128 * 16;
 constexpr int OFF_PATCH = 0;
 constexpr int OFF_EP = OFF_PATCH + 2 * PATCH_BYTES;
 constexpr int OFF_RAW = OFF_EP + 2 * EP_BYTES;
 constexpr int OFF_W0 = (OFF_RAW + RAW_BYTES + 127) / 128 * 128;
 constexpr int OFF_W1 = OFF_W0 + W0_BYTES;
-constexpr int OFF_BIAS = OFF_W1 + W1_BYTES;
-constexpr int OFF_ONES = OFF_BIAS + BIAS_BYTES;
-constexpr int OFF_BAR = OFF_ONES + ONES_BYTES;
+constexpr int OFF_BAR = OFF_W1 + W1_BYTES;
 constexpr int NBAR = 2 + 2 + 12 + 4 + 2 + 2 + 2 + 2;
 constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16;
@@ -62,7 +59,7 @@ struct StemParams {
     const CtuDev *ctus;
     const __half *w1;   // conv1 operand variants (SEC_STEM_CONV1)
     const __half *w0;   // layer0.0.conv1 packed [9][4][32][8] (SEC_W_F16 + 0)
-    const __half *bias; // layer0.0.conv1 bias operand (SEC_BIAS_MMA + 0)
+    const float *bias;  // layer0.0.conv1 folded-BN bias, fp32 [32] (SEC_BIAS_FUSED + 0), added by the final epilogue
     __half *act0q;      // conv1 output at even rows / even columns: dense chunk-planar [ctu][4][64][64][8]
     __half *act1;       // layer0.0.conv1 output: dense chunk-planar [ctu][4][64][64][8]
     int n;
@@ -92,9 +89,6 @@ __global__ void __launch_bounds__(stem::NTHREADS, 1) stem_umma_kernel(const Stem
     }
     for (int i = tid; i < W0_BYTES / 16; i += NTHREADS) reinterpret_cast<uint4 *>(smem + OFF_W0)[i] = __ldg(reinterpret_cast<const uint4 *>(p.w0) + i);
     for (int i = tid; i < W1_BYTES / 16; i += NTHREADS) reinterpret_cast<uint4 *>(smem + OFF_W1)[i] = __ldg(reinterpret_cast<const uint4 *>(p.w1) + i);
-    for (int i = tid; i < BIAS_BYTES / 16; i += NTHREADS) reinterpret_cast<uint4 *>(smem + OFF_BIAS)[i] = __ldg(reinterpret_cast<const uint4 *>(p.bias) + i);
-    for (int i = tid; i < ONES_BYTES / 16; i += NTHREADS)
-        reinterpret_cast<uint4 *>(smem + OFF_ONES)[i] = i < 128 ? make_uint4(0x3C003C00u, 0, 0, 0) : make_uint4(0, 0, 0, 0);
     // EP rows that no stager ever writes must still hold finite numbers
     for (int i = tid; i < 2 * EP_BYTES / 16; i += NTHREADS) reinterpret_cast<uint4 *>(smem + OFF_EP)[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async_smem();
@@ -189,16 +183,16 @@ __global__ void __launch_bounds__(stem::NTHREADS, 1) stem_umma_kernel(const Stem
             __syncwarp();
             if (lane == 0) mbar_arrive(&ep_full[buf]);
         }
-    } else if (warp == W_MMA) {
-        // ======================= MMA issuer: conv1(u) [48 MMAs], then layer0.0.conv1(u-1) [2 x 19 MMAs]
+    } else if (warp == W_MMA || warp == W_MMA2) {
+        // ======================= MMA issuers: conv1(u) [36 MMAs] / layer0.0.conv1(u) [2 x 18 MMAs]
         constexpr uint32_t idesc = umma_idesc_f16(128, 32);
         constexpr uint32_t e_hi = umma_desc_hi(128), b_hi = umma_desc_hi(128), p_hi = umma_desc_hi(PE * 16);
         const uint32_t sW0 = smem_u32(smem + OFF_W0), sW1 = smem_u32(smem + OFF_W1);
-        const uint32_t ones_lo = umma_desc_lo(smem_u32(smem + OFF_ONES), 128 * 16);
-        const uint32_t bias_lo = umma_desc_lo(smem_u32(smem + OFF_BIAS), 32 * 16);
         const int my_units = total_units > (int)blockIdx.x ? (total_units - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-        for (int ul = 0; ul <= my_units; ul++) {
-            if (ul < my_units) {
+        // two issuer warps (one warp cannot issue both MMA streams fast enough): W_MMA runs conv1, W_MMA2 the stride-2 conv;
+        // they only meet through the mid-epilogue's barriers, so conv1(u+1) naturally overlaps conv(u)
+        if (warp == W_MMA) {
+            for (int ul = 0; ul < my_units; ul++) {
                 const uint32_t buf = ul & 1;
                 mbar_wait(&ep_full[buf], (ul >> 1) & 1);
                 tc_fence_after();
@@ -230,8 +224,8 @@ __global__ void __launch_bounds__(stem::NTHREADS, 1) stem_umma_kernel(const Stem
                 if (elect_one_sync()) umma_commit(&ep_empty[buf]);
                 __syncwarp();
             }
-            if (ul >= 1) {
-                const int v = ul - 1;
+        } else {
+            for (int v = 0; v < my_units; v++) {
                 const uint32_t buf = v & 1;
                 mbar_wait(&patch_full[buf], (v >> 1) & 1);
                 mbar_wait(&d_empty[buf], ((v >> 1) & 1) ^ 1);
@@ -241,7 +235,6 @@ __global__ void __launch_bounds__(stem::NTHREADS, 1) stem_umma_kernel(const Stem
 #pragma unroll
                     for (int half = 0; half < 2; half++) { // left / right 8 output columns
                         const uint32_t d_tmem = tmem + TM_D + buf * 64 + half * 32;
-                        umma_f16(d_tmem, umma_desc_pack(ones_lo, b_hi), umma_desc_pack(bias_lo, b_hi), idesc, 0);
 #pragma unroll
                         for (int tap = 0; tap < 9; tap++) {
                             const int kh = tap / 3, kw = tap % 3;
@@ -250,7 +243,8 @@ __global__ void __launch_bounds__(stem::NTHREADS, 1) stem_umma_kernel(const Stem
                             const uint32_t b_lo = umma_desc_lo(sW0 + tap * 2048, 32 * 16);
 #pragma unroll
                             for (int ks = 0; ks < 2; ks++)
-                                umma_f16(d_tmem, umma_desc_pack(a_lo + ks * (2 * P_LBO / 16), p_hi), umma_desc_pack(b_lo + ks * 64, b_hi), idesc, 1);
+                                umma_f16(d_tmem, umma_desc_pack(a_lo + ks * (2 * P_LBO / 16), p_hi), umma_desc_pack(b_lo + ks * 64, b_hi), idesc,
+                                         (tap | ks) != 0); // bias is added by the final epilogue
                         }
                     }
                     umma_commit(&d_full[buf]);
@@ -306,6 +300,9 @@ __global__ void __launch_bounds__(stem::NTHREADS, 1) stem_umma_kernel(const Stem
     } else {
         // ======================= final epilogue: layer0.0.conv1 accumulators (bias included) -> ReLU -> fp16 -> HBM
         const int wq = warp & 3, m = wq * 32 + lane, r = m >> 3, c = m & 7;
+        float bias_r[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) bias_r[j] = __ldg(p.bias + j);
         uint32_t ul = 0;
         for (int u = blockIdx.x; u < total_units; u += gridDim.x, ul++) {
             const int ctu = u >> 4, oy0 = ((u >> 2) & 3) * 16, ox0 = (u & 3) * 16;
@@ -325,7 +322,8 @@ __global__ void __launch_bounds__(stem::NTHREADS, 1) stem_umma_kernel(const Stem
                     __half2 *h2 = reinterpret_cast<__half2 *>(&ov);
 #pragma unroll
                     for (int x = 0; x < 4; x++)
-                        h2[x] = __hmax2(__floats2half2_rn(__uint_as_float(v[q * 8 + x * 2]), __uint_as_float(v[q * 8 + x * 2 + 1])), zero2);
+                        h2[x] = __hmax2(__floats2half2_rn(__uint_as_float(v[q * 8 + x * 2]) + bias_r[q * 8 + x * 2],
+                                                          __uint_as_float(v[q * 8 + x * 2 + 1]) + bias_r[q * 8 + x * 2 + 1]), zero2);
                     *reinterpret_cast<uint4 *>(op + (size_t)q * (64 * 64 * 8)) = ov;
                 }
             }
@@ -348,7 +346,7 @@ cudaError_t stem_umma_init()
     return cudaFuncSetAttribute(stem_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, stem::SMEM_BYTES);
 }
 
-cudaError_t launch_stem_umma(const CtuDev *ctus, int n, const __half *w1, const __half *w0, const __half *bias, __half *act0q,
+cudaError_t launch_stem_umma(const CtuDev *ctus, int n, const __half *w1, const __half *w0, const float *bias, __half *act0q,
                              __half *act1, int num_sms, cudaStream_t s)
 {
     if (n <= 0) return cudaSuccess;
