@@ -153,7 +153,7 @@ int load_blob(mlt_ctx *c, const char *path)
              need(SEC_BIAS_MMA + li, (size_t)L.cout * 32);
         if (ok && (li & 1)) { // second conv of a block: extra operand = shortcut conv (first block) or identity
             const int xc = L.sc >= 0 ? kLayers[li - 1].cin : L.cout;
-            ok = need(SEC_X_W_F16 + li, (size_t)xc * L.cout * 2);
+            ok = need(SEC_X_W_F16 + li, (size_t)xc * L.cout * 2 * (L.sc >= 0 ? 2 : 1)); // shortcut weights: hi + lo
         }
         if (ok && L.sc >= 0) {
             const int csc = kLayers[li - 1].cin;

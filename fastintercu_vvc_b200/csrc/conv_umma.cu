@@ -9,19 +9,19 @@ namespace mlt {
 
 //            CIN  COUT S  HOUT XC  OUT_PAR
 using L0a = ConvCfg<32, 32, 2, 64, 0, 0>;     // layer0.0.conv1
-using L0b = ConvCfg<32, 32, 1, 64, 32, 0>;    // layer0.0.conv2 + shortcut(conv1 out)
+using L0b = ConvCfg<32, 32, 1, 64, 32, 0, 1>;   // layer0.0.conv2 + shortcut(conv1 out)
 using L0c = ConvCfg<32, 32, 1, 64, 0, 0>;     // layer0.1.conv1
 using L0d = ConvCfg<32, 32, 1, 64, 32, 1>;    // layer0.1.conv2 + identity; output feeds a stride-2 block
 using L1a = ConvCfg<32, 64, 2, 32, 0, 0>;     // layer1.0.conv1
-using L1b = ConvCfg<64, 64, 1, 32, 32, 0>;    // layer1.0.conv2 + shortcut
+using L1b = ConvCfg<64, 64, 1, 32, 32, 0, 1>;   // layer1.0.conv2 + shortcut
 using L1c = ConvCfg<64, 64, 1, 32, 0, 0>;     // layer1.1.conv1
 using L1d = ConvCfg<64, 64, 1, 32, 64, 1>;    // layer1.1.conv2 + identity
 using L2a = ConvCfg<64, 128, 2, 16, 0, 0>;    // layer2.0.conv1
-using L2b = ConvCfg<128, 128, 1, 16, 64, 0>;  // layer2.0.conv2 + shortcut
+using L2b = ConvCfg<128, 128, 1, 16, 64, 0, 1>; // layer2.0.conv2 + shortcut
 using L2c = ConvCfg<128, 128, 1, 16, 0, 0>;   // layer2.1.conv1
 using L2d = ConvCfg<128, 128, 1, 16, 128, 1>; // layer2.1.conv2 + identity
 using L3a = ConvCfg<128, 256, 2, 8, 0, 0>;    // layer3.0.conv1
-using L3b = ConvCfg<256, 256, 1, 8, 128, 0>;  // layer3.0.conv2 + shortcut
+using L3b = ConvCfg<256, 256, 1, 8, 128, 0, 1>; // layer3.0.conv2 + shortcut
 using L3c = ConvCfg<256, 256, 1, 8, 0, 0>;    // layer3.1.conv1
 using L3d = ConvCfg<256, 256, 1, 8, 256, 0>;  // layer3.1.conv2 + identity
 

@@ -32,9 +32,12 @@
 
 namespace mlt {
 
-template <int CIN_, int COUT_, int STRIDE_, int HOUT_, int XC_, int OUT_PAR_>
+template <int CIN_, int COUT_, int STRIDE_, int HOUT_, int XC_, int OUT_PAR_, int XLO_ = 0>
 struct ConvCfg {
     static constexpr int CIN = CIN_, COUT = COUT_, STRIDE = STRIDE_, HOUT = HOUT_, XC = XC_, OUT_PAR = OUT_PAR_;
+    // XLO: the extra operand's weights come as an fp16 hi + lo pair (two MMA passes over the same activation stage): the
+    // folded 1x1 shortcut weights are the largest single source of fp16 weight-rounding error and cost < 1 % to do exactly
+    static constexpr int XP = 1 + XLO_;
     // input channels per A stage / weight slab: 32 for the stride-2 convs (four parity planes per stage) and for the
     // 256-channel layers (keeps the activation ring small so the streamed-weight ring can be deep)
     static constexpr int G = (STRIDE == 2 && COUT >= 256) ? 16 : ((STRIDE == 2 || COUT >= 256) ? 32 : (CIN < 64 ? CIN : 64));
@@ -62,7 +65,7 @@ struct ConvCfg {
     static constexpr int SLAB_BYTES = G * COUT * 2; // one (cin_group, tap) weight slab
     static constexpr int X_SLAB_BYTES = GX * COUT * 2;
     static constexpr int W_MAIN_BYTES = NCG * 9 * SLAB_BYTES;
-    static constexpr int W_X_BYTES = XC * COUT * 2;
+    static constexpr int W_X_BYTES = XC * COUT * 2 * XP;
     static constexpr bool RESIDENT = (W_MAIN_BYTES + W_X_BYTES) <= 84 * 1024;
     // weight-slab ring: deep enough that ring depth x MMA time per slab covers the ~2500-cycle L2 -> smem latency of a
     // bulk copy (one slab feeds G/16 MMAs of max(N/2, 32 + N/4) cycles), leaving room for >= MIN_NAS activation stages
@@ -230,9 +233,9 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
                     // reduce over the warp's 32 pixels leaves lane l with the sum of channel c0 + l (pair tiles: 16 pixels per
                     // image, two channels per lane); one partial per (tile, image, lane quadrant, channel) goes to HBM and the
                     // head adds the few partials of an image in a fixed order.
-                    float gv[32];
+                    float gv[32]; // pooled from the fp32 accumulator values (bias and ReLU applied), not from their fp16 roundings
 #pragma unroll
-                    for (int e = 0; e < 16; e++) { const float2 t = __half22float2(hq[e]); gv[2 * e] = t.x; gv[2 * e + 1] = t.y; }
+                    for (int e = 0; e < 32; e++) gv[e] = p.relu ? fmaxf(__uint_as_float(v[e]), 0.0f) : __uint_as_float(v[e]);
                     auto fold = [&](int off, int nkeep) { // lanes with bit `off` keep the upper half of the list
                         const bool upper = (lane & off) != 0;
 #pragma unroll
@@ -311,11 +314,14 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
                     if constexpr (C::XC > 0) {
                         const uint32_t st1 = (j * SPT + 1) % C::NAS;
                         const uint32_t x_lo0 = umma_desc_lo(sA + st1 * C::A_STAGE_BYTES, C::X_LBO);
-                        const uint32_t b_lo0 = umma_desc_lo(sB + C::W_MAIN_BYTES, C::COUT * 16);
 #pragma unroll
-                        for (int ks = 0; ks < C::GX / 16; ks++)
-                            umma_f16(d_tmem, umma_desc_pack(x_lo0 + ks * (2 * C::X_LBO / 16), x_hi),
-                                     umma_desc_pack(b_lo0 + ks * (2 * C::COUT), b_hi), idesc, 1);
+                        for (int part = 0; part < C::XP; part++) {
+                            const uint32_t b_lo0 = umma_desc_lo(sB + C::W_MAIN_BYTES + part * C::X_SLAB_BYTES, C::COUT * 16);
+#pragma unroll
+                            for (int ks = 0; ks < C::GX / 16; ks++)
+                                umma_f16(d_tmem, umma_desc_pack(x_lo0 + ks * (2 * C::X_LBO / 16), x_hi),
+                                         umma_desc_pack(b_lo0 + ks * (2 * C::COUT), b_hi), idesc, 1);
+                        }
                         if (!(p.dbg & 16)) umma_commit(&emptyA[st1]);
                     }
                     if (!(p.dbg & 16)) umma_commit(&accFull[j % C::NACC]);
@@ -421,31 +427,37 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
                             a_lo0[h] = umma_desc_lo(sA + st * C::A_STAGE_BYTES, C::X_LBO);
                         }
                     }
-                    uint32_t bs = 0;
-                    if constexpr (!C::RESIDENT) {
-                        bs = b_it % C::NBS;
-                        mbar_wait(&fullB[bs], (b_it / C::NBS) & 1);
-                        b_it++;
-                    }
                     tc_fence_after();
-                    if (elect_one_sync()) {
-                        const uint32_t b_lo0 = C::RESIDENT ? umma_desc_lo(sB + C::W_MAIN_BYTES + xs * C::X_SLAB_BYTES, C::COUT * 16)
-                                                           : umma_desc_lo(sB + bs * C::SLAB_BYTES, C::COUT * 16);
 #pragma unroll
-                        for (int h = 0; h < C::TP; h++) {
-                            if (h < np) {
+                    for (int part = 0; part < C::XP; part++) { // hi (and lo) weights over the same activation stage
+                        uint32_t bs = 0;
+                        if constexpr (!C::RESIDENT) {
+                            bs = b_it % C::NBS;
+                            mbar_wait(&fullB[bs], (b_it / C::NBS) & 1);
+                            tc_fence_after();
+                            b_it++;
+                        }
+                        if (elect_one_sync()) {
+                            const uint32_t b_lo0 = C::RESIDENT ? umma_desc_lo(sB + C::W_MAIN_BYTES + (xs * C::XP + part) * C::X_SLAB_BYTES, C::COUT * 16)
+                                                               : umma_desc_lo(sB + bs * C::SLAB_BYTES, C::COUT * 16);
 #pragma unroll
-                                for (int ks = 0; ks < C::GX / 16; ks++)
-                                    umma_f16(d_tmem[h], umma_desc_pack(a_lo0[h] + ks * (2 * C::X_LBO / 16), x_hi),
-                                             umma_desc_pack(b_lo0 + ks * (2 * C::COUT), b_hi), idesc, 1);
+                            for (int h = 0; h < C::TP; h++) {
+                                if (h < np) {
+#pragma unroll
+                                    for (int ks = 0; ks < C::GX / 16; ks++)
+                                        umma_f16(d_tmem[h], umma_desc_pack(a_lo0[h] + ks * (2 * C::X_LBO / 16), x_hi),
+                                                 umma_desc_pack(b_lo0 + ks * (2 * C::COUT), b_hi), idesc, 1);
+                                }
+                            }
+                            if constexpr (!C::RESIDENT) umma_commit(&emptyB[bs]);
+                            if (part == C::XP - 1) {
+#pragma unroll
+                                for (int h = 0; h < C::TP; h++)
+                                    if (h < np) umma_commit(&emptyA[(a_it + h) % C::NAS]);
                             }
                         }
-                        if constexpr (!C::RESIDENT) umma_commit(&emptyB[bs]);
-#pragma unroll
-                        for (int h = 0; h < C::TP; h++)
-                            if (h < np) umma_commit(&emptyA[(a_it + h) % C::NAS]);
+                        __syncwarp();
                     }
-                    __syncwarp();
                 }
             }
             if (elect_one_sync()) {
@@ -466,14 +478,14 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
                 mbar_arrive_expect_tx(&fullB[0], C::W_MAIN_BYTES + C::W_X_BYTES);
                 for (int s = 0; s < C::NCG * 9; s++)
                     bulk_g2s(sB + s * C::SLAB_BYTES, gw + (size_t)s * C::SLAB_BYTES, C::SLAB_BYTES, &fullB[0]);
-                for (int s = 0; s < C::NXS; s++)
+                for (int s = 0; s < C::NXS * C::XP; s++)
                     bulk_g2s(sB + C::W_MAIN_BYTES + s * C::X_SLAB_BYTES, gx + (size_t)s * C::X_SLAB_BYTES, C::X_SLAB_BYTES, &fullB[0]);
             }
         } else {
             uint32_t b_it = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += C::TP * gridDim.x) { // once per pass (pair of tiles)
 #pragma unroll 1
-                for (int s = 0; s < C::NCG * 9 + C::NXS; s++, b_it++) {
+                for (int s = 0; s < C::NCG * 9 + C::NXS * C::XP; s++, b_it++) {
                     const uint32_t bs = b_it % C::NBS;
                     mbar_wait(&emptyB[bs], ((b_it / C::NBS) & 1) ^ 1);
                     if (elect_one_sync()) {

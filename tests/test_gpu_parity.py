@@ -226,6 +226,27 @@ def test_agreement_on_larger_sample(pred, oracle):
     assert set(sp.tolist()) == {0, 1, 2, 3}
 
 
+def test_agreement_2048_ctus_vs_fp32_oracle(blob, oracle):
+    """BASELINE north_star bars on a bigger sample: max |dprob| <= 1e-3 vs the fp32 oracle and >= 99.9 % split-decision
+    agreement on 2048 fresh synthetic CTUs (the fp32 C oracle runs on all host cores, ~20 s)."""
+    from fastintercu_vvc_b200 import MltPredictor
+
+    orgpred, pocqp = ref_arch.synth_ctus(2048, 4242)
+    with MltPredictor(blob, device=0, max_batch=2048) as p:
+        res = p.predict_batch_dense(orgpred, pocqp)  # 4 chunks, both activation sets
+    lg, sp = oracle.predict_batch(orgpred, pocqp)
+    dp = np.abs(res["probs"] - softmax_levels(lg)).max()
+    agree = [(res[k] == lg[:, a:b].argmax(1)).mean() for k, (a, b) in (("split_l1", (0, 2)), ("split_l2", (2, 5)), ("split_l3", (5, 9)))]
+    srt = np.sort(lg[:, 5:9], 1)
+    margin = srt[:, -1] - srt[:, -2]
+    bad = res["split_l3"] != sp
+    print(f"n=2048: max|dprob|={dp:.3e}, agreement L1/L2/L3={agree[0]:.4f}/{agree[1]:.4f}/{agree[2]:.4f}, "
+          f"L3 flips={int(bad.sum())} (fp32 margins {np.round(margin[bad], 5).tolist()}), classes={np.bincount(sp, minlength=4).tolist()}")
+    assert dp <= PROB_TOL
+    assert agree[2] >= 0.999 and min(agree) >= 0.998
+    assert np.all(margin[bad] < 2e-3), "a disagreement away from a numerical tie"
+
+
 def test_batch_shapes_and_entry_points_agree(pred, ctus):
     """Ragged / odd batches and every entry point give bit-identical results per CTU."""
     orgpred, pocqp = ctus

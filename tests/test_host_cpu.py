@@ -49,8 +49,17 @@ def test_blob_roundtrip_and_operand_layout(sd):
         packed = secs[pw.SEC_W_F16 + li].reshape(cin // group, 9, group // 8, cout, 8)
         # element (cg, tap, j, n, e) == folded weight [n][cg*G + j*8 + e][kh][kw]
         for (cg, t, j, nn, e) in ((0, 0, 0, 0, 0), (cin // group - 1, 8, group // 8 - 1, cout - 1, 7), (0, 4, 1, 5, 3)):
-            want = np.float16(wf[nn, cg * group + j * 8 + e, t // 3, t % 3])
-            assert packed[cg, t, j, nn, e] == want
+            ci = cg * group + j * 8 + e
+            want = wf[nn, ci, t // 3, t % 3]
+            ulp = float(np.spacing(np.float16(np.abs(wf[nn, ci]).max())))  # ulp of the largest tap of this (cout, cin) kernel
+            assert abs(float(packed[cg, t, j, nn, e]) - float(want)) <= ulp * 1.001
+        # error-diffused rounding: per (cout, cin) the nine rounding errors cancel to within half an ulp of the last tap
+        dense = packed.transpose(3, 0, 2, 4, 1).reshape(cout, cin, 9).astype(np.float64)  # [n][cg][j][e][t] -> [cout][cin][tap]
+        resid = np.abs((dense - wf.reshape(cout, cin, 9).astype(np.float64)).sum(2))
+        ulp_last = np.spacing(np.abs(dense[:, :, 8]).astype(np.float16)).astype(np.float64)
+        assert np.all(resid <= 0.5001 * np.maximum(ulp_last, float(np.spacing(np.float16(2.0 ** -14)))))
+        rn = np.abs((wf.astype(np.float16).astype(np.float64) - wf.astype(np.float64)).reshape(cout, cin, 9).sum(2))
+        assert resid.mean() < 0.6 * rn.mean()  # independent round-to-nearest leaves ~3x more
         assert np.array_equal(secs[pw.SEC_W_F32 + li].reshape(9, cin, cout)[4, 1, 2], wf[2, 1, 1, 1])
         bias_op = secs[pw.SEC_BIAS_MMA + li].reshape(2, cout, 8).astype(np.float32)
         fused = secs[pw.SEC_BIAS_FUSED + li]
@@ -59,13 +68,15 @@ def test_blob_roundtrip_and_operand_layout(sd):
         if li & 1:  # second conv of a block: extra K-slab operand = folded shortcut weights, or the identity
             xc = table[li - 1][1] if sc >= 0 else cout
             gx = min(xc, group)
-            xop = secs[pw.SEC_X_W_F16 + li].reshape(xc // gx, gx // 8, cout, 8).astype(np.float32)
-            dense = xop.transpose(2, 0, 1, 3).reshape(cout, xc)  # [cout][xc]
-            if sc >= 0:
+            if sc >= 0:  # folded 1x1 shortcut weights as an fp16 hi + lo pair
+                xop = secs[pw.SEC_X_W_F16 + li].reshape(xc // gx, 2, gx // 8, cout, 8).astype(np.float64)
+                dense = xop.sum(1).transpose(2, 0, 1, 3).reshape(cout, xc)  # hi + lo, [cout][xc]
                 sp = prefix.rsplit(".", 1)[0] + ".shortcut"
                 ws, _ = pw.fold_bn(sd[f"{sp}.0.weight"], sd, f"{sp}.1")
-                assert np.array_equal(dense, ws.reshape(cout, xc).astype(np.float16).astype(np.float32))
+                assert np.abs(dense - ws.reshape(cout, xc)).max() <= np.abs(ws).max() * 2.0 ** -20
             else:
+                xop = secs[pw.SEC_X_W_F16 + li].reshape(xc // gx, gx // 8, cout, 8).astype(np.float32)
+                dense = xop.transpose(2, 0, 1, 3).reshape(cout, xc)  # [cout][xc]
                 assert np.array_equal(dense, np.eye(cout, dtype=np.float32))
         else:
             assert (pw.SEC_X_W_F16 + li) not in secs
