@@ -145,7 +145,7 @@ int load_blob(mlt_ctx *c, const char *path)
     }
     // every section this architecture needs must be present with the exact size
     auto need = [&](uint32_t id, size_t bytes) { return c->sec[id].dev != nullptr && c->sec[id].bytes == bytes; };
-    bool ok = need(SEC_CONV1_F32, 9 * 2 * 32 * 4) && need(SEC_CONV1_UMMA, 2 * 4 * 32 * 16) && need(SEC_STEM_CONV1, 6 * 1024);
+    bool ok = need(SEC_CONV1_F32, 9 * 2 * 32 * 4) && need(SEC_CONV1_UMMA, 2 * 4 * 32 * 16) && need(SEC_STEM_CONV1, 4 * 1024);
     for (int li = 0; li < NCONV && ok; li++) {
         const LayerDesc &L = kLayers[li];
         ok = need(SEC_W_F16 + li, (size_t)9 * L.cin * L.cout * 2) && need(SEC_W_F32 + li, (size_t)9 * L.cin * L.cout * 4) &&

@@ -13,7 +13,7 @@
 //     that TMEM lane l of tile t is entry 128*t + l and lands at patch address base + entry*16 -- no index math.
 //     The A operand is the expanded input patch EP[col parity][row parity][18][17][8 fp16]: entry = {org, res} of the
 //     four input pixels x-1..x+2 (K chunk = one kernel row kh; the 4th pixel has zero weights); samples enter as
-//     v * 2^-10 (exact in fp16) and the weights carry (float)(1/1023) * 2^10 as a hi + lo fp16 pair (pack_weights.py).
+//     v * 2^-10 (exact in fp16) and the fp16 weights carry (float)(1/1023) * 2^10 (pack_weights.py).
 //     Row / column parity splitting makes the stride-2 sampling of every plane a dense window again, and the three
 //     kernel rows are start-address / LBO variants of the same arrays (two K=16 MMAs per hi / lo part).
 //   * layer0.0.conv1 then reads the patch exactly like conv_umma.cuh reads a TMA-loaded parity patch.
@@ -39,7 +39,7 @@ constexpr int EP_BYTES = 4 * EP_ARR;                       // 19,584
 constexpr int RAW_COLS = 48, RAW_ROWS = 35;
 constexpr int RAW_BYTES = RAW_ROWS * RAW_COLS * 4;         // 6,720: fp16 {org, res} pair per pixel of the input window
 constexpr int W0_BYTES = 9 * 32 * 32 * 2;                  // layer0.0.conv1 weights, resident
-constexpr int W1_BYTES = 6 * 1024;                         // conv1 operand variants [py][3 MMAs][2 chunks][32][8]
+constexpr int W1_BYTES = 4 * 1024;                         // conv1 operand variants [py][2 MMAs][2 chunks][32][8]
 constexpr int OFF_PATCH = 0;
 constexpr int OFF_EP = OFF_PATCH + 2 * PATCH_BYTES;
 constexpr int OFF_RAW = OFF_EP + 2 * EP_BYTES;
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(stem::NTHREADS, 1) stem_umma_kernel(const Stem
             if (lane == 0) mbar_arrive(&ep_full[buf]);
         }
     } else if (warp == W_MMA || warp == W_MMA2) {
-        // ======================= MMA issuers: conv1(u) [36 MMAs] / layer0.0.conv1(u) [2 x 18 MMAs]
+        // ======================= MMA issuers: conv1(u) [24 MMAs] / layer0.0.conv1(u) [2 x 18 MMAs]
         constexpr uint32_t idesc = umma_idesc_f16(128, 32);
         constexpr uint32_t e_hi = umma_desc_hi(128), b_hi = umma_desc_hi(128), p_hi = umma_desc_hi(PE * 16);
         const uint32_t sW0 = smem_u32(smem + OFF_W0), sW1 = smem_u32(smem + OFF_W1);
@@ -197,12 +197,13 @@ __global__ void __launch_bounds__(stem::NTHREADS, 1) stem_umma_kernel(const Stem
                 mbar_wait(&ep_full[buf], (ul >> 1) & 1);
                 tc_fence_after();
                 const uint32_t ep = sEP + buf * EP_BYTES;
-                // Per tile THREE K=16 MMAs cover the six (kernel row, hi/lo) products; the two chunks of each MMA are two
-                // kernel rows whose EP addresses differ by a positive constant (LBO):
+                // Per tile TWO K=16 MMAs cover the three kernel rows (fp16 weights, error-diffused over the taps by the packer;
+                // the 4th chunk slot carries zero weights); the two chunks of an MMA are kernel rows whose EP addresses differ
+                // by a positive constant (LBO):
                 //   py = 0: rows kh0 @ R1+0, kh1 @ R0+17, kh2 @ R1+17   (R0 / R1 = row-parity arrays, entries)
-                //           [kh1 | kh0] x [w1hi | w0hi],  [kh1 | kh2] x [w1lo | w2hi],  [kh0 | kh2] x [w0lo | w2lo]
+                //           [kh1 | kh0] x [w1 | w0],  [kh0 | kh2] x [0 | w2]
                 //   py = 1: rows kh0 @ R0+0, kh1 @ R1+0, kh2 @ R0+17
-                //           [kh0 | kh1] x [w0hi | w1hi],  [kh0 | kh2] x [w0lo | w2hi],  [kh2 | kh1] x [w2lo | w1lo]
+                //           [kh0 | kh1] x [w0 | w1],  [kh0 | kh2] x [0 | w2]
 #pragma unroll
                 for (int k = 0; k < 12; k++) {
                     const int plane = k / 3, t = k % 3, py = plane >> 1, px = plane & 1;
@@ -210,13 +211,12 @@ __global__ void __launch_bounds__(stem::NTHREADS, 1) stem_umma_kernel(const Stem
                     if (elect_one_sync()) {
                         const uint32_t a0 = ep + (1 - px) * 2 * EP_ARR + t * 128 * 16; // row-parity-0 array of column parity 1 - px
                         const uint32_t d_tmem = tmem + TM_C1 + k * 32;
-                        const uint32_t wb = sW1 + py * 3072;
+                        const uint32_t wb = sW1 + py * 2048;
                         constexpr uint32_t ROW = PE * 16, L289 = (EP_ARR - PE * 16);
-                        const uint32_t s0 = py ? a0 : a0 + ROW, s1 = py ? a0 : a0 + ROW, s2 = py ? a0 + ROW : a0 + EP_ARR;
-                        const uint32_t l0 = py ? EP_ARR : L289, l1 = py ? ROW : EP_ARR, l2 = py ? L289 : ROW;
+                        const uint32_t s0 = py ? a0 : a0 + ROW, s1 = py ? a0 : a0 + EP_ARR;
+                        const uint32_t l0 = py ? EP_ARR : L289;
                         umma_f16(d_tmem, umma_desc_pack(umma_desc_lo(s0, l0), e_hi), umma_desc_pack(umma_desc_lo(wb, 32 * 16), b_hi), idesc, 0);
-                        umma_f16(d_tmem, umma_desc_pack(umma_desc_lo(s1, l1), e_hi), umma_desc_pack(umma_desc_lo(wb + 1024, 32 * 16), b_hi), idesc, 1);
-                        umma_f16(d_tmem, umma_desc_pack(umma_desc_lo(s2, l2), e_hi), umma_desc_pack(umma_desc_lo(wb + 2048, 32 * 16), b_hi), idesc, 1);
+                        umma_f16(d_tmem, umma_desc_pack(umma_desc_lo(s1, ROW), e_hi), umma_desc_pack(umma_desc_lo(wb + 1024, 32 * 16), b_hi), idesc, 1);
                         umma_commit(&c1_full[k]);
                     }
                     __syncwarp();
@@ -266,15 +266,21 @@ __global__ void __launch_bounds__(stem::NTHREADS, 1) stem_umma_kernel(const Stem
             for (int k = hsel; k < 12; k += NE1 / 4) {
                 const int plane = k / 3, t = k % 3, py = plane >> 1, px = plane & 1;
                 const int e = t * 128 + wq * 32 + lane, i = e / PE, j = e % PE;
+                // the third tile of a plane holds entries 256..288 only: lane quadrants 2 and 3 (and 1, except for the corner
+                // entry 288 of plane (1, 1)) have nothing to convert -- skipping their TMEM reads matters, the stem is bound by
+                // the TMEM -> register read bandwidth (196 KB of fp32 accumulators per unit)
+                const bool live = t < 2 || wq == 0 || (wq == 1 && plane == 3);
                 mbar_wait(&c1_full[k], ul & 1);
                 tc_fence_after();
                 uint32_t v[32];
-                tmem_ld32(tmem + ((uint32_t)(wq * 32) << 16) + TM_C1 + k * 32, v);
-                tmem_ld_wait();
+                if (live) {
+                    tmem_ld32(tmem + ((uint32_t)(wq * 32) << 16) + TM_C1 + k * 32, v);
+                    tmem_ld_wait();
+                }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&c1_empty[plane]);
-                if (e < PLANE_ENT) {
+                if (live && e < PLANE_ENT) {
                     // conv1 pixel (2*oy0 - py + 2*i, 2*ox0 - px + 2*j); outside the picture = zero padding of the stride-2 conv
                     const bool zero = (py && i == 0 && oy0 == 0) || (px && j == 0 && ox0 == 0);
                     uint4 ov[4];

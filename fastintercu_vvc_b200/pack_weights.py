@@ -165,23 +165,27 @@ def conv1_operand(w: np.ndarray) -> np.ndarray:
 
 
 def stem_conv1_operand(w: np.ndarray) -> np.ndarray:
-    """conv1 for the fused stem kernel (csrc/stem_umma.cu): fp16 [py][3 MMAs][2 chunks][32 cout][8].
+    """conv1 for the fused stem kernel (csrc/stem_umma.cu): fp16 [py][2 MMAs][2 chunks][32 cout][8].
 
-    Same chunks as conv1_operand (chunk kh = one kernel row, scale folded in, hi/lo fp16 split).  Per output-row parity
-    py the stem issues three K=16 MMAs whose two chunks pair kernel rows at a constant shared-memory distance:
-      py = 0: [kh1.hi | kh0.hi], [kh1.lo | kh2.hi], [kh0.lo | kh2.lo]
-      py = 1: [kh0.hi | kh1.hi], [kh0.lo | kh2.hi], [kh2.lo | kh1.lo]
-    so the six (kernel row, hi/lo) products are each covered exactly once."""
-    c = conv1_operand(w)  # [hi, lo][4 chunks][32][8]
-    H, L = 0, 1
-    order = ((((H, 1), (H, 0)), ((L, 1), (H, 2)), ((L, 0), (L, 2))),
-             (((H, 0), (H, 1)), ((L, 0), (H, 2)), ((L, 2), (L, 1))))
-    out = np.zeros((2, 3, 2, 32, 8), np.float16)
+    Chunk kh = one kernel row: element dx*2 + ch = w[cout][ch][kh][dx] * (float)(1/1023) * 2^10 for dx < 3, else 0
+    (the A operand is the integer sample * 2^-10, exact in fp16, so the staging multiply is folded into the weights);
+    fp16 with error diffusion over the nine taps of every (cout, ch) kernel (quantize_fp16_diffused).  Per output-row
+    parity py the stem issues two K=16 MMAs whose two chunks are kernel rows at a constant shared-memory distance:
+      py = 0: [kh1 | kh0], [0 | kh2]        py = 1: [kh0 | kh1], [0 | kh2]"""
+    ws = (w.astype(np.float64) * float(ALPHA) * 1024.0).astype(np.float32)
+    q = quantize_fp16_diffused(ws)  # [32][2][3][3] fp16
+    chunk = np.zeros((4, 32, 8), np.float16)  # chunk 3 = zeros
+    for kh in range(3):
+        for dx in range(3):
+            for ch in range(2):
+                chunk[kh, :, dx * 2 + ch] = q[:, ch, kh, dx]
+    z = 3
+    order = (((1, 0), (z, 2)), ((0, 1), (z, 2)))
+    out = np.zeros((2, 2, 2, 32, 8), np.float16)
     for py in range(2):
-        for m in range(3):
+        for m in range(2):
             for k in range(2):
-                part, kh = order[py][m][k]
-                out[py, m, k] = c[part, kh]
+                out[py, m, k] = chunk[order[py][m][k]]
     return out
 
 
