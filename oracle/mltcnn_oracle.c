@@ -33,10 +33,12 @@ typedef struct {
 } block_t;
 
 struct mlto_model {
+    int arch;          /* 128 = CTU model (mlt_ctu_or_pq_arch.py), 64 / 32 / 16 = smaller-CU model (mlt_cu_or_pq_arch.py) */
+    int nstage, nhead; /* 4 stages + 3 heads (CTU) or 5 stages + 4 heads (CU); head i hangs off stage i + 1 */
     conv_t conv1;      /* arch.py:244 (bn1 at :246 is defined but unused, :277-278) */
-    block_t blk[4][2]; /* layer0..3, two BasicBlocks each (arch.py:247-254,306) */
-    float *fc_w[3], *fc_b[3];
-    int fc_in[3], fc_out[3];
+    block_t blk[5][2]; /* layer0..3(4), two BasicBlocks each (arch.py:247-254,306; mlt_cu_or_pq_arch.py:69-80,130) */
+    float *fc_w[4], *fc_b[4];
+    int fc_in[4], fc_out[4];
 };
 
 /* ---------------------------------------------------------------- loading */
@@ -71,18 +73,24 @@ static int load_bn(FILE *f, bn_t *b, int c)
 
 mlto_model *mlto_load(const char *path)
 {
-    static const int planes[4] = {32, 64, 128, 256};
+    static const int planes_ctu[4] = {32, 64, 128, 256};     /* mlt_ctu_or_pq_arch.py:247-254 */
+    static const int planes_cu[5] = {32, 64, 96, 128, 256};  /* mlt_cu_or_pq_arch.py:69-80 */
     FILE *f = fopen(path, "rb");
     if (!f) return NULL;
     uint32_t hdr[4];
-    if (fread(hdr, 4, 4, f) != 4 || hdr[0] != 0x52544c4du /* "MLTR" */ || hdr[1] != 1 || hdr[2] != 128) {
+    if (fread(hdr, 4, 4, f) != 4 || hdr[0] != 0x52544c4du /* "MLTR" */ || hdr[1] != 1 ||
+        (hdr[2] != 128 && hdr[2] != 64 && hdr[2] != 32 && hdr[2] != 16)) {
         fclose(f);
         return NULL;
     }
     mlto_model *m = (mlto_model *)calloc(1, sizeof(*m));
+    m->arch = (int)hdr[2];
+    m->nstage = m->arch == 128 ? 4 : 5;
+    m->nhead = m->nstage - 1;
+    const int *planes = m->arch == 128 ? planes_ctu : planes_cu;
     int bad = load_conv(f, &m->conv1, 2, 32, 3, 1);
     int in_planes = 32;
-    for (int L = 0; L < 4 && !bad; L++) {
+    for (int L = 0; L < m->nstage && !bad; L++) {
         for (int b = 0; b < 2 && !bad; b++) {
             block_t *B = &m->blk[L][b];
             int stride = b == 0 ? 2 : 1; /* _make_layer: strides = [2, 1] (arch.py:265-271) */
@@ -98,12 +106,13 @@ mlto_model *mlto_load(const char *path)
             in_planes = planes[L];
         }
     }
-    static const int fin[3] = {64 + 2, 128 + 2, 256 + 2}, fout[3] = {2, 3, 4};
-    for (int i = 0; i < 3 && !bad; i++) {
-        m->fc_in[i] = fin[i]; m->fc_out[i] = fout[i];
-        m->fc_w[i] = (float *)malloc((size_t)fin[i] * fout[i] * sizeof(float));
+    static const int fout[4] = {2, 3, 4, 6}; /* arch.py:241; mlt_cu_or_pq_arch.py:62 */
+    for (int i = 0; i < m->nhead && !bad; i++) {
+        const int fin_i = planes[i + 1] + 2; /* pooled features + poc + qp */
+        m->fc_in[i] = fin_i; m->fc_out[i] = fout[i];
+        m->fc_w[i] = (float *)malloc((size_t)fin_i * fout[i] * sizeof(float));
         m->fc_b[i] = (float *)malloc((size_t)fout[i] * sizeof(float));
-        bad |= read_f32(f, m->fc_w[i], (size_t)fin[i] * fout[i]);
+        bad |= read_f32(f, m->fc_w[i], (size_t)fin_i * fout[i]);
         bad |= read_f32(f, m->fc_b[i], (size_t)fout[i]);
     }
     fclose(f);
@@ -115,13 +124,13 @@ void mlto_free(mlto_model *m)
 {
     if (!m) return;
     free(m->conv1.w);
-    for (int L = 0; L < 4; L++)
+    for (int L = 0; L < 5; L++)
         for (int b = 0; b < 2; b++) {
             block_t *B = &m->blk[L][b];
             free(B->conv1.w); free(B->conv2.w); free(B->sc.w);
             free(B->bn1.gamma); free(B->bn2.gamma); free(B->scbn.gamma);
         }
-    for (int i = 0; i < 3; i++) { free(m->fc_w[i]); free(m->fc_b[i]); }
+    for (int i = 0; i < 4; i++) { free(m->fc_w[i]); free(m->fc_b[i]); }
     free(m);
 }
 
@@ -194,7 +203,7 @@ static void bn_apply(const bn_t *b, float *x, size_t npix, int relu)
 /* BasicBlock.forward, arch.py:52-57. in: [h][w][cin] -> out: [ho][wo][planes] */
 static void basic_block(const block_t *B, const float *in, int h, float *out, float *tmp, float *tmp2)
 {
-    const int ho = h / B->conv1.stride, co = B->conv1.cout;
+    const int ho = (h - 1) / B->conv1.stride + 1, co = B->conv1.cout; /* k=3, pad=1 (and the 1x1, pad=0 shortcut): 128->64 ... 2->1, 1->1 */
     const size_t npix = (size_t)ho * ho;
     conv2d(&B->conv1, in, h, h, tmp);
     bn_apply(&B->bn1, tmp, npix, 1);  /* relu(bn1(conv1(x))) */
@@ -256,6 +265,86 @@ void mlto_forward_ex(const mlto_model *m, const float *x, int poc, int qp, float
     basic_block(&m->blk[3][1], b, 8, a, t1, t2);
     gap_fc(m, 2, a, 8, 256, poc, qp, logits + 5, gap3);   /* branch3, arch.py:293-297 */
     free(nhwc); free(a); free(b); free(t1); free(t2);
+}
+
+/* ---------------------------------------------------------------- smaller-CU model (64 / 32 / 16 px) */
+
+void mlto_cu_stage(int size, const int16_t *org, int org_stride, const int16_t *pred, int pred_stride, float *x)
+{
+    /* the same lines as mlto_stage, for a cuw x cuh block (EncCu.cpp:810-867 run with cuw = cuh = size) */
+    const float alpha = (float)(1.0 / 1023);
+    for (int i = 0; i < size; i++)
+        for (int j = 0; j < size; j++) {
+            uint16_t o = (uint16_t)org[(size_t)i * org_stride + j];
+            uint16_t p = (uint16_t)pred[(size_t)i * pred_stride + j];
+            uint16_t r = o > p ? (uint16_t)(o - p) : (uint16_t)(p - o);
+            float fo = (float)o * alpha, fr = (float)r * alpha;
+            if (fo < 0.0f) fo = 0.0f; else if (fo > 1.0f) fo = 1.0f;
+            if (fr < 0.0f) fr = 0.0f; else if (fr > 1.0f) fr = 1.0f;
+            x[i * size + j] = fo;
+            x[size * size + i * size + j] = fr;
+        }
+}
+
+/* MltCnnL4ORPQv4.forward, mlt_cu_or_pq_arch.py:99-127: logits = lvl1[2], lvl2[3], lvl3[4], lvl4[6] */
+void mlto_cu_forward(const mlto_model *m, int size, const float *x, int poc, int qp, float logits[15])
+{
+    const int S = size;
+    const size_t big = (size_t)S * S * 32;
+    float *nhwc = (float *)malloc((size_t)S * S * 2 * sizeof(float));
+    float *a = (float *)malloc(big * sizeof(float)), *b = (float *)malloc(big * sizeof(float));
+    float *t1 = (float *)malloc(big * sizeof(float)), *t2 = (float *)malloc(big * sizeof(float));
+    for (int p = 0; p < S * S; p++) { nhwc[2 * p] = x[p]; nhwc[2 * p + 1] = x[S * S + p]; }
+    conv2d(&m->conv1, nhwc, S, S, a); /* :105 conv1, no BN / ReLU */
+    int h = S, off = 0;
+    for (int L = 0; L < m->nstage; L++) {
+        basic_block(&m->blk[L][0], a, h, b, t1, t2); /* stride-2 block */
+        h = (h - 1) / 2 + 1;
+        basic_block(&m->blk[L][1], b, h, a, t1, t2);
+        if (L >= 1) { /* branch L hangs off layer L (:108-127) */
+            gap_fc(m, L - 1, a, h, m->blk[L][1].conv2.cout, poc, qp, logits + off, NULL);
+            off += m->fc_out[L - 1];
+        }
+    }
+    free(nhwc); free(a); free(b); free(t1); free(t2);
+}
+
+typedef struct {
+    const mlto_model *m;
+    int n, tid, nthreads, size;
+    const int16_t *orgpred;
+    const int32_t *pocqp;
+    float *logits;
+} cu_job;
+
+static void *cu_worker(void *arg)
+{
+    const cu_job *j = (const cu_job *)arg;
+    const size_t plane = (size_t)j->size * j->size;
+    float *x = (float *)malloc(2 * plane * sizeof(float));
+    for (int i = j->tid; i < j->n; i += j->nthreads) {
+        const int16_t *o = j->orgpred + (size_t)i * 2 * plane;
+        mlto_cu_stage(j->size, o, j->size, o + plane, j->size, x);
+        mlto_cu_forward(j->m, j->size, x, j->pocqp[2 * i], j->pocqp[2 * i + 1], j->logits + (size_t)15 * i);
+    }
+    free(x);
+    return NULL;
+}
+
+void mlto_cu_predict_batch(const mlto_model *m, int size, int n, const int16_t *orgpred, const int32_t *pocqp,
+                           float *logits, int nthreads)
+{
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 256) nthreads = 256;
+    if (nthreads > n) nthreads = n > 0 ? n : 1;
+    pthread_t th[256];
+    cu_job jobs[256];
+    for (int t = 0; t < nthreads; t++) {
+        jobs[t] = (cu_job){m, n, t, nthreads, size, orgpred, pocqp, logits};
+        if (t > 0) pthread_create(&th[t], NULL, cu_worker, &jobs[t]);
+    }
+    cu_worker(&jobs[0]);
+    for (int t = 1; t < nthreads; t++) pthread_join(th[t], NULL);
 }
 
 void mlto_forward(const mlto_model *m, const float *x, int poc, int qp, float logits[9])

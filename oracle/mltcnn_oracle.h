@@ -58,6 +58,16 @@ int mlto_predict(const mlto_model *m, const int16_t *org, int org_stride, const 
 void mlto_predict_batch(const mlto_model *m, int n, const int16_t *orgpred, const int32_t *pocqp,
                         float *logits, int32_t *split, int nthreads);
 
+/* ---- smaller-CU model `GapBigMltCuORPQ` (64 / 32 / 16 px; mlt_cu_or_pq_arch.py:59-130): the hook's cuw != 128 branch
+ * (gate EncCu.cpp:754, model file per size :899, elements()[0] :916-919).  The MLTR blob header carries arch = size. */
+void mlto_cu_stage(int size, const int16_t *org, int org_stride, const int16_t *pred, int pred_stride,
+                   float *x /* [2*size*size] NCHW */);
+/* logits[0..1]=lvl1, [2..4]=lvl2, [5..8]=lvl3, [9..14]=lvl4 */
+void mlto_cu_forward(const mlto_model *m, int size, const float *x, int poc, int qp, float logits[15]);
+/* orgpred: [n][2][size][size] int16 dense, pocqp: [n][2], logits: [n][15] */
+void mlto_cu_predict_batch(const mlto_model *m, int size, int n, const int16_t *orgpred, const int32_t *pocqp,
+                           float *logits, int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

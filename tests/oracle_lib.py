@@ -27,6 +27,9 @@ def lib():
         L.mlto_predict.restype = C.c_int
         L.mlto_predict.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.mlto_predict_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.mlto_cu_stage.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        L.mlto_cu_forward.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.mlto_cu_predict_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         _LIB = L
     return _LIB
 
@@ -78,3 +81,43 @@ class OracleModel:
         nt = nthreads or (os.cpu_count() or 1)
         lib().mlto_predict_batch(self.h, n, orgpred.ctypes.data, pocqp.ctypes.data, lg.ctypes.data, sp.ctypes.data, nt)
         return lg, sp
+
+
+class OracleCuModel:
+    """C oracle of the smaller-CU model (64 / 32 / 16 px): raw fp32 parameters of a CU state_dict."""
+
+    def __init__(self, sd: dict, size: int):
+        from oracle.weights_io import write_raw_cu_blob
+
+        self.size = size
+        with tempfile.NamedTemporaryFile(suffix=".mltr", delete=False) as f:
+            path = f.name
+        try:
+            write_raw_cu_blob(sd, size, path)
+            self.h = lib().mlto_load(path.encode())
+        finally:
+            os.unlink(path)
+        if not self.h:
+            raise RuntimeError("mlto_load failed")
+
+    def close(self):
+        if self.h:
+            lib().mlto_free(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def stage(self, org: np.ndarray, pred: np.ndarray) -> np.ndarray:
+        assert org.dtype == np.int16 and pred.dtype == np.int16 and org.strides[1] == 2 and pred.strides[1] == 2
+        x = np.empty((2, self.size, self.size), np.float32)
+        lib().mlto_cu_stage(self.size, org.ctypes.data, org.strides[0] // 2, pred.ctypes.data, pred.strides[0] // 2, x.ctypes.data)
+        return x
+
+    def predict_batch(self, orgpred: np.ndarray, pocqp: np.ndarray, nthreads: int | None = None) -> np.ndarray:
+        orgpred = np.ascontiguousarray(orgpred, np.int16)
+        pocqp = np.ascontiguousarray(pocqp, np.int32)
+        n = len(orgpred)
+        assert orgpred.shape[1:] == (2, self.size, self.size)
+        lg = np.empty((n, 15), np.float32)
+        lib().mlto_cu_predict_batch(self.h, self.size, n, orgpred.ctypes.data, pocqp.ctypes.data, lg.ctypes.data, nthreads or (os.cpu_count() or 1))
+        return lg
