@@ -6,7 +6,7 @@ This package holds that library, the offline weight packer and a thin ctypes bin
 tests and bench.py.  There is no CPU or PyTorch fallback: importing `capi` without the built library,
 or creating a predictor without a Blackwell GPU, raises.
 """
-from .capi import MltError, MltPredictor, MltResult, lib_path, load_library  # noqa: F401
-from .pack_weights import pack, write_blob  # noqa: F401
+from .capi import MltCuPredictor, MltError, MltPredictor, MltResult, lib_path, load_library  # noqa: F401
+from .pack_weights import pack, write_blob, write_cu_blob  # noqa: F401
 
-__all__ = ["MltPredictor", "MltResult", "MltError", "load_library", "lib_path", "pack", "write_blob"]
+__all__ = ["MltPredictor", "MltCuPredictor", "write_cu_blob", "MltResult", "MltError", "load_library", "lib_path", "pack", "write_blob"]

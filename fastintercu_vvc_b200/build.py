@@ -8,7 +8,9 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["api.cu", "conv_umma.cu", "stem_umma.cu", "conv_simt.cu", "stage_conv1.cu", "head.cu"]
+SOURCES = ["api.cu", "conv_umma.cu", "stem_umma.cu", "conv_simt.cu", "stage_conv1.cu", "head.cu",
+           # smaller-CU models (64 / 32 / 16 px): one translation unit of tcgen05 conv instantiations per CU size
+           "cu_api.cu", "cu_net.cu", "cu_net_64.cu", "cu_net_32.cu", "cu_net_16.cu", "cu_stem.cu", "cu_head.cu"]
 LIB = os.path.join(HERE, "libmltcnn.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -27,7 +29,8 @@ def _stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "mltcnn.h")]
+    inc = os.path.join(HERE, "..", "include")
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(inc, f) for f in os.listdir(inc)]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

@@ -69,6 +69,24 @@ EXPORTS = {
     "mlt_debug_activation": (C.c_int64, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]),
 }
 
+CU_RESULT_DTYPE = np.dtype([("split", "<i4", 4), ("logits", "<f4", 15), ("probs", "<f4", 15)])
+assert CU_RESULT_DTYPE.itemsize == 136
+
+# include/mltcnn_cu.h -- the smaller-CU models (64 / 32 / 16 px)
+EXPORTS.update({
+    "mlt_cu_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_char_p, C.c_int, C.c_int, C.c_int]),
+    "mlt_cu_destroy": (None, [C.c_void_p]),
+    "mlt_cu_predict": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "mlt_cu_predict_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "mlt_cu_predict_batch_dense": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mlt_cu_predict_batch_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mlt_cu_last_error": (C.c_char_p, [C.c_void_p]),
+    "mlt_cu_size": (C.c_int, [C.c_void_p]),
+    "mlt_cu_layer_info": (C.c_int, [C.c_int, C.c_int, C.c_void_p]),
+    "mlt_cu_launch_count": (C.c_uint64, [C.c_void_p]),
+    "mlt_cu_debug_activation": (C.c_int64, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]),
+})
+
 _LIB = None
 
 
@@ -225,5 +243,96 @@ class MltPredictor:
         h, c = shapes[layer]
         out = np.empty((n, h, h, c), np.float32)
         got = self._check(self._lib.mlt_debug_activation(self._h, layer, out.ctypes.data, out.size), "mlt_debug_activation")
+        assert got == out.size, (got, out.size)
+        return out
+
+
+class MltCuPredictor:
+    """Smaller-CU model (64 / 32 / 16 px): the hook's cuw != 128 branch (EncCu.cpp:754,899,916-919).  `split[:, 0]` of a
+    result is the level-1 argmax the encoder would hand to setNewModeList."""
+
+    def __init__(self, weights_path: str, size: int, device: int = 0, max_batch: int = 4096):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        rc = self._lib.mlt_cu_create(C.byref(self._h), os.fsencode(weights_path), int(device), int(size), int(max_batch))
+        if rc != 0:
+            self._h = C.c_void_p()
+            raise MltError(rc, "mlt_cu_create", self._lib.mlt_strerror(rc).decode())
+        self.size, self.max_batch = size, max_batch
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.mlt_cu_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc, what):
+        if rc < 0:
+            raise MltError(rc, what, self._lib.mlt_cu_last_error(self._h).decode() or self._lib.mlt_strerror(rc).decode())
+        return rc
+
+    def _view(self, a: np.ndarray):
+        if a.dtype != np.int16 or a.shape != (self.size, self.size) or a.strides[1] != 2 or a.strides[0] % 2:
+            raise ValueError(f"expected an int16 [{self.size},{self.size}] view with unit element stride")
+        return a.ctypes.data, a.strides[0] // 2
+
+    def predict(self, org: np.ndarray, pred: np.ndarray, poc: int, qp: int) -> np.void:
+        op, os_ = self._view(org)
+        pp, ps = self._view(pred)
+        out = np.zeros(1, CU_RESULT_DTYPE)
+        self._check(self._lib.mlt_cu_predict(self._h, op, os_, pp, ps, int(poc), int(qp), out.ctypes.data), "mlt_cu_predict")
+        return out[0]
+
+    def predict_batch(self, cus) -> np.ndarray:
+        n = len(cus)
+        descs = (CtuDesc * max(n, 1))()
+        for i, (org, pred, poc, qp) in enumerate(cus):
+            descs[i].org, descs[i].org_stride = self._view(org)
+            descs[i].pred, descs[i].pred_stride = self._view(pred)
+            descs[i].poc, descs[i].qp = int(poc), int(qp)
+        out = np.zeros(n, CU_RESULT_DTYPE)
+        self._check(self._lib.mlt_cu_predict_batch(self._h, n, descs, out.ctypes.data), "mlt_cu_predict_batch")
+        return out
+
+    def predict_batch_dense(self, orgpred: np.ndarray, pocqp: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        n = len(orgpred)
+        if orgpred.dtype != np.int16 or orgpred.shape[1:] != (2, self.size, self.size) or not orgpred.flags.c_contiguous:
+            raise ValueError("orgpred must be C-contiguous int16 [n,2,size,size]")
+        pocqp = np.ascontiguousarray(pocqp, np.int32)
+        if out is None:
+            out = np.zeros(n, CU_RESULT_DTYPE)
+        self._check(self._lib.mlt_cu_predict_batch_dense(self._h, n, orgpred.ctypes.data, pocqp.ctypes.data, out.ctypes.data),
+                    "mlt_cu_predict_batch_dense")
+        return out
+
+    def predict_batch_device(self, n: int, d_orgpred: int, d_pocqp: int, d_out: int, stream: int = 0):
+        self._check(self._lib.mlt_cu_predict_batch_device(self._h, int(n), C.c_void_p(d_orgpred), C.c_void_p(d_pocqp), C.c_void_p(d_out),
+                                                          C.c_void_p(stream)), "mlt_cu_predict_batch_device")
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.mlt_cu_launch_count(self._h))
+
+    def debug_activation(self, layer: int, n: int) -> np.ndarray:
+        """fp32 NHWC [n][H][H][C] of activation `layer` (0 = conv1 out, 1 + li = conv li out) of the last host batch."""
+        planes = (32, 64, 96, 128, 256)
+        if layer == 0:
+            h, c = self.size, 32
+        else:
+            L = (layer - 1) // 4
+            h, c = max(self.size >> (L + 1), 1), planes[L]
+        out = np.empty((n, h, h, c), np.float32)
+        got = self._check(self._lib.mlt_cu_debug_activation(self._h, layer, out.ctypes.data, out.size), "mlt_cu_debug_activation")
         assert got == out.size, (got, out.size)
         return out

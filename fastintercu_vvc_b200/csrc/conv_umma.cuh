@@ -32,20 +32,30 @@
 
 namespace mlt {
 
-template <int CIN_, int COUT_, int STRIDE_, int HOUT_, int XC_, int OUT_PAR_, int XLO_ = 0>
+// FLAGS_ bit 0 (STRIP): the smaller-CU networks (64 / 32 / 16-px GapBigMltCuORPQ, mlt_cu_or_pq_arch.py:59-130).  Their maps
+// shrink to 4x4, 2x2 and 1x1, so every tensor is stored as ONE strip [plane][C/8][row][img][x][8] over the whole batch
+// (ActLayout::strip) and a tile takes NB consecutive images of it.  Maps of 8x8 and larger use the same tile shapes as
+// the CTU network; maps <= 4x4 use FLAT tiles: the TMA box [row][NB images][x incl. halo] is addressed as 128
+// CONSECUTIVE 16-byte positions (SBO = 128 B), tap (kh, kw) is again just a start-address shift, and the accumulator
+// rows that land on halo positions (x >= HOUT) are simply not stored -- M efficiency HOUT / (HOUT + 2), on < 15 % of
+// the network's FLOPs.
+template <int CIN_, int COUT_, int STRIDE_, int HOUT_, int XC_, int OUT_PAR_, int XLO_ = 0, int FLAGS_ = 0>
 struct ConvCfg {
     static constexpr int CIN = CIN_, COUT = COUT_, STRIDE = STRIDE_, HOUT = HOUT_, XC = XC_, OUT_PAR = OUT_PAR_;
+    static constexpr bool STRIP = (FLAGS_ & 1) != 0;
+    static constexpr bool FLAT = STRIP && HOUT <= 4;
     // XLO: the extra operand's weights come as an fp16 hi + lo pair (two MMA passes over the same activation stage): the
     // folded 1x1 shortcut weights are the largest single source of fp16 weight-rounding error and cost < 1 % to do exactly
     static constexpr int XP = 1 + XLO_;
     // input channels per A stage / weight slab: 32 for the stride-2 convs (four parity planes per stage) and for the
     // 256-channel layers (keeps the activation ring small so the streamed-weight ring can be deep)
-    static constexpr int G = (STRIDE == 2 && COUT >= 256) ? 16 : ((STRIDE == 2 || COUT >= 256) ? 32 : (CIN < 64 ? CIN : 64));
+    // (FLAT tiles carry NB images' whole patches per stage: 16 / 32 channels keep the stage small)
+    static constexpr int G = (STRIDE == 2 && (COUT >= 256 || FLAT)) ? 16 : ((STRIDE == 2 || COUT >= 256 || FLAT) ? 32 : (CIN % 64 != 0 ? 32 : 64));
     static constexpr int NCG = CIN / G;
     static constexpr int CH = G / 8;               // 16-byte chunks per pixel per A stage
-    static constexpr int NB = (HOUT == 8) ? 2 : 1; // images per tile (pair layouts)
-    static constexpr int TR = 128 / (8 * NB);      // tile rows (16 or 8); tile = TR x (NB * 8) pixels
-    static constexpr int BLKW = (STRIDE == 1) ? 10 : 9; // patch pixels per 8-wide block (halo included)
+    static constexpr int BLKW = FLAT ? (STRIDE == 1 ? HOUT + 2 : HOUT + 1) : ((STRIDE == 1) ? 10 : 9); // patch pixels per block (halo included)
+    static constexpr int NB = FLAT ? 128 / (HOUT * BLKW) : ((HOUT == 8) ? 2 : 1); // images per tile
+    static constexpr int TR = FLAT ? HOUT : 128 / (8 * NB); // tile rows; tile = TR x (NB * 8) pixels [FLAT: TR x NB x BLKW positions]
     static constexpr int PITCH = BLKW * NB;
     static constexpr int PROWS = (STRIDE == 1) ? TR + 2 : TR + 1;
     static constexpr int NPLANES = (STRIDE == 1) ? 1 : 4;
@@ -53,20 +63,21 @@ struct ConvCfg {
     static constexpr int PLANE_BYTES = CH * PLANE_PX * 16;              // one TMA box
     static constexpr int PLANE_STRIDE = (PLANE_BYTES + 127) / 128 * 128; // TMA destinations are 128-byte aligned
     static constexpr int A_LBO = PLANE_PX * 16; // bytes between 8-channel chunks
-    static constexpr int A_SBO = BLKW * 16;     // bytes between 8-pixel groups (M direction)
+    static constexpr int A_SBO = FLAT ? 128 : BLKW * 16; // bytes between 8-pixel groups (M direction); FLAT: consecutive positions
     static constexpr int A_MAIN_BYTES = NPLANES * PLANE_STRIDE;
     static constexpr int A_TX_BYTES = NPLANES * PLANE_BYTES;
     // extra operand: dense [chunk][128 pixels][8]
-    static constexpr int GX = XC == 0 ? 16 : (XC < G ? XC : G); // extra-operand channels per stage / weight slab
+    static constexpr int GX = XC == 0 ? 16 : (XC < G ? XC : (XC % G == 0 ? G : 32)); // extra-operand channels per stage / weight slab
     static constexpr int NXS = XC == 0 ? 0 : XC / GX;
-    static constexpr int X_LBO = 128 * 16, X_SBO = 128;
+    static constexpr int XBOXW = FLAT ? BLKW : 8; // extra-operand box: same position pitch as the accumulator rows
+    static constexpr int X_LBO = FLAT ? TR * PITCH * 16 : 128 * 16, X_SBO = 128;
     static constexpr int X_STAGE_BYTES = (GX / 8) * X_LBO;
     static constexpr int A_STAGE_BYTES = ((A_MAIN_BYTES > X_STAGE_BYTES ? A_MAIN_BYTES : X_STAGE_BYTES) + 127) / 128 * 128;
     static constexpr int SLAB_BYTES = G * COUT * 2; // one (cin_group, tap) weight slab
     static constexpr int X_SLAB_BYTES = GX * COUT * 2;
     static constexpr int W_MAIN_BYTES = NCG * 9 * SLAB_BYTES;
     static constexpr int W_X_BYTES = XC * COUT * 2 * XP;
-    static constexpr bool RESIDENT = (W_MAIN_BYTES + W_X_BYTES) <= 84 * 1024;
+    static constexpr bool RESIDENT = (W_MAIN_BYTES + W_X_BYTES) <= 84 * 1024 && !FLAT; // (FLAT: several cin groups -> streamed path)
     // weight-slab ring: deep enough that ring depth x MMA time per slab covers the ~2500-cycle L2 -> smem latency of a
     // bulk copy (one slab feeds G/16 MMAs of max(N/2, 32 + N/4) cycles), leaving room for >= MIN_NAS activation stages
     // streamed weights: the activation ring holds exactly two passes' worth of one step (MIN_NAS = 4: one stage per tile
@@ -82,13 +93,14 @@ struct ConvCfg {
     static constexpr int ONES_BYTES = 2 * 128 * 16; // matching A operand: k=0,1 -> 1.0, rest 0
     static constexpr int A_BUDGET = 231000 - B_BYTES - BIAS_BYTES - ONES_BYTES;
     static constexpr int NAS = (A_BUDGET / A_STAGE_BYTES) > 8 ? 8 : (A_BUDGET / A_STAGE_BYTES); // A ring depth
-    static constexpr int NACC = (COUT <= 128) ? 4 : 2; // TMEM accumulator stages (NACC * COUT <= 512 columns)
+    static constexpr int NACC = (COUT <= 128) ? 4 : 2; // TMEM accumulator stages (NACC * ACC_COLS <= 512 columns)
+    static constexpr int ACC_COLS = (COUT == 96) ? 128 : COUT; // accumulator pitch in TMEM columns (power of two)
     // bias: for the smem-operand-bound 32/64-channel layers it is added in the epilogue from registers (an extra MMA
     // would cost 5 % / 3 % of the tile); for 128/256 channels it enters the accumulator through one K=16 MMA
     static constexpr bool BIAS_REG = COUT <= 64;
     // last conv of a stage whose output feeds a prediction head (layer1.1 / layer2.1 / layer3.1 conv2, arch.py:282,288,294):
     // the epilogue also emits per-tile global-average-pool partial sums, so the head never re-reads the activation
-    static constexpr bool GAP = (XC == COUT) && COUT >= 64;
+    static constexpr bool GAP = (XC == COUT) && COUT >= 64 && !STRIP; // (the CU networks' head pools the stored activations)
     static constexpr int NBAR = 2 * NAS + 2 * (RESIDENT ? 1 : NBS) + 2 * NACC;
     static constexpr int OFF_A = 0;
     static constexpr int OFF_B = OFF_A + NAS * A_STAGE_BYTES;
@@ -97,13 +109,13 @@ struct ConvCfg {
     static constexpr int OFF_BAR = OFF_ONES + ONES_BYTES;
     static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
     static constexpr int SMEM_BYTES = OFF_TMEM + 16;
-    static constexpr int TMEM_COLS = (NACC * COUT <= 32) ? 32 : (NACC * COUT <= 64 ? 64 : (NACC * COUT <= 128 ? 128 : (NACC * COUT <= 256 ? 256 : 512)));
+    static constexpr int TMEM_COLS = (NACC * ACC_COLS <= 32) ? 32 : (NACC * ACC_COLS <= 64 ? 64 : (NACC * ACC_COLS <= 128 ? 128 : (NACC * ACC_COLS <= 256 ? 256 : 512)));
     // warp roles: 0-3 epilogue group 0, 4-7 epilogue group 1 (alternate tiles), 8 MMA issuer, 9 weight loader, 10 activation TMA
     // (resident-weight layers: a second issuer warp takes the odd tiles -- one warp cannot issue a tile's ~220 instructions
     //  in the 750 cycles its 18 N=32 MMAs take, see profiles/r01/README.md)
     static constexpr int W_MMA = 8, W_BLOAD = 9, W_ALOAD = 10, W_MMA2 = 11;
     static constexpr int NTHREADS = 384;
-    static constexpr int TILES_PER_IMG = (NB == 2) ? 1 : (HOUT / 16) * (HOUT / 8);
+    static constexpr int TILES_PER_IMG = (NB != 1 || FLAT) ? 1 : (HOUT / 16) * (HOUT / 8);
     // layouts of the tensors this conv touches
     static constexpr int IN_PAIR = (NB == 2);
     static constexpr int OUT_PAIR = (HOUT == 8) || (HOUT == 16 && OUT_PAR);
@@ -114,10 +126,13 @@ struct ConvCfg {
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
     static_assert(NAS >= 2, "need at least a double-buffered A ring");
     static_assert(A_LBO / 16 < 16384 && COUT * 16 / 16 < 16384, "descriptor field range");
-    static_assert(COUT % 32 == 0 && G % 16 == 0 && GX % 16 == 0, "shape");
+    static_assert(COUT % 32 == 0 && G % 16 == 0 && GX % 16 == 0 && CIN % G == 0 && (XC == 0 || XC % GX == 0), "shape");
+    static_assert(NACC * ACC_COLS <= 512, "TMEM columns");
+    static_assert(!FLAT || (TR * PITCH <= 128 && NB >= 1 && NB <= 256), "flat tile must fit the 128 accumulator rows");
+    static_assert(STRIP || (HOUT >= 8 && COUT != 96), "the CTU network has no small maps");
     static_assert(BLKW * 8 <= 256 && PROWS <= 256, "TMA box extents");
 
-    __host__ __device__ static int num_tiles(int nimg) { return NB == 2 ? (nimg + 1) / 2 : nimg * TILES_PER_IMG; }
+    __host__ __device__ static int num_tiles(int nimg) { return (NB != 1 || FLAT) ? (nimg + NB - 1) / NB : nimg * TILES_PER_IMG; }
 };
 
 // offset (in 16-byte units) of tap (kh, kw) inside the A stage
@@ -173,7 +188,10 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
         // two groups of 4 warps take alternate tiles, so one group's global stores overlap the other's TMEM reads
         const int grp = warp >> 2, wq = warp & 3;
         const int m = wq * 32 + lane; // accumulator row == TMEM lane == pixel of the tile
-        const int r = m / (8 * C::NB), h = (m / 8) % C::NB, c = m % 8;
+        // FLAT: row m is position m of the flattened [row][image][x incl. halo] box; halo positions are not stored
+        const int r = C::FLAT ? m / C::PITCH : m / (8 * C::NB), h = C::FLAT ? (m % C::PITCH) / C::BLKW : (m / 8) % C::NB,
+                  c = C::FLAT ? m % C::BLKW : m % 8;
+        const bool row_ok = !C::FLAT || (r < C::HOUT && c < C::HOUT);
         uint32_t acc_it = grp;
         float bias_r[C::BIAS_REG ? C::COUT : 1];
         if constexpr (C::BIAS_REG) {
@@ -185,26 +203,29 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
             // the activations the previous kernel wrote last (still in the 126 MB L2) -- consecutive layers zig-zag
             const int ptile = p.reverse ? ntiles - 1 - tile : tile;
             int img, oy, ox;
-            if (C::NB == 2) { img = ptile * 2 + h; oy = r; ox = c; }
+            if constexpr (C::NB != 1 || C::FLAT) { img = ptile * C::NB + h; oy = r; ox = c; }
             else {
                 img = ptile / C::TILES_PER_IMG;
                 const int rem = ptile % C::TILES_PER_IMG;
                 oy = (rem / (C::HOUT / 8)) * 16 + r;
                 ox = (rem % (C::HOUT / 8)) * 8 + c;
             }
-            const bool valid = img < p.nimg && !(p.dbg & 2);
+            const bool valid = img < p.nimg && row_ok && !(p.dbg & 2);
             const int unit = C::OUT_PAIR ? img >> 1 : img, sub = C::OUT_PAIR ? img & 1 : 0;
             const int plane = C::OUT_PAR ? (oy & 1) * 2 + (ox & 1) : 0;
             const int yy = C::OUT_PAR ? oy >> 1 : oy, xx = C::OUT_PAR ? ox >> 1 : ox;
-            const size_t off = (size_t)unit * C::OUNIT + (size_t)plane * (C::OCHUNK * (C::COUT / 8)) +
-                               (size_t)((yy * C::ONIMG + sub) * C::OHP + xx) * 8;
+            // strip layout: [plane][COUT/8][OHP rows][strip_cap images][OHP][8]
+            const size_t ochunk = C::STRIP ? (size_t)C::OHP * p.strip_cap * C::OHP * 8 : (size_t)C::OCHUNK;
+            const size_t off = C::STRIP ? (size_t)plane * (ochunk * (C::COUT / 8)) + ((size_t)(yy * p.strip_cap + img) * C::OHP + xx) * 8
+                                        : (size_t)unit * C::OUNIT + (size_t)plane * (C::OCHUNK * (C::COUT / 8)) +
+                                              (size_t)((yy * C::ONIMG + sub) * C::OHP + xx) * 8;
             const uint32_t acc = acc_it % C::NACC;
             mbar_wait(&accFull[acc], (acc_it / C::NACC) & 1);
             tc_fence_after();
 #pragma unroll(C::BIAS_REG ? 2 : 1)
             for (int c0 = 0; c0 < ((p.dbg & 4) ? 0 : C::COUT); c0 += 32) {
                 uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + acc * C::COUT + c0, v);
+                tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + acc * C::ACC_COLS + c0, v);
                 tmem_ld_wait();
                 if constexpr (C::BIAS_REG) {
 #pragma unroll
@@ -218,14 +239,14 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
                     hq[e] = p.relu ? __hmax2(t, zero2) : t; // max(round(x), 0) == round(max(x, 0))
                 }
                 if (valid) {
-                    __half *op = p.out + off + (size_t)(c0 / 8) * C::OCHUNK;
+                    __half *op = p.out + off + (size_t)(c0 / 8) * ochunk;
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
                         uint4 ov;
                         __half2 *h2 = reinterpret_cast<__half2 *>(&ov);
 #pragma unroll
                         for (int e = 0; e < 4; e++) h2[e] = hq[q * 4 + e];
-                        *reinterpret_cast<uint4 *>(op + (size_t)q * C::OCHUNK) = ov;
+                        *reinterpret_cast<uint4 *>(op + (size_t)q * ochunk) = ov;
                     }
                 }
                 if constexpr (C::GAP) {
@@ -275,7 +296,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
             // two issuer warps take alternate tiles.
             static_assert(!C::RESIDENT || (C::NCG == 1 && C::NXS <= 1 && C::TP == 1 && C::BIAS_REG), "resident-weight path assumptions");
             constexpr int SPT = 1 + C::NXS; // stages per tile
-            static_assert(!C::RESIDENT || C::NAS >= 3 * SPT, "A ring must hold the two tiles in flight plus one prefetched");
+            static_assert(!C::RESIDENT || C::NAS >= 2 * SPT + 1, "A ring must hold the two tiles in flight plus a prefetched stage");
             mbar_wait(&fullB[0], 0);
             auto wait_tile = [&](uint32_t j) {
                 if (p.dbg & 8) return; // debug: free-running MMA stream, no handshakes
@@ -294,7 +315,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
                 wait_tile(j); // each issuer has two tile-times per tile: the wait latency is off the critical path
                 if (p.trace != nullptr && blockIdx.x == 0 && j < 1024 && lane == 0) p.trace[j] = clock64();
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (j % C::NACC) * C::COUT;
+                const uint32_t d_tmem = tmem_base + (j % C::NACC) * C::ACC_COLS;
                 const uint32_t st0 = (j * SPT) % C::NAS;
                 const uint32_t a_lo0 = umma_desc_lo(sA + st0 * C::A_STAGE_BYTES, C::A_LBO);
                 auto issue_taps = [&](int t0, int t1) {
@@ -344,7 +365,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
                 if (h < np) {
                     const uint32_t acc = (acc_it + h) % C::NACC;
                     mbar_wait(&accEmpty[acc], (((acc_it + h) / C::NACC) & 1) ^ 1);
-                    d_tmem[h] = tmem_base + acc * C::COUT;
+                    d_tmem[h] = tmem_base + acc * C::ACC_COLS;
                 }
             }
             tc_fence_after();
@@ -513,7 +534,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
                     const int ltile = tile0 + h * (int)gridDim.x;
                     const int tile = p.reverse ? ntiles - 1 - ltile : ltile;
                     int unit, oy0, ox0;
-                    if (C::NB == 2) { unit = tile; oy0 = 0; ox0 = 0; }
+                    if constexpr (C::NB != 1 || C::FLAT) { unit = tile; oy0 = 0; ox0 = 0; }
                     else {
                         unit = tile / C::TILES_PER_IMG;
                         const int rem = tile % C::TILES_PER_IMG;
@@ -528,17 +549,20 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
                         const uint32_t abase = sA + st * C::A_STAGE_BYTES;
                         if (it < C::NCG) {
                             mbar_arrive_expect_tx(&fullA[st], C::A_TX_BYTES);
+                            // strip layout: the image index is a box coordinate (first image of the tile), the last one the plane
+                            const int ci = C::STRIP ? unit * C::NB : 0;
                             if constexpr (C::STRIDE == 1) {
-                                tma_load_5d(abase, &p.in_map, (ox0 - 1) * 8, 0, oy0 - 1, it * C::CH, unit, &fullA[st]);
+                                tma_load_5d(abase, &p.in_map, (ox0 - 1) * 8, ci, oy0 - 1, it * C::CH, C::STRIP ? 0 : unit, &fullA[st]);
                             } else {
 #pragma unroll
                                 for (int pl = 0; pl < 4; pl++)
-                                    tma_load_5d(abase + pl * C::PLANE_STRIDE, &p.in_map, (ox0 - (pl & 1)) * 8, 0, oy0 - (pl >> 1),
-                                                it * C::CH, unit * 4 + pl, &fullA[st]);
+                                    tma_load_5d(abase + pl * C::PLANE_STRIDE, &p.in_map, (ox0 - (pl & 1)) * 8, ci, oy0 - (pl >> 1),
+                                                it * C::CH, C::STRIP ? pl : unit * 4 + pl, &fullA[st]);
                             }
                         } else {
                             mbar_arrive_expect_tx(&fullA[st], C::X_STAGE_BYTES);
-                            tma_load_5d(abase, &p.x_map, ox0 * 8, 0, oy0, (it - C::NCG) * (C::GX / 8), unit * p.x_unit_mul, &fullA[st]);
+                            tma_load_5d(abase, &p.x_map, ox0 * 8, C::STRIP ? unit * C::NB : 0, oy0, (it - C::NCG) * (C::GX / 8),
+                                        C::STRIP ? 0 : unit * p.x_unit_mul, &fullA[st]);
                         }
                     }
                     __syncwarp();

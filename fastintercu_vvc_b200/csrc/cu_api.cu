@@ -1,0 +1,346 @@
+// cu_api.cu -- C ABI for the smaller-CU models (include/mltcnn_cu.h): context, weight blob, strip buffers, launch
+// sequence (staging + conv1, 20 tcgen05 convs, head).  Drop-in for the cuw != 128 branch of the reference hook
+// (EncCu.cpp:754,899,916-919).  No CPU fallback.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "mlt_internal.h"
+
+using namespace mlt;
+
+namespace {
+
+constexpr uint32_t MLTW_MAGIC = 0x57544C4Du;
+enum : uint32_t { SEC_CONV1_UMMA = 0x002, SEC_W_F16 = 0x100, SEC_BIAS_FUSED = 0x200, SEC_FC_W = 0x800, SEC_FC_B = 0x900, SEC_BIAS_MMA = 0xA00, SEC_X_W_F16 = 0xB00 };
+constexpr int FC_IN[CU_NHEAD] = {66, 98, 130, 258}, FC_OUT[CU_NHEAD] = {2, 3, 4, 6};
+
+struct Section { const uint8_t *dev = nullptr; size_t bytes = 0; };
+
+} // namespace
+
+struct mlt_cu_ctx {
+    int device = 0, size = 0, cap = 0, num_sms = 0;
+    cudaStream_t stream = nullptr;
+    uint8_t *d_blob = nullptr;
+    Section sec[0x1000];
+    CuLayerInfo info[CU_NCONV];
+    ActLayout lay[CU_NACT];
+    __half *act[CU_NACT] = {};
+    ConvParams conv_p[CU_NCONV];
+    int16_t *d_in = nullptr, *h_in = nullptr; // dense [cap][2][size][size]
+    int32_t *d_pq = nullptr, *h_pq = nullptr; // [cap][2]
+    CtuDev *d_cus = nullptr;
+    mlt_cu_result *d_out = nullptr, *h_out = nullptr;
+    float *d_dbg = nullptr;
+    size_t dbg_bytes = 0;
+    int last_n = 0;
+    uint64_t launches = 0;
+    std::string err;
+};
+
+namespace {
+
+int fail(mlt_cu_ctx *c, int rc, const char *fmt, ...)
+{
+    if (c) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        c->err = buf;
+    }
+    return rc;
+}
+
+#define CU(call)                                                                                                   \
+    do {                                                                                                           \
+        cudaError_t e_ = (call);                                                                                   \
+        if (e_ != cudaSuccess) return fail(c, e_ == cudaErrorMemoryAllocation ? MLT_E_NOMEM : MLT_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+template <typename T>
+const T *secp(const mlt_cu_ctx *c, uint32_t id) { return reinterpret_cast<const T *>(c->sec[id].dev); }
+
+int load_blob(mlt_cu_ctx *c, const char *path)
+{
+    FILE *f = fopen(path, "rb");
+    if (!f) return fail(c, MLT_E_IO, "cannot open weight blob '%s'", path);
+    fseek(f, 0, SEEK_END);
+    const long sz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    std::vector<uint8_t> raw((size_t)(sz > 0 ? sz : 0));
+    const size_t got = raw.empty() ? 0 : fread(raw.data(), 1, raw.size(), f);
+    fclose(f);
+    if (got != raw.size() || raw.size() < 32) return fail(c, MLT_E_IO, "short read on '%s'", path);
+    uint32_t hdr[4];
+    uint64_t total;
+    memcpy(hdr, raw.data(), 16);
+    memcpy(&total, raw.data() + 16, 8);
+    // the operand layouts depend on the CU size (tile shapes differ per size), so a blob is packed for ONE size
+    if (hdr[0] != MLTW_MAGIC || hdr[1] != 2 || (int)hdr[2] != c->size || total != raw.size() || 32 + (size_t)hdr[3] * 24 > raw.size())
+        return fail(c, MLT_E_FORMAT, "'%s' is not an MLTW v2 blob for the %dx%d CU model", path, c->size, c->size);
+    CU(cudaMalloc(&c->d_blob, raw.size()));
+    CU(cudaMemcpy(c->d_blob, raw.data(), raw.size(), cudaMemcpyHostToDevice));
+    for (uint32_t i = 0; i < hdr[3]; i++) {
+        uint32_t id, dt;
+        uint64_t off, nb;
+        const uint8_t *e = raw.data() + 32 + (size_t)i * 24;
+        memcpy(&id, e, 4); memcpy(&dt, e + 4, 4); memcpy(&off, e + 8, 8); memcpy(&nb, e + 16, 8);
+        if (id >= 0x1000 || off + nb > raw.size() || (off & 255)) return fail(c, MLT_E_FORMAT, "bad section table in '%s'", path);
+        c->sec[id].dev = c->d_blob + off;
+        c->sec[id].bytes = nb;
+    }
+    auto need = [&](uint32_t id, size_t bytes) { return c->sec[id].dev != nullptr && c->sec[id].bytes == bytes; };
+    bool ok = need(SEC_CONV1_UMMA, 2 * 4 * 32 * 16);
+    for (int li = 0; li < CU_NCONV && ok; li++) {
+        const CuLayerInfo &L = c->info[li];
+        ok = need(SEC_W_F16 + li, (size_t)9 * L.cin * L.cout * 2) && need(SEC_BIAS_FUSED + li, (size_t)L.cout * 4) &&
+             need(SEC_BIAS_MMA + li, (size_t)L.cout * 32);
+        if (ok && L.xc > 0) ok = need(SEC_X_W_F16 + li, (size_t)L.xc * L.cout * 2 * ((li & 3) == 1 ? 2 : 1)); // shortcut weights: hi + lo
+    }
+    for (int i = 0; i < CU_NHEAD && ok; i++) ok = need(SEC_FC_W + i, (size_t)FC_IN[i] * FC_OUT[i] * 4) && need(SEC_FC_B + i, (size_t)FC_OUT[i] * 4);
+    if (!ok) return fail(c, MLT_E_FORMAT, "'%s': missing or mis-sized section", path);
+    return MLT_OK;
+}
+
+__global__ void cu_dense_descs_kernel(CtuDev *cus, const int16_t *orgpred, const int32_t *pocqp, int n, int size)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    CtuDev d;
+    d.org = orgpred + (size_t)i * 2 * size * size;
+    d.pred = d.org + (size_t)size * size;
+    d.org_stride = d.pred_stride = size;
+    d.poc = pocqp[2 * i];
+    d.qp = pocqp[2 * i + 1];
+    cus[i] = d;
+}
+
+// the whole network on n CUs stored densely at d_orgpred; results to device array `out`
+int run_network(mlt_cu_ctx *c, int n, const int16_t *d_orgpred, const int32_t *d_pocqp, mlt_cu_result *out, cudaStream_t s)
+{
+    cu_dense_descs_kernel<<<(n + 255) / 256, 256, 0, s>>>(c->d_cus, d_orgpred, d_pocqp, n, c->size);
+    CU(cudaGetLastError());
+    CU(launch_cu_conv1(c->size, c->d_cus, n, secp<__half>(c, SEC_CONV1_UMMA), c->act[0], c->cap, s));
+    c->launches += 2;
+    for (int li = 0; li < CU_NCONV; li++) {
+        ConvParams &p = c->conv_p[li];
+        p.nimg = n;
+        CU(launch_cu_conv(c->size, li, p, c->num_sms, s));
+        c->launches++;
+    }
+    CuHeadParams hp;
+    for (int i = 0; i < CU_NHEAD; i++) {
+        const int a = 4 * (i + 1) + 4; // output of layer(i+1).1.conv2 = conv 4 * (i + 1) + 3
+        hp.act[i] = c->act[a];
+        hp.lay[i] = c->lay[a];
+        hp.fc_w[i] = secp<float>(c, SEC_FC_W + i);
+        hp.fc_b[i] = secp<float>(c, SEC_FC_B + i);
+    }
+    hp.cus = c->d_cus; hp.out = out; hp.n = n;
+    CU(launch_cu_head(hp, s));
+    c->launches++;
+    c->last_n = n;
+    return MLT_OK;
+}
+
+int check_ctx(mlt_cu_ctx *c)
+{
+    if (!c) return MLT_E_INVAL;
+    c->err.clear();
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e != cudaSuccess) return fail(c, MLT_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    return MLT_OK;
+}
+
+// h_in[0..n) / h_pq[0..n) are filled: upload, run, download, wait
+int run_host_batch(mlt_cu_ctx *c, int n, const int16_t *src, const int32_t *pq, mlt_cu_result *out)
+{
+    cudaStream_t s = c->stream;
+    const size_t per = (size_t)2 * c->size * c->size;
+    CU(cudaMemcpyAsync(c->d_in, src, (size_t)n * per * sizeof(int16_t), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(c->d_pq, pq, (size_t)n * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    int rc = run_network(c, n, c->d_in, c->d_pq, c->d_out, s);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(c->h_out, c->d_out, (size_t)n * sizeof(mlt_cu_result), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    memcpy(out, c->h_out, (size_t)n * sizeof(mlt_cu_result));
+    return MLT_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+const char *mlt_cu_last_error(const mlt_cu_ctx *c) { return c ? c->err.c_str() : ""; }
+
+int mlt_cu_layer_info(int cu_size, int layer, int32_t info[10])
+{
+    CuLayerInfo L;
+    if (!info || cu_conv_info(cu_size, layer, &L) != cudaSuccess) return MLT_E_INVAL;
+    const int32_t v[10] = {L.cin, L.cout, L.stride, L.hout, L.xc, L.out_par, L.nb, L.flat, L.g, L.gx};
+    memcpy(info, v, sizeof v);
+    return MLT_OK;
+}
+int mlt_cu_size(const mlt_cu_ctx *c) { return c ? c->size : 0; }
+uint64_t mlt_cu_launch_count(const mlt_cu_ctx *c) { return c ? c->launches : 0; }
+
+void mlt_cu_destroy(mlt_cu_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (__half *a : c->act) cudaFree(a);
+    cudaFree(c->d_blob); cudaFree(c->d_in); cudaFree(c->d_pq); cudaFree(c->d_cus); cudaFree(c->d_out); cudaFree(c->d_dbg);
+    cudaFreeHost(c->h_in); cudaFreeHost(c->h_pq); cudaFreeHost(c->h_out);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int mlt_cu_create(mlt_cu_ctx **out, const char *weights_path, int cuda_device, int cu_size, int max_batch)
+{
+    if (!out) return MLT_E_INVAL;
+    *out = nullptr;
+    if (!weights_path || (cu_size != 64 && cu_size != 32 && cu_size != 16) || max_batch < 1 || max_batch > (1 << 18)) return MLT_E_INVAL;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return MLT_E_NODEVICE;
+    if (cuda_device < 0 || cuda_device >= ndev) return MLT_E_NODEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cuda_device) != cudaSuccess) return MLT_E_NODEVICE;
+    if (prop.major != 10) return MLT_E_NODEVICE; // sm_100a cubin only: tcgen05 / TMEM required, no other path exists
+    mlt_cu_ctx *c = new (std::nothrow) mlt_cu_ctx();
+    if (!c) return MLT_E_NOMEM;
+    c->device = cuda_device;
+    c->size = cu_size;
+    c->cap = max_batch;
+    c->num_sms = prop.multiProcessorCount;
+    auto body = [&]() -> int {
+        CU(cudaSetDevice(cuda_device));
+        CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        for (int li = 0; li < CU_NCONV; li++) CU(cu_conv_info(cu_size, li, &c->info[li]));
+        int r = load_blob(c, weights_path);
+        if (r) return r;
+        CU(conv_umma_init()); // resolves cuTensorMapEncodeTiled
+        CU(cu_conv_init(cu_size));
+        // every activation is ONE strip over the whole batch: [plane][C/8][row][cap images][x][8] fp16
+        c->lay[0] = ActLayout{cu_size, 32, 1, 0, c->cap};
+        for (int li = 0; li < CU_NCONV; li++) c->lay[li + 1] = ActLayout{c->info[li].hout, c->info[li].cout, c->info[li].out_par, 0, c->cap};
+        for (int a = 0; a < CU_NACT; a++) {
+            const size_t bytes = c->lay[a].unit_elems() * sizeof(__half);
+            CU(cudaMalloc(&c->act[a], bytes));
+            CU(cudaMemsetAsync(c->act[a], 0, bytes, c->stream)); // images beyond a batch's n are read by the last tile: keep them finite
+        }
+        memset(c->conv_p, 0, sizeof c->conv_p);
+        for (int li = 0; li < CU_NCONV; li++) {
+            ConvParams &p = c->conv_p[li];
+            const bool has_x = c->info[li].xc > 0; // second conv of a block: X = the block's input = activation li - 1
+            CU(cu_conv_prepare(cu_size, li, &p, c->act[li], c->lay[li], has_x ? c->act[li - 1] : nullptr, has_x ? &c->lay[li - 1] : nullptr));
+            p.w = secp<__half>(c, SEC_W_F16 + li);
+            p.bias = secp<__half>(c, SEC_BIAS_MMA + li);
+            p.bias_f32 = secp<float>(c, SEC_BIAS_FUSED + li);
+            p.x_w = has_x ? secp<__half>(c, SEC_X_W_F16 + li) : nullptr;
+            p.out = c->act[li + 1];
+            p.relu = 1;
+            p.reverse = getenv("MLT_NO_REVERSE") ? 0 : (li & 1);
+        }
+        const size_t per = (size_t)2 * cu_size * cu_size;
+        CU(cudaMalloc(&c->d_in, (size_t)max_batch * per * sizeof(int16_t)));
+        CU(cudaMalloc(&c->d_pq, (size_t)max_batch * 2 * sizeof(int32_t)));
+        CU(cudaMalloc(&c->d_cus, (size_t)max_batch * sizeof(CtuDev)));
+        CU(cudaMalloc(&c->d_out, (size_t)max_batch * sizeof(mlt_cu_result)));
+        CU(cudaHostAlloc(&c->h_in, (size_t)max_batch * per * sizeof(int16_t), cudaHostAllocDefault));
+        CU(cudaHostAlloc(&c->h_pq, (size_t)max_batch * 2 * sizeof(int32_t), cudaHostAllocDefault));
+        CU(cudaHostAlloc(&c->h_out, (size_t)max_batch * sizeof(mlt_cu_result), cudaHostAllocDefault));
+        CU(cudaStreamSynchronize(c->stream));
+        return MLT_OK;
+    };
+    const int rc = body();
+    if (rc != MLT_OK) {
+        fprintf(stderr, "mlt_cu_create: %s (%s)\n", mlt_strerror(rc), c->err.c_str());
+        mlt_cu_destroy(c);
+        return rc;
+    }
+    *out = c;
+    return MLT_OK;
+}
+
+int mlt_cu_predict_batch(mlt_cu_ctx *c, int n, const mlt_ctu_desc *descs, mlt_cu_result *out)
+{
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!descs || !out))) return fail(c, MLT_E_INVAL, "null argument");
+    if (n > c->cap) return fail(c, MLT_E_BATCH, "n=%d > max_batch=%d", n, c->cap);
+    if (n == 0) return MLT_OK;
+    const int S = c->size;
+    for (int i = 0; i < n; i++) {
+        if (!descs[i].org || !descs[i].pred) return fail(c, MLT_E_INVAL, "descs[%d]: null org/pred", i);
+        int16_t *dst = c->h_in + (size_t)i * 2 * S * S; // private dense copy, like the hook's xMalloc buffers (EncCu.cpp:811-830)
+        for (int y = 0; y < S; y++) memcpy(dst + (size_t)y * S, descs[i].org + (size_t)y * descs[i].org_stride, S * sizeof(int16_t));
+        dst += (size_t)S * S;
+        for (int y = 0; y < S; y++) memcpy(dst + (size_t)y * S, descs[i].pred + (size_t)y * descs[i].pred_stride, S * sizeof(int16_t));
+        c->h_pq[2 * i] = descs[i].poc;
+        c->h_pq[2 * i + 1] = descs[i].qp;
+    }
+    return run_host_batch(c, n, c->h_in, c->h_pq, out);
+}
+
+int mlt_cu_predict(mlt_cu_ctx *c, const int16_t *org, int org_stride, const int16_t *pred, int pred_stride, int poc, int qp,
+                   mlt_cu_result *out)
+{
+    mlt_ctu_desc d;
+    d.org = org; d.pred = pred; d.org_stride = org_stride; d.pred_stride = pred_stride; d.poc = poc; d.qp = qp;
+    return mlt_cu_predict_batch(c, 1, &d, out);
+}
+
+int mlt_cu_predict_batch_dense(mlt_cu_ctx *c, int n, const int16_t *orgpred, const int32_t *pocqp, mlt_cu_result *out)
+{
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!orgpred || !pocqp || !out))) return fail(c, MLT_E_INVAL, "null argument");
+    if (n > c->cap) return fail(c, MLT_E_BATCH, "n=%d > max_batch=%d", n, c->cap);
+    if (n == 0) return MLT_OK;
+    return run_host_batch(c, n, orgpred, pocqp, out);
+}
+
+int mlt_cu_predict_batch_device(mlt_cu_ctx *c, int n, const int16_t *d_orgpred, const int32_t *d_pocqp, mlt_cu_result *d_out,
+                                void *cuda_stream)
+{
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!d_orgpred || !d_pocqp || !d_out))) return fail(c, MLT_E_INVAL, "null argument");
+    if (n > c->cap) return fail(c, MLT_E_BATCH, "n=%d > max_batch=%d", n, c->cap);
+    if (((uintptr_t)d_orgpred & 15) != 0) return fail(c, MLT_E_INVAL, "d_orgpred must be 16-byte aligned");
+    if (n == 0) return MLT_OK;
+    return run_network(c, n, d_orgpred, d_pocqp, d_out, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int64_t mlt_cu_debug_activation(mlt_cu_ctx *c, int layer, float *out, int64_t capacity)
+{
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (layer < 0 || layer >= CU_NACT || !out) return fail(c, MLT_E_INVAL, "bad layer");
+    if (c->last_n <= 0) return fail(c, MLT_E_STATE, "no batch has been run");
+    const ActLayout &L = c->lay[layer];
+    const size_t elems = (size_t)L.H * L.H * L.C * c->last_n;
+    if ((int64_t)elems > capacity) return fail(c, MLT_E_INVAL, "capacity %lld < %zu", (long long)capacity, elems);
+    if (c->dbg_bytes < elems * sizeof(float)) {
+        if (c->d_dbg) cudaFree(c->d_dbg);
+        c->d_dbg = nullptr;
+        c->dbg_bytes = 0;
+        CU(cudaMalloc(&c->d_dbg, elems * sizeof(float)));
+        c->dbg_bytes = elems * sizeof(float);
+    }
+    cudaStream_t s = c->stream;
+    CU(launch_unpack_act(c->act[layer], c->d_dbg, c->last_n, L, s));
+    CU(cudaMemcpyAsync(out, c->d_dbg, elems * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return (int64_t)elems;
+}
+
+} // extern "C"

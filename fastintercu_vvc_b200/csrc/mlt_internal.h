@@ -7,6 +7,7 @@
 #include <stdlib.h>
 
 #include "../../include/mltcnn.h"
+#include "../../include/mltcnn_cu.h"
 
 namespace mlt {
 
@@ -70,14 +71,16 @@ cudaError_t launch_conv_simt(const float *in, const float *w /*[k*k][cin][cout]*
 //   (((((u * NPL + p) * (C/8) + k) * HP + y) * NIMG + s) * HP + x) * 8 + e
 // PAR : four parity planes, plane = (row & 1) * 2 + (col & 1), (y, x) = (row >> 1, col >> 1), HP = H / 2
 // PAIR: two images per unit (row-interleaved), image i = unit i >> 1, sub-image i & 1
+// STRIP (smaller-CU networks): ONE unit holds the whole batch, strip = images per unit = buffer capacity; unit index 0
 struct ActLayout {
     int H, C, par, pair;
+    int strip = 0;
     __host__ __device__ int hp() const { return par ? H / 2 : H; }
     __host__ __device__ int npl() const { return par ? 4 : 1; }
-    __host__ __device__ int nimg() const { return pair ? 2 : 1; }
+    __host__ __device__ int nimg() const { return strip ? strip : (pair ? 2 : 1); }
     __host__ __device__ size_t chunk_stride() const { return (size_t)hp() * nimg() * hp() * 8; }
     __host__ __device__ size_t unit_elems() const { return chunk_stride() * (C / 8) * npl(); }
-    __host__ __device__ size_t units_for(int images) const { return pair ? (size_t)(images + 1) / 2 : (size_t)images; }
+    __host__ __device__ size_t units_for(int images) const { return strip ? (size_t)1 : (pair ? (size_t)(images + 1) / 2 : (size_t)images); }
 };
 
 struct ConvParams {
@@ -95,6 +98,7 @@ struct ConvParams {
     int dbg;        // MLT_DEBUG_FLAGS (timing experiments only, results invalid): 1 no activation TMA, 2 no stores, 4 no TMEM reads
     int reverse;    // walk the tiles from the last image to the first (L2 reuse across consecutive layers)
     int x_unit_mul; // 4 when the extra operand tensor is parity-planar (plane 0 = even rows, even columns), else 1
+    int strip_cap;  // strip layouts (smaller-CU networks): images per strip of the OUTPUT tensor (= buffer capacity)
 };
 
 cudaError_t conv_umma_init(); // opt in to large dynamic shared memory for every instantiation; resolve cuTensorMapEncodeTiled
@@ -104,6 +108,33 @@ ActLayout conv_umma_out_layout(int layer); // layout of the activation conv `lay
 cudaError_t conv_umma_prepare(int layer, ConvParams *p, const __half *in, const ActLayout &in_l, const __half *x, const ActLayout *x_l,
                               size_t images);
 cudaError_t launch_conv_umma(int layer, const ConvParams &p, int num_sms, cudaStream_t s);
+// 5-D tiled tensor map over a chunk-planar activation tensor: dims (x*8, img, row, chunk, unit*plane), box (px, img, rows, chunks, 1)
+cudaError_t make_act_map(CUtensorMap *tm, const __half *base, const ActLayout &L, size_t units, int box_px, int box_img,
+                         int box_rows, int box_chunks);
+
+// ---- cu_net_*.cu / cu_stem.cu / cu_head.cu : the smaller-CU networks (64 / 32 / 16-px GapBigMltCuORPQ, mlt_cu_or_pq_arch.py:59-130)
+constexpr int CU_NCONV = 20, CU_NACT = 21, CU_NHEAD = 4, CU_NLOGIT = 15;
+struct CuLayerInfo { // one 3x3 conv of the CU network at a given CU size (forward order, after conv1)
+    int cin, cout, stride, hout, xc, out_par, nb, flat; // stride as executed (a stride-2 conv on a 1x1 map runs as stride 1)
+    int g, gx;                                          // channels per weight slab of the main / extra operand (packer layout)
+};
+cudaError_t cu_conv_init(int size);                    // opt in to large dynamic shared memory for this size's kernels
+cudaError_t cu_conv_info(int size, int layer, CuLayerInfo *info);
+// fill p->in_map / x_map for conv `layer` of the `size`-px network; every tensor is a strip of `cap` images
+cudaError_t cu_conv_prepare(int size, int layer, ConvParams *p, const __half *in, const ActLayout &in_l, const __half *x, const ActLayout *x_l);
+cudaError_t launch_cu_conv(int size, int layer, const ConvParams &p, int num_sms, cudaStream_t s);
+// staging + conv1 on tcgen05 -> activation 0 (H = size, 32 channels, parity-planar strip of `cap` images)
+cudaError_t launch_cu_conv1(int size, const CtuDev *cus, int n, const __half *wop, __half *out, int cap, cudaStream_t s);
+struct CuHeadParams {
+    const __half *act[CU_NHEAD]; // outputs of layer1..layer4 (strip layouts)
+    ActLayout lay[CU_NHEAD];
+    const float *fc_w[CU_NHEAD]; // [out][in]
+    const float *fc_b[CU_NHEAD];
+    const CtuDev *cus;           // poc / qp
+    mlt_cu_result *out;
+    int n;
+};
+cudaError_t launch_cu_head(const CuHeadParams &p, cudaStream_t s);
 
 // ---- head.cu : global average pools + FC heads + softmax + argmax + flags (arch.py:281-297, EncCu.cpp:913-921)
 struct HeadParams {

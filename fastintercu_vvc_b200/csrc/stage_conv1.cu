@@ -285,8 +285,8 @@ __global__ void unpack_act_kernel(const __half *__restrict__ in, float *__restri
         const size_t pix = i / c;
         const int x = (int)(pix % h), y = (int)((pix / h) % h);
         const size_t img = pix / ((size_t)h * h);
-        const size_t unit = L.pair ? img >> 1 : img;
-        const int sub = L.pair ? (int)(img & 1) : 0, plane = L.par ? (y & 1) * 2 + (x & 1) : 0;
+        const size_t unit = L.strip ? 0 : (L.pair ? img >> 1 : img);
+        const int sub = L.strip ? (int)img : (L.pair ? (int)(img & 1) : 0), plane = L.par ? (y & 1) * 2 + (x & 1) : 0;
         const int yy = L.par ? y >> 1 : y, xx = L.par ? x >> 1 : x, hp = L.hp();
         const size_t off = (unit * L.npl() + plane) * (size_t)(c / 8) * L.chunk_stride() + (size_t)(ch / 8) * L.chunk_stride() +
                            (size_t)((yy * L.nimg() + sub) * hp + xx) * 8 + (ch & 7);

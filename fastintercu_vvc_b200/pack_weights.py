@@ -19,7 +19,12 @@ What it does
   * writes fp32 copies ([tap][Cin][Cout]) for the fp32 CUDA-core cross-check engine, the fp32 biases, the
     fp32 conv1 ([tap][2][32], consumed by the fused staging+conv1 kernel) and the three FC heads.
 
-CLI:  python -m fastintercu_vvc_b200.pack_weights model.pth out.mltw
+The smaller-CU models (64 / 32 / 16-px `GapBigMltCuORPQ`, mlt_cu_or_pq_arch.py:59-130; exported per size by
+model2torchScript.py:14-22) use the same container with the header's arch field = CU size: the operand layouts follow
+the per-size tile shapes of csrc/cu_net.cuh, so a blob is packed for ONE size (`cu_conv_table(size)`).
+
+CLI:  python -m fastintercu_vvc_b200.pack_weights model.pth out.mltw            (128x128 CTU model)
+      python -m fastintercu_vvc_b200.pack_weights --cu 64 model.pth out.mltw    (64 / 32 / 16-px CU model)
 """
 from __future__ import annotations
 
@@ -247,8 +252,70 @@ def build_sections(sd: dict) -> list:
     return secs
 
 
-def pack(sd: dict) -> bytes:
-    secs = build_sections(sd)
+def cu_conv_table(size: int):
+    """3x3 convs of the `size`-px CU network after conv1, forward order -- mirrors csrc/cu_net.cuh CuSel / ConvCfg:
+    (prefix, cin, cout, stride as executed, hout, cin_group G, xc, gx, kind) with kind 0..3 = position in the stage."""
+    planes_all = (32, 64, 96, 128, 256)
+    rows = []
+    cin_stage, hin = 32, size
+    for L, planes in enumerate(planes_all):
+        fake_s2 = hin == 1  # stride-2 conv on a 1x1 map == the stride-1 conv (reads the same samples)
+        hout = max(hin // 2, 1)
+        flat = hout <= 4
+        for k in range(4):
+            cin = cin_stage if k == 0 else planes
+            stride = 2 if (k == 0 and not fake_s2) else 1
+            if stride == 2 and (planes >= 256 or flat):
+                g = 16
+            elif stride == 2 or planes >= 256 or flat:
+                g = 32
+            else:
+                g = 32 if cin % 64 else 64
+            xc = cin_stage if k == 1 else (planes if k == 3 else 0)
+            gx = 0 if xc == 0 else (xc if xc < g else (g if xc % g == 0 else 32))
+            prefix = f"layer{L}.{k // 2}.conv{k % 2 + 1}"
+            rows.append((prefix, cin, planes, stride, hout, g, xc, gx, k))
+        cin_stage, hin = planes, hout
+    return rows
+
+
+def build_cu_sections(sd: dict, size: int) -> list:
+    sd = normalise_state_dict(sd)
+    secs = []
+
+    def add(sid, arr, dtype):
+        secs.append((sid, np.ascontiguousarray(arr, dtype)))
+
+    w = sd["conv1.weight"].astype(np.float32)  # [32][2][3][3], no BN / bias (mlt_cu_or_pq_arch.py:105)
+    add(SEC_CONV1_F32, w.transpose(2, 3, 1, 0).reshape(9, 2, 32), np.float32)
+    add(SEC_CONV1_UMMA, conv1_operand(w), np.float16)
+    for li, (prefix, cin, cout, stride, hout, group, xc, gx, kind) in enumerate(cu_conv_table(size)):
+        wf, bf = fold_bn(sd[f"{prefix}.weight"], sd, prefix.replace("conv", "bn"))
+        assert wf.shape == (cout, cin, 3, 3), (prefix, wf.shape)
+        add(SEC_W_F16 + li, pack_umma_b(wf, group), np.float16)
+        add(SEC_W_F32 + li, wf.transpose(2, 3, 1, 0).reshape(9, cin, cout), np.float32)
+        add(SEC_BIAS + li, bf, np.float32)
+        fused = bf
+        if kind == 1:  # 1x1 stride-2 shortcut conv + BN of the stage's first block, as hi + lo fp16 K-slabs
+            sp = prefix.rsplit(".", 1)[0] + ".shortcut"
+            ws, bs = fold_bn(sd[f"{sp}.0.weight"], sd, f"{sp}.1")
+            assert ws.shape[1] == xc
+            add(SEC_X_W_F16 + li, extra_operand_hilo(ws.reshape(cout, xc), gx), np.float16)
+            add(SEC_SC_W_F32 + li // 4, ws.reshape(cout, xc).T, np.float32)
+            add(SEC_SC_BIAS + li // 4, bs, np.float32)
+            fused = (bf.astype(np.float32) + bs.astype(np.float32)).astype(np.float32)
+        elif kind == 3:  # identity residual of the second block
+            add(SEC_X_W_F16 + li, extra_operand(np.eye(cout, dtype=np.float32), gx), np.float16)
+        add(SEC_BIAS_FUSED + li, fused, np.float32)
+        add(SEC_BIAS_MMA + li, bias_operand(fused), np.float16)
+    for i in range(4):
+        add(SEC_FC_W + i, sd[f"branch{i + 1}.weight"], np.float32)
+        add(SEC_FC_B + i, sd[f"branch{i + 1}.bias"], np.float32)
+    return secs
+
+
+def pack(sd: dict, arch: int = ARCH_CTU128) -> bytes:
+    secs = build_sections(sd) if arch == ARCH_CTU128 else build_cu_sections(sd, arch)
     table_bytes = 24 * len(secs)
     off = (32 + table_bytes + 255) // 256 * 256
     table, blobs = [], []
@@ -258,7 +325,7 @@ def pack(sd: dict) -> bytes:
         pad = (-len(raw)) % 256
         blobs.append(raw + b"\0" * pad)
         off += len(raw) + pad
-    head = struct.pack("<IIIIQQ", MAGIC, VERSION, ARCH_CTU128, len(secs), off, 0)
+    head = struct.pack("<IIIIQQ", MAGIC, VERSION, arch, len(secs), off, 0)
     body = head + b"".join(table)
     body += b"\0" * ((-len(body)) % 256)
     out = body + b"".join(blobs)
@@ -273,12 +340,20 @@ def write_blob(sd: dict, path: str) -> int:
     return len(data)
 
 
-def read_sections(path: str) -> dict:
+def write_cu_blob(sd: dict, size: int, path: str) -> int:
+    assert size in (64, 32, 16)
+    data = pack(sd, size)
+    with open(path, "wb") as f:
+        f.write(data)
+    return len(data)
+
+
+def read_sections(path: str, arch: int = ARCH_CTU128) -> dict:
     """Parse an MLTW blob back into {section id: numpy array} (round-trip checks / tooling)."""
     raw = open(path, "rb").read()
-    magic, ver, arch, nsec, total, _ = struct.unpack_from("<IIIIQQ", raw, 0)
-    if magic != MAGIC or ver != VERSION or arch != ARCH_CTU128 or total != len(raw):
-        raise ValueError("not an MLTW v2 blob for the 128x128 CTU model")
+    magic, ver, barch, nsec, total, _ = struct.unpack_from("<IIIIQQ", raw, 0)
+    if magic != MAGIC or ver != VERSION or barch != arch or total != len(raw):
+        raise ValueError(f"not an MLTW v2 blob for arch {arch}")
     out = {}
     for i in range(nsec):
         sid, dt, off, nb = struct.unpack_from("<IIQQ", raw, 32 + 24 * i)
@@ -288,13 +363,16 @@ def read_sections(path: str) -> dict:
 
 def main(argv=None):
     argv = list(sys.argv[1:] if argv is None else argv)
-    if len(argv) != 2:
+    size = 0
+    if len(argv) >= 2 and argv[0] == "--cu":
+        size, argv = int(argv[1]), argv[2:]
+    if len(argv) != 2 or size not in (0, 64, 32, 16):
         print(__doc__)
         return 2
     import torch
 
     sd = torch.load(argv[0], map_location="cpu")
-    n = write_blob(sd, argv[1])
+    n = write_cu_blob(sd, size, argv[1]) if size else write_blob(sd, argv[1])
     print(f"wrote {argv[1]}: {n} bytes")
     return 0
 

@@ -1,0 +1,178 @@
+"""GPU parity tests of the smaller-CU models (64 / 32 / 16 px) -- run on the B200 box.
+
+Everything goes through the C ABI of libmltcnn.so (include/mltcnn_cu.h via fastintercu_vvc_b200.capi).  The checker is
+the CPU oracle (oracle/ref_arch.MltCuNet, oracle/mltcnn_oracle.c) and the golden vectors produced by the reference's own
+mlt_cu_or_pq_arch.py (tests/golden/cu_logits_seed10.npz, tools/gen_golden_cu.py).
+
+Bars: same as the CTU model -- probabilities max |diff| <= 1e-3 vs fp32, decisions equal except within a tie margin,
+every entry point bit-identical per CU, results independent of batch size and position.
+"""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from oracle import ref_arch
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+PROB_TOL = 1e-3
+LEVELS = ((0, 2), (2, 5), (5, 9), (9, 15))
+
+
+def softmax_levels(lg):
+    out = np.empty_like(lg)
+    for a, b in LEVELS:
+        e = np.exp(lg[:, a:b] - lg[:, a:b].max(1, keepdims=True))
+        out[:, a:b] = e / e.sum(1, keepdims=True)
+    return out
+
+
+@pytest.fixture(scope="module", params=ref_arch.CU_SIZES)
+def ctx(request):
+    from fastintercu_vvc_b200 import MltCuPredictor, write_cu_blob
+
+    size = request.param
+    sd = ref_arch.make_cu_state_dict(10, size)
+    with tempfile.NamedTemporaryFile(suffix=".mltw", delete=False) as f:
+        path = f.name
+    write_cu_blob(sd, size, path)
+    p = MltCuPredictor(path, size, device=0, max_batch=300)
+    os.unlink(path)
+    yield size, sd, p
+    p.close()
+
+
+def test_cu_every_layer_matches_the_oracle(ctx):
+    """Layer by layer against the fp32 torch restatement: localises any tile / layout / packing error."""
+    size, sd, p = ctx
+    n = 45  # ragged against every images-per-tile count (1, 2, 5, 6, 16, 21, 42, 64)
+    orgpred, pocqp = ref_arch.synth_cus(n, size, 10)
+    res = p.predict_batch_dense(orgpred, pocqp)
+    want = ref_arch.cu_activations(ref_arch.build_cu_model(sd), ref_arch.stage_numpy(orgpred))
+    report, bad = [], 0
+    for layer in range(21):
+        got = p.debug_activation(layer, n)
+        w = want[layer]
+        assert got.shape == w.shape, (layer, got.shape, w.shape)
+        err = float(np.abs(got - w).max())
+        scale = float(np.abs(w).max())
+        ok = err <= 1.5e-2 * max(scale, 1e-3) + 1e-3
+        bad += not ok
+        report.append(f"act {layer:2d} {tuple(w.shape[1:])}: max|d|={err:.3e} scale={scale:.3e} {'ok' if ok else 'BAD'}")
+    print("\n".join(report))
+    assert bad == 0, "\n" + "\n".join(report)
+    assert np.isfinite(res["logits"]).all()
+
+
+def test_cu_logits_probs_and_decisions(ctx):
+    size, sd, p = ctx
+    n = 256
+    orgpred, pocqp = ref_arch.synth_cus(n, size, 10)
+    res = p.predict_batch_dense(orgpred, pocqp)
+    lg = ref_arch.forward_cu_logits(ref_arch.build_cu_model(sd), ref_arch.stage_numpy(orgpred), pocqp)
+    pr = softmax_levels(lg)
+    dp = float(np.abs(res["probs"] - pr).max())
+    dl = float(np.abs(res["logits"] - lg).max())
+    print(f"size {size}: max|dprob|={dp:.2e} max|dlogit|={dl:.2e}")
+    assert dp <= PROB_TOL, dp
+    agree = []
+    for lvl, (a, b) in enumerate(LEVELS):
+        ref_arg = lg[:, a:b].argmax(1)
+        srt = np.sort(lg[:, a:b], 1)
+        margin = srt[:, -1] - srt[:, -2]
+        same = res["split"][:, lvl] == ref_arg
+        assert np.all(same | (margin < 4e-3)), (size, lvl, int((~same).sum()))
+        agree.append(float(same.mean()))
+    print(f"size {size}: decision agreement per level {agree}")
+    assert min(agree) >= 0.99
+    # the GPU's own softmax / argmax are consistent with its logits
+    assert np.abs(softmax_levels(res["logits"]) - res["probs"]).max() < 1e-6
+    for lvl, (a, b) in enumerate(LEVELS):
+        assert np.array_equal(res["split"][:, lvl], res["logits"][:, a:b].argmax(1))
+
+
+def test_cu_matches_reference_golden_vectors(ctx):
+    size, sd, p = ctx
+    gold = np.load(os.path.join(GOLD, "cu_logits_seed10.npz"))
+    n = int(gold["n"])
+    orgpred, pocqp = ref_arch.synth_cus(n, size, int(gold["seed"]))
+    res = p.predict_batch_dense(orgpred, pocqp)
+    assert np.abs(softmax_levels(gold[f"logits_{size}"]) - res["probs"]).max() <= PROB_TOL
+    srt = np.sort(gold[f"logits_{size}"][:, :2], 1)
+    same = res["split"][:, 0] == gold[f"split_{size}"]  # what the hook uses below 128: elements()[0] (EncCu.cpp:916-919)
+    assert np.all(same | (srt[:, 1] - srt[:, 0] < 4e-3))
+
+
+def test_cu_results_do_not_depend_on_batch_or_entry_point(ctx):
+    """Bit-identical per CU: alone, in ragged batches, shifted inside a batch, through descriptors with strided views,
+    and through the device-resident entry point."""
+    import torch
+
+    size, sd, p = ctx
+    n = 131
+    orgpred, pocqp = ref_arch.synth_cus(n, size, 23)
+    full = p.predict_batch_dense(orgpred, pocqp)
+    for k in (1, 2, 5, 7, 17, 43, 65, 130):
+        part = p.predict_batch_dense(np.ascontiguousarray(orgpred[:k]), pocqp[:k])
+        assert part.tobytes() == full[:k].tobytes(), k
+    shifted = p.predict_batch_dense(np.ascontiguousarray(orgpred[3:90]), pocqp[3:90])
+    assert shifted.tobytes() == full[3:90].tobytes()
+    one = p.predict(orgpred[77, 0], orgpred[77, 1], pocqp[77, 0], pocqp[77, 1])
+    assert one.tobytes() == full[77].tobytes()
+    # strided views inside a larger "picture" buffer (what VTM's AreaBuf hands out)
+    pic_o = np.zeros((size + 6, 3 * size + 10), np.int16)
+    pic_p = np.zeros_like(pic_o)
+    cus = []
+    for j in range(3):
+        pic_o[5 : 5 + size, 7 + j * size : 7 + (j + 1) * size] = orgpred[j, 0]
+        pic_p[5 : 5 + size, 7 + j * size : 7 + (j + 1) * size] = orgpred[j, 1]
+        cus.append((pic_o[5 : 5 + size, 7 + j * size : 7 + (j + 1) * size], pic_p[5 : 5 + size, 7 + j * size : 7 + (j + 1) * size],
+                    pocqp[j, 0], pocqp[j, 1]))
+    assert p.predict_batch(cus).tobytes() == full[:3].tobytes()
+    # device-resident entry point on a torch stream
+    from fastintercu_vvc_b200.capi import CU_RESULT_DTYPE
+
+    d_in = torch.from_numpy(orgpred).cuda()
+    d_pq = torch.from_numpy(pocqp).cuda()
+    d_out = torch.zeros(n * CU_RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream()
+    p.predict_batch_device(n, d_in.data_ptr(), d_pq.data_ptr(), d_out.data_ptr(), st.cuda_stream)
+    torch.cuda.synchronize()
+    dev = d_out.cpu().numpy().view(CU_RESULT_DTYPE)
+    assert dev.tobytes() == full.tobytes()
+    # deterministic run to run
+    assert p.predict_batch_dense(orgpred, pocqp).tobytes() == full.tobytes()
+
+
+def test_cu_staging_edge_cases(ctx):
+    """Negative Pel (cast to uint16 > 1023 -> clamp), org < pred, extremes: the integer staging must follow EncCu.cpp:810-867."""
+    size, sd, p = ctx
+    rng = np.random.RandomState(5)
+    orgpred = rng.randint(-200, 1300, (16, 2, size, size)).astype(np.int16)
+    orgpred[0] = 0
+    orgpred[1, 0] = 1023
+    orgpred[1, 1] = 0
+    orgpred[2, 0] = 0
+    orgpred[2, 1] = 1023
+    pocqp = np.stack([rng.randint(0, 33, 16), rng.randint(20, 50, 16)], 1).astype(np.int32)
+    res = p.predict_batch_dense(orgpred, pocqp)
+    got0 = p.debug_activation(0, 16)  # conv1 of the staged input
+    want = ref_arch.cu_activations(ref_arch.build_cu_model(sd), ref_arch.stage_numpy(orgpred))[0]
+    assert np.abs(got0 - want).max() <= 2e-3 * max(1.0, float(np.abs(want).max()))
+    lg = ref_arch.forward_cu_logits(ref_arch.build_cu_model(sd), ref_arch.stage_numpy(orgpred), pocqp)
+    assert np.abs(res["probs"] - softmax_levels(lg)).max() <= 2 * PROB_TOL  # saturated inputs: large activations
+
+
+def test_cu_error_paths(ctx):
+    from fastintercu_vvc_b200.capi import MltError
+
+    size, sd, p = ctx
+    orgpred, pocqp = ref_arch.synth_cus(4, size, 1)
+    assert len(p.predict_batch_dense(orgpred[:0], pocqp[:0])) == 0
+    big = np.zeros((p.max_batch + 1, 2, size, size), np.int16)
+    with pytest.raises(MltError) as e:
+        p.predict_batch_dense(big, np.zeros((p.max_batch + 1, 2), np.int32))
+    assert e.value.rc == -7

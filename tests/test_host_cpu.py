@@ -101,12 +101,12 @@ def test_blob_roundtrip_and_operand_layout(sd):
 def test_library_exports_every_declared_symbol():
     from fastintercu_vvc_b200 import capi
 
-    hdr = open(os.path.join(ROOT, "include", "mltcnn.h")).read()
+    hdr = open(os.path.join(ROOT, "include", "mltcnn.h")).read() + open(os.path.join(ROOT, "include", "mltcnn_cu.h")).read()
     declared = set(re.findall(r"MLT_API[^;(]*?\b(mlt_[a-z_]+)\s*\(", hdr))
-    assert len(declared) >= 18, declared
+    assert len(declared) >= 18 + 11, declared
     lib = capi.load_library()
     for name in declared:
-        assert hasattr(lib, name), f"{name} declared in mltcnn.h but not exported"
+        assert hasattr(lib, name), f"{name} declared in include/*.h but not exported"
     assert declared == set(capi.EXPORTS), declared ^ set(capi.EXPORTS)
     out = subprocess.run(["nm", "-D", "--defined-only", capi.lib_path()], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (mlt_[a-z_]+)", out))
@@ -128,6 +128,60 @@ def test_no_cpu_fallback_without_gpu():
     with pytest.raises(MltError) as e:
         MltPredictor("/nonexistent.mltw")
     assert e.value.rc == -6  # MLT_E_NODEVICE: fails loudly, never computes on the CPU
+
+
+def test_no_cpu_fallback_for_the_cu_models_without_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from fastintercu_vvc_b200 import MltCuPredictor, MltError
+
+    with pytest.raises(MltError) as e:
+        MltCuPredictor("/nonexistent.mltw", 64)
+    assert e.value.rc == -6
+    with pytest.raises(MltError) as e:
+        MltCuPredictor("/nonexistent.mltw", 48)  # only 64 / 32 / 16 exist (EncCu.cpp:754)
+    assert e.value.rc == -1
+
+
+def test_cu_packer_layout_agrees_with_the_kernel_tables(tmp_path):
+    """The per-size operand layouts (weight-slab channel groups) the packer writes are the ones the tcgen05 kernels
+    were instantiated with (csrc/cu_net.cuh), read back through mlt_cu_layer_info -- no GPU needed."""
+    from fastintercu_vvc_b200 import capi, synth
+
+    lib = capi.load_library()
+    planes = (32, 64, 96, 128, 256)
+    for size in (64, 32, 16):
+        table = pw.cu_conv_table(size)
+        assert len(table) == 20
+        flops = 2 * size * size * 32 * 18
+        for li, (prefix, cin, cout, stride, hout, g, xc, gx, kind) in enumerate(table):
+            info = np.zeros(10, np.int32)
+            assert lib.mlt_cu_layer_info(size, li, info.ctypes.data) == 0
+            assert (cin, cout, stride, hout, xc) == tuple(info[:5]), (size, li)
+            assert (g, gx) == tuple(info[8:10]), (size, li)
+            assert cout == planes[li // 4] and hout == max(size >> (li // 4 + 1), 1)
+            assert cin % g == 0 and (xc == 0 or xc % gx == 0)
+            nb, flat = int(info[6]), int(info[7])
+            assert flat == (hout <= 4)
+            if flat:  # NB images x HOUT rows x (HOUT + halo) positions fit the 128 accumulator rows
+                assert nb * hout * (hout + (2 if stride == 1 else 1)) <= 128
+        assert lib.mlt_cu_layer_info(size, 20, np.zeros(10, np.int32).ctypes.data) == -1
+        path = str(tmp_path / f"cu{size}.mltw")
+        sd = synth.make_cu_state_dict(10, size)
+        pw.write_cu_blob(sd, size, path)
+        secs = pw.read_sections(path, size)
+        with pytest.raises(ValueError):
+            pw.read_sections(path)  # not a CTU blob
+        # spot-check one packed element of a streamed 96-channel layer: conv 9 = layer2.0.conv2 (96 -> 96)
+        prefix, cin, cout, stride, hout, g, xc, gx, kind = table[9]
+        wf, _ = pw.fold_bn(sd[f"{prefix}.weight"], sd, prefix.replace("conv", "bn"))
+        packed = secs[pw.SEC_W_F16 + 9].reshape(cin // g, 9, g // 8, cout, 8)
+        co, ci, kh, kw = 77, 50, 2, 1
+        assert abs(float(packed[ci // g, kh * 3 + kw, (ci % g) // 8, co, ci % 8]) - float(wf[co, ci, kh, kw])) <= 2e-3 * abs(float(wf[co, ci, kh, kw])) + 1e-6
+        assert secs[pw.SEC_X_W_F16 + 9].size == 2 * xc * cout  # shortcut weights as hi + lo
+    assert lib.mlt_cu_layer_info(48, 0, np.zeros(10, np.int32).ctypes.data) == -1
 
 
 def test_product_code_never_touches_the_oracle():
