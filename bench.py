@@ -183,6 +183,87 @@ def run_reference_arm(args):
     return 0
 
 
+# ----------------------------------------------------------------------------------------------- smaller-CU models
+
+
+def cu_flops(size: int) -> int:
+    """Algorithmic FLOPs (2 * MAC) of one `size`-px CU through GapBigMltCuORPQ (mlt_cu_or_pq_arch.py:59-130)."""
+    from fastintercu_vvc_b200.pack_weights import cu_conv_table
+
+    f = 2 * size * size * 32 * 18
+    for _, cin, cout, _, hout, _, xc, _, kind in cu_conv_table(size):
+        f += 2 * hout * hout * cout * cin * 9
+        if kind == 1:
+            f += 2 * hout * hout * cout * xc  # 1x1 stride-2 shortcut conv
+    return f + 2 * (66 * 2 + 98 * 3 + 130 * 4 + 258 * 6)
+
+
+def synth_cu_batch(n: int, size: int, seed: int):
+    per = (128 // size) ** 2
+    ctus, pq = synth_frames((n + per - 1) // per, seed)
+    k = 128 // size
+    cus = ctus.reshape(-1, 2, k, size, k, size).transpose(0, 2, 4, 1, 3, 5).reshape(-1, 2, size, size)[:n]
+    return np.ascontiguousarray(cus), np.ascontiguousarray(np.repeat(pq, per, 0)[:n])
+
+
+def bench_cu_models(local: int, frames: int, steps: int, warm: int):
+    """Device-resident and host-buffer throughput of the 64 / 32 / 16-px CU models on all
+    same-size CUs of `frames` 1080p frames per step.  Secondary numbers: the headline metric stays the CTU model."""
+    import torch
+
+    import fastintercu_vvc_b200 as pkg
+    from fastintercu_vvc_b200.capi import CU_RESULT_DTYPE
+    from fastintercu_vvc_b200.synth import make_cu_state_dict
+
+    out = {}
+    stream = torch.cuda.current_stream()
+    for size in (64, 32, 16):
+        n = frames * CTUS_PER_FRAME * (128 // size) ** 2
+        blob = tempfile.NamedTemporaryFile(suffix=".mltw", delete=False).name
+        pkg.write_cu_blob(make_cu_state_dict(10, size), size, blob)
+        pred = pkg.MltCuPredictor(blob, size, device=local, max_batch=n)
+        os.unlink(blob)
+        cus, pq = synth_cu_batch(n, size, 2000 + size)
+        h_in, h_pq = torch.from_numpy(cus).pin_memory(), torch.from_numpy(pq).pin_memory()
+        d_in, d_pq = h_in.cuda(), h_pq.cuda()
+        d_out = torch.zeros(n * CU_RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+        h_out = np.zeros(n, CU_RESULT_DTYPE)
+        for _ in range(warm):
+            pred.predict_batch_device(n, d_in.data_ptr(), d_pq.data_ptr(), d_out.data_ptr(), stream.cuda_stream)
+        torch.cuda.synchronize()
+        l0 = pred.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            pred.predict_batch_device(n, d_in.data_ptr(), d_pq.data_ptr(), d_out.data_ptr(), stream.cuda_stream)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        launches = pred.launch_count - l0
+        hin, hpq = h_in.numpy(), h_pq.numpy()
+        pred.predict_batch_dense(hin, hpq, h_out)
+        t0 = time.perf_counter()
+        for _ in range(max(steps // 2, 1)):
+            pred.predict_batch_dense(hin, hpq, h_out)
+        e2e_s = (time.perf_counter() - t0) / max(steps // 2, 1)
+        o1, p1 = np.ascontiguousarray(hin[0, 0]), np.ascontiguousarray(hin[0, 1])
+        for _ in range(10):
+            pred.predict(o1, p1, int(hpq[0, 0]), int(hpq[0, 1]))
+        t0 = time.perf_counter()
+        for _ in range(100):
+            pred.predict(o1, p1, int(hpq[0, 0]), int(hpq[0, 1]))
+        one_us = (time.perf_counter() - t0) / 100 * 1e6
+        fl = cu_flops(size)
+        out[str(size)] = {"cus_per_step": n, "ms_per_step": ms, "cus_per_s": n / (ms * 1e-3), "e2e_cus_per_s": n / e2e_s,
+                          "flop_per_cu": fl, "tflops": n * fl / (ms * 1e-3) / 1e12, "gpu_launches_per_step": launches // steps,
+                          "cu_latency_us": one_us, "h2d_bytes_per_step": int(n * (4 * size * size + 8)),
+                          "d2h_bytes_per_step": int(n * CU_RESULT_DTYPE.itemsize)}
+        pred.close()
+        del d_in, d_pq, d_out
+        torch.cuda.empty_cache()
+    return out
+
+
 # ----------------------------------------------------------------------------------------------- product arm
 
 
@@ -195,6 +276,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU baseline work (rank 0, N=1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cu-frames", type=int, default=8, help="1080p frames whose 64 / 32 / 16-px CUs form one step of the CU-model lines (0 = skip)")
+    ap.add_argument("--cu-only", action="store_true", help="only the smaller-CU models (tuning runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -217,6 +300,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     steps, warm = args.steps, max(args.warmup, 3)
     n = args.frames * CTUS_PER_FRAME
+    if args.cu_only:
+        print(json.dumps({"metric": "mlt_cnn_cu_split_cus_per_s", "cu_models": bench_cu_models(local, args.cu_frames, max(steps // 5, 3), warm)}))
+        return 0
 
     # seeded random weights of the exact architecture (the trained .pt is not distributed with the reference)
     from fastintercu_vvc_b200.synth import make_state_dict
@@ -348,6 +434,11 @@ def main():
             "ctu_latency_us": ctu_us,
             "tflops_whole_net": value / world * FLOP_PER_CTU / 1e12,
         }
+        if args.cu_frames > 0 and world == 1:
+            pred.close()
+            line["cu_models"] = bench_cu_models(local, args.cu_frames, max(steps // 5, 3), warm)
+            line["cu_models"]["note"] = (f"secondary (SURVEY.md section 8f rank 1): 64 / 32 / 16-px GapBigMltCuORPQ on all same-size CUs of "
+                                         f"{args.cu_frames} 1080p frames per step, device-resident and host-buffer (e2e) CUs/s")
         if not args.no_cpu_baseline and world == 1:
             r, cores, cn, cdt = cpu_reference_rate(args.cpu_budget)
             line["cpu_baseline"] = {"value": r, "unit": "CTU/s", "cores": cores, "kind": "port",

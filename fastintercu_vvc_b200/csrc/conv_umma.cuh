@@ -92,7 +92,15 @@ struct ConvCfg {
     static constexpr int BIAS_BYTES = COUT * 32;    // bias as a K=16 B operand
     static constexpr int ONES_BYTES = 2 * 128 * 16; // matching A operand: k=0,1 -> 1.0, rest 0
     static constexpr int A_BUDGET = 231000 - B_BYTES - BIAS_BYTES - ONES_BYTES;
-    static constexpr int NAS = (A_BUDGET / A_STAGE_BYTES) > 8 ? 8 : (A_BUDGET / A_STAGE_BYTES); // A ring depth
+    static constexpr int NAS_RAW = (A_BUDGET / A_STAGE_BYTES) > 8 ? 8 : (A_BUDGET / A_STAGE_BYTES);
+    // A ring depth.  Resident-weight layers run TWO MMA-issuer warps on alternate tiles.  Each issuer owns HALF of the ring
+    // (stages [iss * NAS/2, (iss + 1) * NAS/2)), so every full-barrier has exactly one consumer: with one shared ring two
+    // issuers wait on the same barriers whenever the depth is not a multiple of a tile pair's stages, and a parity wait
+    // cannot tell fill k from fill k + 2 -- the (32 -> 32, stride 2) layer with its 5-stage ring faulted after ~120 tiles
+    // per CTA once TMA fills landed out of order (profiles/r01/README.md).
+    static constexpr int SPT_ = 1 + NXS; // A stages per tile
+    static constexpr int NAS = !RESIDENT ? NAS_RAW : NAS_RAW / 2 * 2;
+    static constexpr int NAS_HALF = NAS / 2;
     static constexpr int NACC = (COUT <= 128) ? 4 : 2; // TMEM accumulator stages (NACC * ACC_COLS <= 512 columns)
     static constexpr int ACC_COLS = (COUT == 96) ? 128 : COUT; // accumulator pitch in TMEM columns (power of two)
     // bias: for the smem-operand-bound 32/64-channel layers it is added in the epilogue from registers (an extra MMA
@@ -296,15 +304,15 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
             // two issuer warps take alternate tiles.
             static_assert(!C::RESIDENT || (C::NCG == 1 && C::NXS <= 1 && C::TP == 1 && C::BIAS_REG), "resident-weight path assumptions");
             constexpr int SPT = 1 + C::NXS; // stages per tile
-            static_assert(!C::RESIDENT || C::NAS >= 2 * SPT + 1, "A ring must hold the two tiles in flight plus a prefetched stage");
+            static_assert(!C::RESIDENT || (C::NAS_HALF >= SPT && C::NAS % 2 == 0), "each issuer's half ring must hold one tile");
             mbar_wait(&fullB[0], 0);
             auto wait_tile = [&](uint32_t j) {
                 if (p.dbg & 8) return; // debug: free-running MMA stream, no handshakes
                 mbar_wait(&accEmpty[j % C::NACC], ((j / C::NACC) & 1) ^ 1);
 #pragma unroll
                 for (int sidx = 0; sidx < SPT; sidx++) {
-                    const uint32_t it = j * SPT + sidx;
-                    mbar_wait(&fullA[it % C::NAS], (it / C::NAS) & 1);
+                    const uint32_t u = (j >> 1) * SPT + sidx; // this issuer's stage counter
+                    mbar_wait(&fullA[(j & 1) * C::NAS_HALF + u % C::NAS_HALF], (u / C::NAS_HALF) & 1);
                 }
             };
             // two issuer warps: W_MMA takes the even local tiles, W_MMA2 the odd ones (different accumulators and stages;
@@ -316,7 +324,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
                 if (p.trace != nullptr && blockIdx.x == 0 && j < 1024 && lane == 0) p.trace[j] = clock64();
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (j % C::NACC) * C::ACC_COLS;
-                const uint32_t st0 = (j * SPT) % C::NAS;
+                const uint32_t st0 = iss * C::NAS_HALF + ((j >> 1) * SPT) % C::NAS_HALF;
                 const uint32_t a_lo0 = umma_desc_lo(sA + st0 * C::A_STAGE_BYTES, C::A_LBO);
                 auto issue_taps = [&](int t0, int t1) {
 #pragma unroll
@@ -333,7 +341,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
                     issue_taps(0, 9);
                     if (!(p.dbg & 16)) umma_commit(&emptyA[st0]);
                     if constexpr (C::XC > 0) {
-                        const uint32_t st1 = (j * SPT + 1) % C::NAS;
+                        const uint32_t st1 = iss * C::NAS_HALF + ((j >> 1) * SPT + 1) % C::NAS_HALF;
                         const uint32_t x_lo0 = umma_desc_lo(sA + st1 * C::A_STAGE_BYTES, C::X_LBO);
 #pragma unroll
                         for (int part = 0; part < C::XP; part++) {
@@ -541,8 +549,14 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
                         oy0 = (rem / (C::HOUT / 8)) * 16;
                         ox0 = (rem % (C::HOUT / 8)) * 8;
                     }
-                    const uint32_t st = a_it % C::NAS;
-                    mbar_wait(&emptyA[st], ((a_it / C::NAS) & 1) ^ 1);
+                    // resident-weight layers: tile t of this CTA belongs to issuer t & 1, which owns half of the ring
+                    uint32_t st = a_it % C::NAS, fill = a_it / C::NAS;
+                    if constexpr (C::RESIDENT) {
+                        const uint32_t t = a_it / C::SPT_, u = (t >> 1) * C::SPT_ + a_it % C::SPT_;
+                        st = (t & 1) * C::NAS_HALF + u % C::NAS_HALF;
+                        fill = u / C::NAS_HALF;
+                    }
+                    mbar_wait(&emptyA[st], (fill & 1) ^ 1);
                     if ((p.dbg & 1) && a_it >= (uint32_t)C::NAS) { // debug: stale smem, no TMA traffic
                         if (elect_one_sync()) mbar_arrive(&fullA[st]);
                     } else if (elect_one_sync()) {

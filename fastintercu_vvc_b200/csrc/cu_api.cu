@@ -129,10 +129,21 @@ int run_network(mlt_cu_ctx *c, int n, const int16_t *d_orgpred, const int32_t *d
     CU(cudaGetLastError());
     CU(launch_cu_conv1(c->size, c->d_cus, n, secp<__half>(c, SEC_CONV1_UMMA), c->act[0], c->cap, s));
     c->launches += 2;
+    static const int stop_after = getenv("MLT_CU_STOP_AFTER") ? atoi(getenv("MLT_CU_STOP_AFTER")) : -1; // debug: run conv1 + this many convs, then synchronise
+    if (stop_after >= 0) {
+        const cudaError_t e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) return fail(c, MLT_E_CUDA, "conv1 of the %d-px network (n=%d): %s", c->size, n, cudaGetErrorString(e));
+    }
     for (int li = 0; li < CU_NCONV; li++) {
+        if (stop_after >= 0 && li >= stop_after) { c->last_n = n; return MLT_OK; }
         ConvParams &p = c->conv_p[li];
         p.nimg = n;
-        CU(launch_cu_conv(c->size, li, p, c->num_sms, s));
+        const cudaError_t e = launch_cu_conv(c->size, li, p, c->num_sms, s);
+        if (e != cudaSuccess) return fail(c, MLT_E_CUDA, "conv %d of the %d-px network (n=%d): %s", li, c->size, n, cudaGetErrorString(e));
+        if (stop_after >= 0) {
+            const cudaError_t e2 = cudaStreamSynchronize(s);
+            if (e2 != cudaSuccess) return fail(c, MLT_E_CUDA, "conv %d of the %d-px network (n=%d), after sync: %s", li, c->size, n, cudaGetErrorString(e2));
+        }
         c->launches++;
     }
     CuHeadParams hp;
@@ -248,6 +259,7 @@ int mlt_cu_create(mlt_cu_ctx **out, const char *weights_path, int cuda_device, i
             p.out = c->act[li + 1];
             p.relu = 1;
             p.reverse = getenv("MLT_NO_REVERSE") ? 0 : (li & 1);
+            p.dbg = getenv("MLT_DEBUG_FLAGS") ? atoi(getenv("MLT_DEBUG_FLAGS")) : 0; // timing / bisect experiments only (results invalid)
         }
         const size_t per = (size_t)2 * cu_size * cu_size;
         CU(cudaMalloc(&c->d_in, (size_t)max_batch * per * sizeof(int16_t)));
