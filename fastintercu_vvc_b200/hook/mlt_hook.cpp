@@ -6,6 +6,7 @@
 #include <cstring>
 
 #include "../../include/mltcnn.h"
+#include "../../include/mltcnn_cu.h"
 
 namespace mlt_hook {
 
@@ -14,6 +15,25 @@ bool useCNN(int chType, bool isIntraSlice, int cuw, int cuh, int cux, int cuy, i
     if (chType != 0 || isIntraSlice) return false;          // luma tree of a non-I slice
     if (cuw != MLT_CTU_SIZE || cuh != MLT_CTU_SIZE) return false; // only the 128x128 model is wired (EncCu.cpp:754)
     return cux + cuw <= picWidth && cuy + cuh <= picHeight;  // CU entirely inside the picture
+}
+
+bool useCNN(int chType, bool isIntraSlice, int cuw, int cuh, int cux, int cuy, int picWidth, int picHeight, unsigned sizeMask)
+{
+    if (chType != 0 || isIntraSlice || cuw != cuh) return false;
+    const bool sizeOk = cuw == MLT_CTU_SIZE || (cuw == 64 && (sizeMask & 1u)) || (cuw == 32 && (sizeMask & 2u)) || (cuw == 16 && (sizeMask & 4u));
+    return sizeOk && cux + cuw <= picWidth && cuy + cuh <= picHeight;
+}
+
+unsigned cuSizeMaskFromEnv()
+{
+    const char *s = std::getenv("MLT_CU_SIZES");
+    unsigned m = 0;
+    if (s) {
+        if (std::strstr(s, "64")) m |= 1u;
+        if (std::strstr(s, "32")) m |= 2u;
+        if (std::strstr(s, "16")) m |= 4u;
+    }
+    return m;
 }
 
 SplitPredictor &SplitPredictor::instance()
@@ -25,7 +45,7 @@ SplitPredictor &SplitPredictor::instance()
 SplitPredictor::SplitPredictor()
 {
     const char *dis = std::getenv("MLT_DISABLE");
-    if (dis && std::strcmp(dis, "0") != 0) return; // anchor run: hook off, stock RDO
+    if (dis && std::strcmp(dis, "0") != 0) { m_disabled = true; return; } // anchor run: hook off, stock RDO
     const char *weights = std::getenv("MLT_WEIGHTS");
     const char *dev = std::getenv("MLT_DEVICE");
     if (!weights) {
@@ -44,6 +64,33 @@ SplitPredictor::SplitPredictor()
 SplitPredictor::~SplitPredictor()
 {
     if (m_ctx) mlt_destroy(m_ctx);
+    for (mlt_cu_ctx *c : m_cu)
+        if (c) mlt_cu_destroy(c);
+}
+
+int SplitPredictor::predictCu(int cuw, const int16_t *org, int orgStride, const int16_t *pred, int predStride, int poc, int qp)
+{
+    const int idx = cuw == 64 ? 0 : (cuw == 32 ? 1 : (cuw == 16 ? 2 : -1));
+    if (idx < 0 || m_disabled) return -1;
+    if (!m_cuTried[idx]) { // the reference re-loads MLTORPQ_splitMode_<cuw>.pt on every call (EncCu.cpp:894-900); here: once
+        m_cuTried[idx] = true;
+        char name[32];
+        std::snprintf(name, sizeof name, "MLT_WEIGHTS_%d", cuw);
+        const char *weights = std::getenv(name), *dev = std::getenv("MLT_DEVICE");
+        const int rc = weights ? mlt_cu_create(&m_cu[idx], weights, dev ? std::atoi(dev) : 0, cuw, 1024) : MLT_E_IO;
+        if (rc != MLT_OK) {
+            std::fprintf(stderr, "error loading the model\n");
+            std::fprintf(stderr, "mlt_hook: %s -> %d (%s)\n", name, rc, mlt_strerror(rc));
+            m_cu[idx] = nullptr;
+        }
+    }
+    if (!m_cu[idx]) return -1;
+    mlt_cu_result r;
+    if (mlt_cu_predict(m_cu[idx], org, orgStride, pred, predStride, poc, qp, &r) != MLT_OK) {
+        std::fprintf(stderr, "error\n"); // EncCu.cpp:925
+        return -1;
+    }
+    return r.split[0];
 }
 
 int SplitPredictor::predict(const int16_t *org, int orgStride, const int16_t *pred, int predStride, int poc, int qp)

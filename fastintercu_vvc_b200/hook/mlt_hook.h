@@ -15,11 +15,16 @@
 #include <vector>
 
 struct mlt_ctx;
+struct mlt_cu_ctx;
 
 namespace mlt_hook {
 
 // EncCu.cpp:752-756 : luma tree, non-I slice, 128x128 CU, fully inside the picture.
 bool useCNN(int chType, bool isIntraSlice, int cuw, int cuh, int cux, int cuy, int picWidth, int picHeight);
+// The same gate with the square sizes the reference left commented out at EncCu.cpp:754 (64x64, 32x32, 16x16) switched
+// on through `sizeMask` (bit 0: 64, bit 1: 32, bit 2: 16; 0 == the reference as shipped).  Env MLT_CU_SIZES="64,32,16".
+bool useCNN(int chType, bool isIntraSlice, int cuw, int cuh, int cux, int cuy, int picWidth, int picHeight, unsigned sizeMask);
+unsigned cuSizeMaskFromEnv();
 
 class SplitPredictor {
 public:
@@ -37,6 +42,11 @@ public:
     bool beginPicture(const int16_t *orgLuma, int stride, int width, int height, int poc);
     int predictInPicture(int cux, int cuy, const int16_t *pred, int predStride, int qp);
 
+    // Smaller CUs (cuw = 64 / 32 / 16): the hook's `elements()[0]` branch (EncCu.cpp:916-919) == argmax of the FIRST head
+    // of the per-size model MLTORPQ_splitMode_<cuw> (EncCu.cpp:899); weights from env MLT_WEIGHTS_<cuw>, loaded once on
+    // first use.  -1 on failure or when that size has no weights.
+    int predictCu(int cuw, const int16_t *org, int orgStride, const int16_t *pred, int predStride, int poc, int qp);
+
     ~SplitPredictor();
     SplitPredictor(const SplitPredictor &) = delete;
     SplitPredictor &operator=(const SplitPredictor &) = delete;
@@ -44,6 +54,9 @@ public:
 private:
     SplitPredictor();
     mlt_ctx *m_ctx = nullptr;
+    mlt_cu_ctx *m_cu[3] = {nullptr, nullptr, nullptr}; // 64, 32, 16
+    bool m_cuTried[3] = {false, false, false};
+    bool m_disabled = false;
 };
 
 // ---- restatement of the consumer's semantics (EncModeCtrl.cpp:95-149), used by tests only ------------------

@@ -31,6 +31,20 @@ int main()
     assert(!useCNN(0, true, 128, 128, 0, 0, 416, 240));  // I slice
     assert(!useCNN(0, false, 64, 64, 0, 0, 416, 240));   // smaller CUs are gated off (EncCu.cpp:754)
     assert(!useCNN(0, false, 128, 64, 0, 0, 416, 240));
+    // the sizes the reference left commented out at EncCu.cpp:754, switched on through the mask
+    assert(!useCNN(0, false, 64, 64, 0, 0, 416, 240, 0u) && useCNN(0, false, 128, 128, 0, 0, 416, 240, 0u));
+    assert(useCNN(0, false, 64, 64, 64, 64, 416, 240, 1u) && !useCNN(0, false, 32, 32, 0, 0, 416, 240, 1u));
+    assert(useCNN(0, false, 32, 32, 384, 208, 416, 240, 2u) && !useCNN(0, false, 32, 32, 400, 208, 416, 240, 2u));
+    assert(useCNN(0, false, 16, 16, 400, 224, 416, 240, 7u) && !useCNN(0, false, 16, 8, 0, 0, 416, 240, 7u));
+    assert(!useCNN(0, false, 8, 8, 0, 0, 416, 240, 7u) && !useCNN(0, true, 64, 64, 0, 0, 416, 240, 7u));
+    {
+        int n64 = 0; // 1920x1080: 64-px CUs fully inside the picture = 30 x 16
+        for (int y = 0; y < 1080; y += 64)
+            for (int x = 0; x < 1920; x += 64) n64 += useCNN(0, false, 64, 64, x, y, 1920, 1080, 1u);
+        assert(n64 == 30 * 16);
+        setenv("MLT_CU_SIZES", "64,16", 1);
+        assert(cuSizeMaskFromEnv() == 5u);
+    }
 
     // ---- consumer semantics
     for (int pred = 1; pred <= 3; pred++) {
@@ -63,6 +77,9 @@ int main()
     std::vector<int16_t> blk(128 * 128, 512);
     const int r = p.predict(blk.data(), 128, blk.data(), 128, 1, 32);
     if (!p.enabled()) assert(r == -1);
+    setenv("MLT_WEIGHTS_64", "/nonexistent/cu64.mltw", 1);
+    assert(p.predictCu(64, blk.data(), 128, blk.data(), 128, 1, 32) == -1); // no weights / no GPU -> -1, full RDO
+    assert(p.predictCu(48, blk.data(), 128, blk.data(), 128, 1, 32) == -1);
     std::printf("test_hook: OK (predictor %s, predict -> %d)\n", p.enabled() ? "enabled" : "disabled", r);
     return 0;
 }
