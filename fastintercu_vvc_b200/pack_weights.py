@@ -361,6 +361,34 @@ def read_sections(path: str, arch: int = ARCH_CTU128) -> dict:
     return out
 
 
+def load_checkpoint(path: str) -> dict:
+    """Reads what the reference produces: a BasicSR checkpoint `.pth` whose state_dict sits
+    under 'params' with optional 'module.' prefixes (model2torchScript.py:23-32), a bare state_dict, or the traced
+    TorchScript `.pt` the hook loads (MLTORPQ_splitMode_<cuw>.pt, model2torchScript.py:46-48; EncCu.cpp:899)."""
+    import zipfile
+
+    import torch
+
+    is_script = False
+    if zipfile.is_zipfile(path):
+        with zipfile.ZipFile(path) as z:
+            is_script = any(n.endswith("constants.pkl") or "/code/" in n for n in z.namelist())
+    if is_script:
+        sd = torch.jit.load(path, map_location="cpu").state_dict()
+    else:
+        sd = torch.load(path, map_location="cpu")
+    sd = normalise_state_dict(sd)
+    return {k: v for k, v in sd.items() if not k.endswith("num_batches_tracked")}
+
+
+def export_state_dict(sd: dict, path: str) -> None:
+    """Writes a checkpoint in the reference's own container ({'params': state_dict}, mlt_base_model.py save format) so that
+    blobs can be round-tripped and seeded parameters handed to the reference's scripts."""
+    import torch
+
+    torch.save({"params": {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in normalise_state_dict(sd).items()}}, path)
+
+
 def main(argv=None):
     argv = list(sys.argv[1:] if argv is None else argv)
     size = 0
@@ -369,9 +397,7 @@ def main(argv=None):
     if len(argv) != 2 or size not in (0, 64, 32, 16):
         print(__doc__)
         return 2
-    import torch
-
-    sd = torch.load(argv[0], map_location="cpu")
+    sd = load_checkpoint(argv[0])
     n = write_cu_blob(sd, size, argv[1]) if size else write_blob(sd, argv[1])
     print(f"wrote {argv[1]}: {n} bytes")
     return 0

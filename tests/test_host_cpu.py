@@ -252,3 +252,40 @@ def test_two_rank_gloo_sharding(tmp_path):
         capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "GLOO_OK 2" in r.stdout
+
+
+# ------------------------------------------------------------------------------------------- weight tooling (section 8f rank 3)
+
+
+def test_packer_reads_the_reference_containers(tmp_path):
+    """`.pth` with 'params' + 'module.' prefixes (model2torchScript.py:23-32) and the traced TorchScript `.pt` the hook
+    loads (model2torchScript.py:46-48) pack to byte-identical blobs; the CLI takes both, for the CTU and the CU models."""
+    import torch
+
+    from fastintercu_vvc_b200 import synth
+    from oracle import ref_arch
+
+    for size in (128, 16):
+        sd = make_state_dict(10) if size == 128 else synth.make_cu_state_dict(10, size)
+        want = pw.pack(sd) if size == 128 else pw.pack(sd, size)
+        # BasicSR-style checkpoint with DataParallel prefixes
+        pth = str(tmp_path / f"net_{size}.pth")
+        torch.save({"params": {"module." + k: torch.from_numpy(v) for k, v in sd.items()}}, pth)
+        # TorchScript traced exactly like model2torchScript.py:37-48
+        net = ref_arch.build_model(sd) if size == 128 else ref_arch.build_cu_model(sd)
+        ex = (torch.cat((torch.rand(1, 1, 128, 128), torch.rand(1, 1, 128, 128)), 1), torch.rand(1), torch.rand(1))
+        pt = str(tmp_path / f"MLTORPQ_splitMode_{size}.pt")
+        torch.jit.trace(net, ex).save(pt)
+        for src in (pth, pt):
+            got = pw.load_checkpoint(src)
+            assert set(got) == set(sd)
+            assert all(np.array_equal(got[k], sd[k]) for k in sd)
+            out = str(tmp_path / "out.mltw")
+            argv = ([] if size == 128 else ["--cu", str(size)]) + [src, out]
+            assert pw.main(argv) == 0
+            assert open(out, "rb").read() == want
+        # export in the reference's container and back
+        rt = str(tmp_path / "rt.pth")
+        pw.export_state_dict(sd, rt)
+        assert all(np.array_equal(pw.load_checkpoint(rt)[k], sd[k]) for k in sd)
+    assert pw.main(["only-one-arg"]) == 2
