@@ -56,7 +56,7 @@ struct Section { const uint8_t *dev = nullptr; size_t bytes = 0; };
 struct mlt_ctx {
     int device = 0, max_batch = 0, engine = 0, num_sms = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
-    static constexpr int MAX_CHUNKS = 8;
+    static constexpr int MAX_CHUNKS = 16;
     cudaEvent_t ev_in[MAX_CHUNKS] = {}; // "chunk i of the input batch has landed in HBM"
     uint8_t *d_blob = nullptr;
     size_t blob_bytes = 0;
@@ -350,12 +350,27 @@ int run_host_batch_chunked(mlt_ctx *c, int n, const int16_t *src, const mlt_ctu_
     cudaStream_t s = c->stream;
     dense_descs(c, n, pocqp, descs);
     CU(cudaMemcpyAsync(c->d_ctus, c->h_ctus, (size_t)n * sizeof(CtuDev), cudaMemcpyHostToDevice, s));
-    const int nchunks = n >= 1024 ? (n / 512 < mlt_ctx::MAX_CHUNKS ? n / 512 : mlt_ctx::MAX_CHUNKS) : 1;
-    const int per = (n + nchunks - 1) / nchunks;
+    // Chunk schedule: only the FIRST chunk's H2D is exposed (every later copy hides behind the previous chunks' kernels,
+    // which are slower than PCIe), so the chunks start small (n / 16) and grow by 1.5x up to n / 4.
+    int sizes[mlt_ctx::MAX_CHUNKS], nchunks = 0;
+    if (n < 1024) sizes[nchunks++] = n;
+    else {
+        const int cap = n / 4 < c->set[1].cap ? n / 4 : c->set[1].cap;
+        for (int rem = n, cur = n / 16 > 120 ? n / 16 : 120; rem > 0;) {
+            int m = rem < cur ? rem : cur;
+            if (rem - m < cur / 2 && rem <= cap) m = rem; // no tiny tail chunk
+            if (nchunks == mlt_ctx::MAX_CHUNKS - 1) m = rem;
+            sizes[nchunks++] = m;
+            rem -= m;
+            cur = cur * 3 / 2 < cap ? cur * 3 / 2 : cap;
+        }
+    }
+    int per = 0;
+    for (int i = 0; i < nchunks; i++) per = sizes[i] > per ? sizes[i] : per;
     const bool two = nchunks > 1 && !c->profiling; // chunks alternate between the two activation sets / compute streams
     if (two) { CU(cudaEventRecord(c->ev_fork, s)); CU(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0)); } // descriptors uploaded
-    for (int i = 0, off = 0; off < n; i++, off += per) {
-        const int m = n - off < per ? n - off : per;
+    for (int i = 0, off = 0; off < n; off += sizes[i], i++) {
+        const int m = sizes[i];
         const int16_t *from = src ? src + (size_t)off * CTU_IN_ELEMS : c->h_in + (size_t)off * CTU_IN_ELEMS;
         if (!src)
             for (int k = off; k < off + m; k++)
