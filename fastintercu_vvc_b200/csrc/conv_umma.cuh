@@ -53,11 +53,16 @@ struct ConvCfg {
     static constexpr int G = (STRIDE == 2 && (COUT >= 256 || FLAT)) ? 16 : ((STRIDE == 2 || COUT >= 256 || FLAT) ? 32 : (CIN % 64 != 0 ? 32 : 64));
     static constexpr int NCG = CIN / G;
     static constexpr int CH = G / 8;               // 16-byte chunks per pixel per A stage
-    static constexpr int BLKW = FLAT ? (STRIDE == 1 ? HOUT + 2 : HOUT + 1) : ((STRIDE == 1) ? 10 : 9); // patch pixels per block (halo included)
+    // 1x1 maps: eight of the nine taps of a stride-1 3x3 conv only ever see zero padding, so the conv IS its centre tap --
+    // no halo, 128 images per tile, one weight slab per channel group instead of nine
+    static constexpr bool CENTER_ONLY = FLAT && HOUT == 1 && STRIDE == 1;
+    static constexpr int HALO = CENTER_ONLY ? 0 : 1;
+    static constexpr int TAP0 = CENTER_ONLY ? 4 : 0, NTAPS = CENTER_ONLY ? 1 : 9;
+    static constexpr int BLKW = FLAT ? (STRIDE == 1 ? HOUT + 2 * HALO : HOUT + 1) : ((STRIDE == 1) ? 10 : 9); // patch pixels per block (halo included)
     static constexpr int NB = FLAT ? 128 / (HOUT * BLKW) : ((HOUT == 8) ? 2 : 1); // images per tile
     static constexpr int TR = FLAT ? HOUT : 128 / (8 * NB); // tile rows; tile = TR x (NB * 8) pixels [FLAT: TR x NB x BLKW positions]
     static constexpr int PITCH = BLKW * NB;
-    static constexpr int PROWS = (STRIDE == 1) ? TR + 2 : TR + 1;
+    static constexpr int PROWS = (STRIDE == 1) ? TR + 2 * HALO : TR + 1;
     static constexpr int NPLANES = (STRIDE == 1) ? 1 : 4;
     static constexpr int PLANE_PX = PROWS * PITCH;
     static constexpr int PLANE_BYTES = CH * PLANE_PX * 16;              // one TMA box
@@ -108,7 +113,7 @@ struct ConvCfg {
     static constexpr bool BIAS_REG = COUT <= 64;
     // last conv of a stage whose output feeds a prediction head (layer1.1 / layer2.1 / layer3.1 conv2, arch.py:282,288,294):
     // the epilogue also emits per-tile global-average-pool partial sums, so the head never re-reads the activation
-    static constexpr bool GAP = (XC == COUT) && COUT >= 64 && !STRIP; // (the CU networks' head pools the stored activations)
+    static constexpr bool GAP = (XC == COUT) && COUT >= 64 && !FLAT; // (flat small-map layers: the head pools the stored activation)
     static constexpr int NBAR = 2 * NAS + 2 * (RESIDENT ? 1 : NBS) + 2 * NACC;
     static constexpr int OFF_A = 0;
     static constexpr int OFF_B = OFF_A + NAS * A_STAGE_BYTES;
@@ -137,6 +142,7 @@ struct ConvCfg {
     static_assert(COUT % 32 == 0 && G % 16 == 0 && GX % 16 == 0 && CIN % G == 0 && (XC == 0 || XC % GX == 0), "shape");
     static_assert(NACC * ACC_COLS <= 512, "TMEM columns");
     static_assert(!FLAT || (TR * PITCH <= 128 && NB >= 1 && NB <= 256), "flat tile must fit the 128 accumulator rows");
+    static_assert(!CENTER_ONLY || !RESIDENT, "centre-tap layers use the streamed-weight path");
     static_assert(STRIP || (HOUT >= 8 && COUT != 96), "the CTU network has no small maps");
     static_assert(BLKW * 8 <= 256 && PROWS <= 256, "TMA box extents");
 
@@ -147,7 +153,7 @@ struct ConvCfg {
 template <class C>
 __device__ __forceinline__ int tap_offset16(int kh, int kw)
 {
-    if (C::STRIDE == 1) return kh * C::PITCH + kw;
+    if (C::STRIDE == 1) return (kh - 1 + C::HALO) * C::PITCH + (kw - 1 + C::HALO);
     // stride 2: input row 2*oy + kh - 1 -> odd-row plane for kh != 1; the box of an odd plane starts one row/column
     // earlier (row oy0 - 1), so kh == 2 is one patch row further down
     const int py = (kh != 1), ro = (kh == 2), px = (kw != 1), co = (kw == 2);
@@ -415,7 +421,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
                     __syncwarp();
                 } else {
 #pragma unroll
-                    for (int tap = 0; tap < 9; tap++, b_it++) {
+                    for (int tap = C::TAP0; tap < C::TAP0 + C::NTAPS; tap++, b_it++) {
                         const uint32_t bs = b_it % C::NBS;
                         mbar_wait(&fullB[bs], (b_it / C::NBS) & 1);
                         tc_fence_after();
@@ -429,11 +435,11 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
                                     for (int ks = 0; ks < C::G / 16; ks++)
                                         umma_f16(d_tmem[h], umma_desc_pack(a_tap + ks * (2 * C::A_LBO / 16), a_hi),
                                                  umma_desc_pack(b_lo0 + ks * (2 * C::COUT), b_hi), idesc,
-                                                 (C::BIAS_REG && tap == 0 && ks == 0) ? (uint32_t)(cg != 0) : 1u);
+                                                 (C::BIAS_REG && tap == C::TAP0 && ks == 0) ? (uint32_t)(cg != 0) : 1u);
                                 }
                             }
                             umma_commit(&emptyB[bs]);
-                            if (tap == 8) {
+                            if (tap == C::TAP0 + C::NTAPS - 1) {
 #pragma unroll
                                 for (int h = 0; h < C::TP; h++)
                                     if (h < np) umma_commit(&emptyA[(a_it + h) % C::NAS]);
@@ -514,13 +520,15 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
             uint32_t b_it = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += C::TP * gridDim.x) { // once per pass (pair of tiles)
 #pragma unroll 1
-                for (int s = 0; s < C::NCG * 9 + C::NXS * C::XP; s++, b_it++) {
+                for (int s = 0; s < C::NCG * C::NTAPS + C::NXS * C::XP; s++, b_it++) {
                     const uint32_t bs = b_it % C::NBS;
                     mbar_wait(&emptyB[bs], ((b_it / C::NBS) & 1) ^ 1);
                     if (elect_one_sync()) {
-                        const bool is_x = s >= C::NCG * 9;
+                        const bool is_x = s >= C::NCG * C::NTAPS;
                         const uint32_t bytes = is_x ? C::X_SLAB_BYTES : C::SLAB_BYTES;
-                        const uint8_t *src = is_x ? gx + (size_t)(s - C::NCG * 9) * C::X_SLAB_BYTES : gw + (size_t)s * C::SLAB_BYTES;
+                        // packed [cin_group][9 taps]: slab (s / NTAPS) * 9 + TAP0 + s % NTAPS
+                        const uint8_t *src = is_x ? gx + (size_t)(s - C::NCG * C::NTAPS) * C::X_SLAB_BYTES
+                                                  : gw + (size_t)((s / C::NTAPS) * 9 + C::TAP0 + s % C::NTAPS) * C::SLAB_BYTES;
                         mbar_arrive_expect_tx(&fullB[bs], bytes);
                         bulk_g2s(sB + bs * C::SLAB_BYTES, src, bytes, &fullB[bs]);
                     }
@@ -566,7 +574,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
                             // strip layout: the image index is a box coordinate (first image of the tile), the last one the plane
                             const int ci = C::STRIP ? unit * C::NB : 0;
                             if constexpr (C::STRIDE == 1) {
-                                tma_load_5d(abase, &p.in_map, (ox0 - 1) * 8, ci, oy0 - 1, it * C::CH, C::STRIP ? 0 : unit, &fullA[st]);
+                                tma_load_5d(abase, &p.in_map, (ox0 - C::HALO) * 8, ci, oy0 - C::HALO, it * C::CH, C::STRIP ? 0 : unit, &fullA[st]);
                             } else {
 #pragma unroll
                                 for (int pl = 0; pl < 4; pl++)

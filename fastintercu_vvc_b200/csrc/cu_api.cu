@@ -31,6 +31,7 @@ struct mlt_cu_ctx {
     CuLayerInfo info[CU_NCONV];
     ActLayout lay[CU_NACT];
     __half *act[CU_NACT] = {};
+    float *gap_part[CU_NHEAD] = {}; // fp32 pool partial sums of the head-feeding convs on maps >= 8x8
     ConvParams conv_p[CU_NCONV];
     int16_t *d_in = nullptr, *h_in = nullptr; // dense [cap][2][size][size]
     int32_t *d_pq = nullptr, *h_pq = nullptr; // [cap][2]
@@ -151,6 +152,8 @@ int run_network(mlt_cu_ctx *c, int n, const int16_t *d_orgpred, const int32_t *d
         const int a = 4 * (i + 1) + 4; // output of layer(i+1).1.conv2 = conv 4 * (i + 1) + 3
         hp.act[i] = c->act[a];
         hp.lay[i] = c->lay[a];
+        hp.gap_part[i] = c->gap_part[i];
+        hp.gap_count[i] = c->info[a - 1].gap_count;
         hp.fc_w[i] = secp<float>(c, SEC_FC_W + i);
         hp.fc_b[i] = secp<float>(c, SEC_FC_B + i);
     }
@@ -208,6 +211,7 @@ void mlt_cu_destroy(mlt_cu_ctx *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (__half *a : c->act) cudaFree(a);
+    for (float *g : c->gap_part) cudaFree(g);
     cudaFree(c->d_blob); cudaFree(c->d_in); cudaFree(c->d_pq); cudaFree(c->d_cus); cudaFree(c->d_out); cudaFree(c->d_dbg);
     cudaFreeHost(c->h_in); cudaFreeHost(c->h_pq); cudaFreeHost(c->h_out);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -257,6 +261,11 @@ int mlt_cu_create(mlt_cu_ctx **out, const char *weights_path, int cuda_device, i
             p.bias_f32 = secp<float>(c, SEC_BIAS_FUSED + li);
             p.x_w = has_x ? secp<__half>(c, SEC_X_W_F16 + li) : nullptr;
             p.out = c->act[li + 1];
+            if (c->info[li].gap_count > 0) { // last conv of layer1..4 on a map >= 8x8: its epilogue also emits pool partial sums
+                const int hi = li / 4 - 1;
+                CU(cudaMalloc(&c->gap_part[hi], ((size_t)c->cap + 2) * c->info[li].gap_count * c->info[li].cout * sizeof(float)));
+                p.gap_part = c->gap_part[hi];
+            }
             p.relu = 1;
             p.reverse = getenv("MLT_NO_REVERSE") ? 0 : (li & 1);
             p.dbg = getenv("MLT_DEBUG_FLAGS") ? atoi(getenv("MLT_DEBUG_FLAGS")) : 0; // timing / bisect experiments only (results invalid)

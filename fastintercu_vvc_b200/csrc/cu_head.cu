@@ -1,6 +1,6 @@
 // cu_head.cu -- prediction head of the smaller-CU networks: four global average pools (after layer1..layer4,
 // mlt_cu_or_pq_arch.py:108-127), cat(poc, qp) + Linear (66->2, 98->3, 130->4, 258->6), per-level softmax and argmax
-// (the hook uses level 1 below 128x128: EncCu.cpp:916-921).  One block per CU; every reduction runs in a fixed order, so
+// (the hook uses level 1 below 128x128: EncCu.cpp:916-921).  One warp per CU; every reduction runs in a fixed order, so
 // results are bit-reproducible run to run and independent of the batch a CU is in.
 #include "mlt_internal.h"
 #include "ptx.cuh"
@@ -14,53 +14,57 @@ __device__ __forceinline__ int feat_off(int h) { return h == 0 ? 0 : (h == 1 ? 6
 __device__ __forceinline__ int logit_off(int l) { return l == 0 ? 0 : (l == 1 ? 2 : (l == 2 ? 5 : (l == 3 ? 9 : 15))); }
 } // namespace
 
-// mean over all pixels of image `img` of a strip-layout tensor -> feat[C].  Thread group (chunk, pixel slice) walks its
-// pixels in order with 128-bit loads; slices are then added in order.
-__device__ __forceinline__ void cu_gap(const __half *act, const ActLayout L, int img, float *partial, float *feat)
-{
-    const int hp = L.hp(), npl = L.npl(), nch = L.C / 8, npix = npl * hp * hp;
-    const int slices = NT / nch; // C in {64, 96, 128, 256} -> nch in {8, 12, 16, 32}: 32 / 21 / 16 / 8 slices
-    const int cj = threadIdx.x % nch, sl = threadIdx.x / nch;
-    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (sl < slices) {
-        for (int p = sl; p < npix; p += slices) {
-            const int pl = p / (hp * hp), y = (p / hp) % hp, x = p % hp;
-            const size_t off = ((((size_t)pl * nch + cj) * hp + y) * L.strip + img) * hp * 8 + (size_t)x * 8;
-            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(act + off));
-            const __half2 *h2 = reinterpret_cast<const __half2 *>(&v);
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-                const float2 t = __half22float2(h2[e]);
-                s[2 * e] += t.x;
-                s[2 * e + 1] += t.y;
-            }
-        }
-#pragma unroll
-        for (int e = 0; e < 8; e++) partial[sl * L.C + cj * 8 + e] = s[e];
-    }
-    __syncthreads();
-    const int used = slices < npix ? slices : npix; // slices beyond the pixel count hold zeros
-    for (int c = threadIdx.x; c < L.C; c += NT) {
-        float t = 0.0f;
-        for (int k = 0; k < used; k++) t += partial[k * L.C + c];
-        feat[c] = t / (float)(L.H * L.H);
-    }
-    __syncthreads();
-}
-
+// One WARP per CU (8 CUs per block): the pooled inputs are tiny -- fp32 partial sums left by the conv epilogues for maps
+// >= 8x8 (conv_umma.cuh GAP), or the stored fp16 activation of a map <= 4x4 -- so a block per CU would be all launch and
+// scheduling overhead (measured: 1.07 ms of 3.9 ms for 61,440 16-px CUs).
 __global__ void __launch_bounds__(NT) cu_head_kernel(const CuHeadParams p)
 {
-    __shared__ float partial[32 * 64 + 64]; // max over heads of slices * C = 2048 (+ slack for 21 * 96 = 2016)
-    __shared__ float feat[FEAT_TOTAL];
-    __shared__ float logits[CU_NLOGIT];
-    const int n = blockIdx.x;
+    __shared__ float s_feat[NT / 32][FEAT_TOTAL];
+    __shared__ float s_logits[NT / 32][CU_NLOGIT + 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = blockIdx.x * (NT / 32) + warp;
     griddep_launch_dependents();
     griddep_wait(); // PDL: activations come from the previous kernels of the stream
-    for (int h = 0; h < CU_NHEAD; h++) cu_gap(p.act[h], p.lay[h], n, partial, feat + feat_off(h));
-
+    if (n >= p.n) return; // (no block-level barrier below: warps are independent)
+    float *feat = s_feat[warp], *logits = s_logits[warp];
+    for (int h = 0; h < CU_NHEAD; h++) {
+        const ActLayout L = p.lay[h];
+        const float inv = 1.0f / (float)(L.H * L.H);
+        float *f = feat + feat_off(h);
+        if (p.gap_part[h] != nullptr) {
+            // maps >= 8x8: add the per-(tile, lane quadrant) fp32 partial sums in a fixed order
+            const int cnt = p.gap_count[h];
+            const float *g = p.gap_part[h] + (size_t)n * cnt * L.C;
+            for (int c = lane; c < L.C; c += 32) {
+                float t = 0.0f;
+                for (int k = 0; k < cnt; k++) t += g[k * L.C + c];
+                f[c] = t * inv;
+            }
+        } else {
+            // maps <= 4x4: pool the stored strip-layout activation; lane = 8-channel chunk, pixels in order
+            const int hp = L.hp(), npix = L.npl() * hp * hp, nch = L.C / 8;
+            for (int cj = lane; cj < nch; cj += 32) {
+                float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                for (int q = 0; q < npix; q++) {
+                    const int pl = q / (hp * hp), y = (q / hp) % hp, x = q % hp;
+                    const size_t off = ((((size_t)pl * nch + cj) * hp + y) * L.strip + n) * hp * 8 + (size_t)x * 8;
+                    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p.act[h] + off));
+                    const __half2 *h2 = reinterpret_cast<const __half2 *>(&v);
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const float2 t = __half22float2(h2[e]);
+                        s[2 * e] += t.x;
+                        s[2 * e + 1] += t.y;
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < 8; e++) f[cj * 8 + e] = s[e] * inv;
+            }
+        }
+    }
+    __syncwarp();
     const float poc = (float)p.cus[n].poc, qp = (float)p.cus[n].qp; // raw ints promoted by torch.cat (mlt_cu_or_pq_arch.py:100-101,110)
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int o = warp; o < CU_NLOGIT; o += NT / 32) {
+    for (int o = 0; o < CU_NLOGIT; o++) {
         int lvl = 0;
         while (o >= logit_off(lvl + 1)) lvl++;
         const int row = o - logit_off(lvl);
@@ -68,15 +72,15 @@ __global__ void __launch_bounds__(NT) cu_head_kernel(const CuHeadParams p)
         const float *f = feat + feat_off(lvl);
         const float *wr = p.fc_w[lvl] + (size_t)row * (C + 2);
         float s = 0.0f;
-        for (int k = lane; k < C; k += 32) s = fmaf(wr[k], f[k], s);
-        if (lane == 0) s = fmaf(wr[C], poc, s);
-        if (lane == 1) s = fmaf(wr[C + 1], qp, s);
+        for (int k = lane; k < C; k += 32) s = fmaf(__ldg(wr + k), f[k], s);
+        if (lane == 0) s = fmaf(__ldg(wr + C), poc, s);
+        if (lane == 1) s = fmaf(__ldg(wr + C + 1), qp, s);
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-        if (lane == 0) logits[o] = s + p.fc_b[lvl][row];
+        if (lane == 0) logits[o] = s + __ldg(p.fc_b[lvl] + row);
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    __syncwarp();
+    if (lane == 0) {
         mlt_cu_result r;
         for (int l = 0; l < CU_NHEAD; l++) {
             const int b = logit_off(l), cnt = logit_off(l + 1) - b;
@@ -97,7 +101,7 @@ __global__ void __launch_bounds__(NT) cu_head_kernel(const CuHeadParams p)
 cudaError_t launch_cu_head(const CuHeadParams &p, cudaStream_t s)
 {
     if (p.n <= 0) return cudaSuccess;
-    return launch_pdl(cu_head_kernel, dim3(p.n), dim3(NT), 0, s, p);
+    return launch_pdl(cu_head_kernel, dim3((p.n + NT / 32 - 1) / (NT / 32)), dim3(NT), 0, s, p);
 }
 
 } // namespace mlt

@@ -56,7 +56,8 @@ struct CuNetOps {
     {
         return cu_dispatch<S>(li, [o](auto sel) {
             using C = typename decltype(sel)::type;
-            *o = CuLayerInfo{C::CIN, C::COUT, C::STRIDE, C::HOUT, C::XC, C::OUT_PAR, C::NB, C::FLAT ? 1 : 0, C::G, C::XC > 0 ? C::GX : 0};
+            *o = CuLayerInfo{C::CIN, C::COUT, C::STRIDE, C::HOUT, C::XC, C::OUT_PAR, C::NB, C::FLAT ? 1 : 0, C::G, C::XC > 0 ? C::GX : 0,
+                             C::GAP ? (C::NB == 2 ? 4 : C::TILES_PER_IMG * 4) : 0};
             return cudaSuccess;
         });
     }

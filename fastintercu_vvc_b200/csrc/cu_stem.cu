@@ -4,8 +4,11 @@
 // Same formulation as conv1_umma_kernel (stage_conv1.cu) -- the integer part of the staging is exact ((uint16) cast,
 // |org - pred|, clamp at 1023 == clamp of v / 1023 to [0, 1]); the A operand is v * 2^-10 (exact in fp16), the B operand
 // the hi / lo fp16 split of w * (float)(1/1023) * 2^10, fp32 accumulation in TMEM -- generalised over the CU size:
-// one CTA = 8 MMA tiles of 16 x 8 pixels = 64 / SW sub-strips of 16 rows x SW columns (SW = min(size, 64)), i.e. one
-// row-strip of a 64-px CU, a whole 32-px CU (two row-strips) or four whole 16-px CUs.
+// one CTA = 4 MMA tiles of 16 x 8 pixels = 32 / SW sub-strips of 16 rows x SW columns (SW = min(size, 32)), i.e. half a
+// row-strip of a 64-px CU, one row-strip of a 32-px CU or two whole 16-px CUs.  Small CTAs on purpose: the kernel is a
+// chain of latencies (global loads -> expansion -> 16 MMAs -> TMEM reads -> stores), so throughput comes from CTAs in
+// flight, and 128 TMEM columns per CTA let four of them overlap on an SM (8 tiles / 256 columns: two; measured 342 us
+// for 3840 64-px CUs).
 // Output: activation 0, fp16, parity-planar STRIP layout [plane][4 chunks][size/2][cap][size/2][8] (conv_umma.cuh).
 #include "conv_umma.cuh"
 #include "mlt_internal.h"
@@ -16,10 +19,12 @@ template <int S>
 __global__ void __launch_bounds__(256) cu_conv1_umma_kernel(const CtuDev *__restrict__ cus, int n, const __half *__restrict__ wop,
                                                            __half *__restrict__ out, int cap)
 {
-    constexpr int SW = S < 64 ? S : 64; // sub-strip width
-    constexpr int NSUB = 64 / SW;       // sub-strips per CTA
+    constexpr int NT = 4;               // MMA tiles per CTA
+    constexpr int SW = S < 32 ? S : 32; // sub-strip width
+    constexpr int NSUB = 32 / SW;       // sub-strips per CTA
     constexpr int TPS = SW / 8;         // MMA tiles per sub-strip
-    constexpr int SPI = S / 16;         // sub-strips (16 rows each) per CU
+    constexpr int CST = S / SW;         // column strips per row strip
+    constexpr int SPI = (S / 16) * CST; // sub-strips (16 rows x SW columns) per CU
     constexpr int INC = SW + 16;        // staged input columns x = -8 .. SW + 7 (16-byte aligned loads)
     constexpr int E_BYTES = 19 * SW * 16;
     static_assert(S == 64 || S == 32 || S == 16, "CU size");
@@ -32,15 +37,15 @@ __global__ void __launch_bounds__(256) cu_conv1_umma_kernel(const CtuDev *__rest
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
-    if (warp == 0) { tmem_alloc(&tmem_slot, 256); tmem_relinquish(); }
+    if (warp == 0) { tmem_alloc(&tmem_slot, NT * 32); tmem_relinquish(); }
     reinterpret_cast<uint4 *>(s_w)[tid] = __ldg(reinterpret_cast<const uint4 *>(wop) + tid); // 256 x 16 B
     // raw samples of every sub-strip: 2 planes x 18 rows x INC/8 vectors; outside the CU = conv zero padding (org = pred = 0)
     constexpr int VPR = INC / 8, PER_SUB = 2 * 18 * VPR;
     for (int i = tid; i < NSUB * PER_SUB; i += 256) {
         const int sub = i / PER_SUB, rem = i % PER_SUB;
         const int plane = rem / (18 * VPR), row = (rem / VPR) % 18, v = rem % VPR;
-        const int g = blockIdx.x * NSUB + sub, cu = g / SPI, y0 = (g % SPI) * 16;
-        const int y = y0 - 1 + row, x = -8 + v * 8;
+        const int g = blockIdx.x * NSUB + sub, cu = g / SPI, y0 = ((g % SPI) / CST) * 16, x0 = ((g % SPI) % CST) * SW;
+        const int y = y0 - 1 + row, x = x0 - 8 + v * 8;
         uint4 val = make_uint4(0, 0, 0, 0);
         if (cu < n && y >= 0 && y < S && x >= 0 && x < S) {
             const CtuDev d = cus[cu];
@@ -90,7 +95,7 @@ __global__ void __launch_bounds__(256) cu_conv1_umma_kernel(const CtuDev *__rest
             constexpr uint32_t a_hi = umma_desc_hi(SW * 16), b_hi = umma_desc_hi(128);
             const uint32_t sE = smem_u32(s_e), sW = smem_u32(s_w);
 #pragma unroll
-            for (int tile = 0; tile < 8; tile++) {
+            for (int tile = 0; tile < NT; tile++) {
                 const uint32_t base = sE + (tile / TPS) * E_BYTES + (tile % TPS) * 128;
                 const uint32_t a0 = umma_desc_lo(base, SW * 16);               // chunks kh = 0, 1 (patch rows r, r + 1)
                 const uint32_t a2 = umma_desc_lo(base + 2 * SW * 16, SW * 16); // chunks kh = 2, (3: zero weights)
@@ -107,18 +112,18 @@ __global__ void __launch_bounds__(256) cu_conv1_umma_kernel(const CtuDev *__rest
     }
     mbar_wait(&bar, 0);
     tc_fence_after();
-    // epilogue: warp w reads TMEM lane quadrant w % 4 (pixels), tiles (w / 4) * 4 .. + 3
+    // epilogue: warp w reads TMEM lane quadrant w % 4 (pixels), tiles (w / 4) * 2, + 1
     {
         const int wq = warp & 3, m = wq * 32 + lane, r = m >> 3, c = m & 7;
         constexpr int HP = S / 2;
         const size_t chunk = (size_t)HP * cap * HP * 8, plane_stride = chunk * 4; // [plane][4 chunks][HP][cap][HP][8]
 #pragma unroll 1
-        for (int tile = (warp >> 2) * 4; tile < (warp >> 2) * 4 + 4; tile++) {
+        for (int tile = (warp >> 2) * (NT / 2); tile < (warp >> 2) * (NT / 2) + NT / 2; tile++) {
             uint32_t v[32];
             tmem_ld32(tmem + ((uint32_t)(wq * 32) << 16) + tile * 32, v);
             tmem_ld_wait();
             const int g = blockIdx.x * NSUB + tile / TPS, cu = g / SPI;
-            const int oy = (g % SPI) * 16 + r, ox = (tile % TPS) * 8 + c;
+            const int oy = ((g % SPI) / CST) * 16 + r, ox = ((g % SPI) % CST) * SW + (tile % TPS) * 8 + c;
             if (cu < n) {
                 __half *op = out + (size_t)((oy & 1) * 2 + (ox & 1)) * plane_stride + ((size_t)((oy >> 1) * cap + cu) * HP + (ox >> 1)) * 8;
 #pragma unroll
@@ -134,13 +139,13 @@ __global__ void __launch_bounds__(256) cu_conv1_umma_kernel(const CtuDev *__rest
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 256); }
+    if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, NT * 32); }
 }
 
 cudaError_t launch_cu_conv1(int size, const CtuDev *cus, int n, const __half *wop, __half *out, int cap, cudaStream_t s)
 {
     if (n <= 0) return cudaSuccess;
-    const int spi = size / 16, nsub = size >= 64 ? 1 : 64 / size;
+    const int sw = size < 32 ? size : 32, spi = (size / 16) * (size / sw), nsub = 32 / sw;
     const int grid = (n * spi + nsub - 1) / nsub;
     switch (size) {
     case 64: cu_conv1_umma_kernel<64><<<grid, 256, 0, s>>>(cus, n, wop, out, cap); break;

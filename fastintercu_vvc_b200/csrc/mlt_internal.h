@@ -117,6 +117,7 @@ constexpr int CU_NCONV = 20, CU_NACT = 21, CU_NHEAD = 4, CU_NLOGIT = 15;
 struct CuLayerInfo { // one 3x3 conv of the CU network at a given CU size (forward order, after conv1)
     int cin, cout, stride, hout, xc, out_par, nb, flat; // stride as executed (a stride-2 conv on a 1x1 map runs as stride 1)
     int g, gx;                                          // channels per weight slab of the main / extra operand (packer layout)
+    int gap_count;                                      // pool partial vectors per image its epilogue writes (0: none)
 };
 cudaError_t cu_conv_init(int size);                    // opt in to large dynamic shared memory for this size's kernels
 cudaError_t cu_conv_info(int size, int layer, CuLayerInfo *info);
@@ -128,6 +129,8 @@ cudaError_t launch_cu_conv1(int size, const CtuDev *cus, int n, const __half *wo
 struct CuHeadParams {
     const __half *act[CU_NHEAD]; // outputs of layer1..layer4 (strip layouts)
     ActLayout lay[CU_NHEAD];
+    const float *gap_part[CU_NHEAD]; // maps >= 8x8: fp32 pool partial sums written by that conv's epilogue [image][gap_count][C], else nullptr
+    int gap_count[CU_NHEAD];
     const float *fc_w[CU_NHEAD]; // [out][in]
     const float *fc_b[CU_NHEAD];
     const CtuDev *cus;           // poc / qp

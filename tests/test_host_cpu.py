@@ -166,7 +166,9 @@ def test_cu_packer_layout_agrees_with_the_kernel_tables(tmp_path):
             nb, flat = int(info[6]), int(info[7])
             assert flat == (hout <= 4)
             if flat:  # NB images x HOUT rows x (HOUT + halo) positions fit the 128 accumulator rows
-                assert nb * hout * (hout + (2 if stride == 1 else 1)) <= 128
+                halo = 0 if (hout == 1 and stride == 1) else 1  # a 3x3 conv on a 1x1 map is its centre tap: no halo, 128 images per tile
+                assert nb * hout * (hout + (2 * halo if stride == 1 else 1)) <= 128
+                assert nb == 128 // (hout * (hout + (2 * halo if stride == 1 else 1)))
         assert lib.mlt_cu_layer_info(size, 20, np.zeros(10, np.int32).ctypes.data) == -1
         path = str(tmp_path / f"cu{size}.mltw")
         sd = synth.make_cu_state_dict(10, size)
