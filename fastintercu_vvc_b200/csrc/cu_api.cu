@@ -25,7 +25,9 @@ struct Section { const uint8_t *dev = nullptr; size_t bytes = 0; };
 
 struct mlt_cu_ctx {
     int device = 0, size = 0, cap = 0, num_sms = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    static constexpr int MAX_CHUNKS = 12;
+    cudaEvent_t ev_in[MAX_CHUNKS] = {}; // "chunk i of the input batch has landed in HBM"
     uint8_t *d_blob = nullptr;
     Section sec[0x1000];
     CuLayerInfo info[CU_NCONV];
@@ -178,10 +180,32 @@ int run_host_batch(mlt_cu_ctx *c, int n, const int16_t *src, const int32_t *pq, 
 {
     cudaStream_t s = c->stream;
     const size_t per = (size_t)2 * c->size * c->size;
-    CU(cudaMemcpyAsync(c->d_in, src, (size_t)n * per * sizeof(int16_t), cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(c->d_pq, pq, (size_t)n * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-    int rc = run_network(c, n, c->d_in, c->d_pq, c->d_out, s);
-    if (rc) return rc;
+    // Large batches are pipelined in three chunks (n/8, 3n/8, n/2): chunk i + 1 is copied (copy stream) while chunk i
+    // computes, so only the first, small copy is exposed.  Few chunks on purpose: every pass over the 23 kernels has a
+    // latency floor of ~0.25 ms (the last stages stream megabytes of weights through a handful of CTAs), which six
+    // finer chunks paid six times (measured).  The strip buffers are reused by every chunk (their kernels are ordered
+    // on the compute stream).
+    int sizes[mlt_cu_ctx::MAX_CHUNKS], nchunks = 0;
+    if ((size_t)n * per * sizeof(int16_t) < ((size_t)8 << 20)) sizes[nchunks++] = n; // < 8 MiB: one copy, one pass
+    else {
+        sizes[0] = n / 8;
+        sizes[1] = 3 * (n / 8);
+        sizes[2] = n - sizes[0] - sizes[1];
+        nchunks = 3;
+    }
+    for (int i = 0, off = 0; i < nchunks; off += sizes[i], i++) {
+        const int m = sizes[i];
+        CU(cudaMemcpyAsync(c->d_in + (size_t)off * per, src + (size_t)off * per, (size_t)m * per * sizeof(int16_t), cudaMemcpyHostToDevice,
+                           nchunks > 1 ? c->copy_stream : s));
+        if (nchunks > 1) {
+            CU(cudaEventRecord(c->ev_in[i], c->copy_stream));
+            CU(cudaStreamWaitEvent(s, c->ev_in[i], 0));
+        }
+        const int rc = run_network(c, m, c->d_in + (size_t)off * per, c->d_pq + (size_t)off * 2, c->d_out + off, s);
+        if (rc) { cudaStreamSynchronize(c->copy_stream); return rc; }
+    }
+    c->last_n = nchunks == 1 ? n : 0; // debug_activation only sees a batch that ran as one pass
     CU(cudaMemcpyAsync(c->h_out, c->d_out, (size_t)n * sizeof(mlt_cu_result), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     memcpy(out, c->h_out, (size_t)n * sizeof(mlt_cu_result));
@@ -214,6 +238,8 @@ void mlt_cu_destroy(mlt_cu_ctx *c)
     for (float *g : c->gap_part) cudaFree(g);
     cudaFree(c->d_blob); cudaFree(c->d_in); cudaFree(c->d_pq); cudaFree(c->d_cus); cudaFree(c->d_out); cudaFree(c->d_dbg);
     cudaFreeHost(c->h_in); cudaFreeHost(c->h_pq); cudaFreeHost(c->h_out);
+    for (cudaEvent_t e : c->ev_in) if (e) cudaEventDestroy(e);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -238,6 +264,8 @@ int mlt_cu_create(mlt_cu_ctx **out, const char *weights_path, int cuda_device, i
     auto body = [&]() -> int {
         CU(cudaSetDevice(cuda_device));
         CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (cudaEvent_t &e : c->ev_in) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         for (int li = 0; li < CU_NCONV; li++) CU(cu_conv_info(cu_size, li, &c->info[li]));
         int r = load_blob(c, weights_path);
         if (r) return r;

@@ -182,3 +182,27 @@ def test_cu_error_paths(ctx):
     with pytest.raises(MltError) as e:
         p.predict_batch_dense(big, np.zeros((p.max_batch + 1, 2), np.int32))
     assert e.value.rc == -7
+
+
+@pytest.mark.parametrize("size", ref_arch.CU_SIZES)
+def test_cu_large_batches_take_the_pipelined_path_and_stay_bit_identical(size):
+    """Batches >= 8 MiB are cut into growing chunks (H2D of chunk i + 1 overlaps the kernels of chunk i): every CU's result
+    must equal the small-batch result bit for bit, whatever chunk and tile position it lands in.  Also the scale at which
+    the resident-weight ring race (profiles/r01/README.md) used to fault."""
+    from fastintercu_vvc_b200 import MltCuPredictor, write_cu_blob
+
+    sd = ref_arch.make_cu_state_dict(10, size)
+    with tempfile.NamedTemporaryFile(suffix=".mltw", delete=False) as f:
+        path = f.name
+    write_cu_blob(sd, size, path)
+    n = {64: 3840, 32: 15360, 16: 61440}[size]  # all CUs of 8 1080p frames
+    base, pq = ref_arch.synth_cus(50, size, 31)
+    idx = np.arange(n) % 50
+    orgpred, pocqp = np.ascontiguousarray(base[idx]), np.ascontiguousarray(pq[idx])
+    with MltCuPredictor(path, size, device=0, max_batch=n) as p:
+        small = p.predict_batch_dense(base, pq)
+        big = p.predict_batch_dense(orgpred, pocqp)
+        again = p.predict_batch_dense(orgpred, pocqp)
+    os.unlink(path)
+    assert big.tobytes() == again.tobytes()
+    assert big.tobytes() == small[idx].tobytes()
