@@ -206,7 +206,33 @@ def synth_cu_batch(n: int, size: int, seed: int):
     return np.ascontiguousarray(cus), np.ascontiguousarray(np.repeat(pq, per, 0)[:n])
 
 
-def bench_cu_models(local: int, frames: int, steps: int, warm: int):
+def cpu_cu_reference_rate(size: int, budget_s: float):
+    """Reference CPU path of a smaller-CU model: traced TorchScript of `GapBigMltCuORPQ` on torch CPU fp32 (libtorch), one CU
+    per forward like the hook's cuw != 128 branch (EncCu.cpp:869-921), model loaded once.  Bounded by `budget_s` seconds."""
+    import torch
+
+    from oracle import ref_arch
+
+    torch.set_num_threads(len(os.sched_getaffinity(0)))
+    net = ref_arch.build_cu_model(ref_arch.make_cu_state_dict(10, size))
+    traced = torch.jit.trace(net, (torch.rand(1, 2, 128, 128), torch.rand(1), torch.rand(1)))  # as model2torchScript.py:37-48
+    cus, pq = ref_arch.synth_cus(16, size, 10)
+    x = torch.from_numpy(ref_arch.stage_numpy(cus))
+    with torch.no_grad():
+        for i in range(3):
+            traced(x[i : i + 1], torch.tensor([int(pq[i, 0])]), torch.tensor([int(pq[i, 1])]))
+        n, t0 = 0, time.perf_counter()
+        while True:
+            i = n % 16
+            traced(x[i : i + 1], torch.tensor([int(pq[i, 0])]), torch.tensor([int(pq[i, 1])]))
+            n += 1
+            dt = time.perf_counter() - t0
+            if (dt >= budget_s and n >= 16) or n >= 100000:
+                break
+    return n / dt, torch.get_num_threads(), n, dt
+
+
+def bench_cu_models(local: int, frames: int, steps: int, warm: int, cpu_budget: float = 0.0):
     """Device-resident and host-buffer throughput of the 64 / 32 / 16-px CU models on all
     same-size CUs of `frames` 1080p frames per step.  Secondary numbers: the headline metric stays the CTU model."""
     import torch
@@ -261,6 +287,10 @@ def bench_cu_models(local: int, frames: int, steps: int, warm: int):
         pred.close()
         del d_in, d_pq, d_out
         torch.cuda.empty_cache()
+        if cpu_budget > 0:
+            r, cores, cn, cdt = cpu_cu_reference_rate(size, cpu_budget)
+            out[str(size)]["cpu_baseline"] = {"value": r, "unit": "CU/s", "cores": cores, "kind": "port",
+                                              "sample": f"{cn} CUs at B=1 through traced TorchScript (torch CPU fp32 = libtorch) in {cdt:.1f}s"}
     return out
 
 
@@ -436,7 +466,8 @@ def main():
         }
         if args.cu_frames > 0 and world == 1:
             pred.close()
-            line["cu_models"] = bench_cu_models(local, args.cu_frames, max(steps // 5, 3), warm)
+            line["cu_models"] = bench_cu_models(local, args.cu_frames, max(steps // 5, 3), warm,
+                                                0.0 if args.no_cpu_baseline else min(3.0, args.cpu_budget / 4))
             line["cu_models"]["note"] = (f"secondary (SURVEY.md section 8f rank 1): 64 / 32 / 16-px GapBigMltCuORPQ on all same-size CUs of "
                                          f"{args.cu_frames} 1080p frames per step, device-resident and host-buffer (e2e) CUs/s")
         if not args.no_cpu_baseline and world == 1:
