@@ -75,6 +75,18 @@ struct mlt_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     float *act_f[NACT] = {};
     float *scratch_f = nullptr; // shortcut-conv output of the fp32 engine
+    // Host-batch slot: the device / pinned buffers one host batch lives in.  Slot 0 = the buffers below (every synchronous
+    // call); slot 1 is allocated on the first mlt_submit_batch_dense so that two batches can be in flight (the H2D of
+    // batch k + 1 runs while batch k computes).
+    struct HostSlot {
+        int16_t *d_in = nullptr;
+        CtuDev *d_ctus = nullptr, *h_ctus = nullptr;
+        mlt_result *d_out = nullptr, *h_out = nullptr;
+        cudaEvent_t done = nullptr;
+        int n = 0;
+        bool busy = false;
+    } slot[2];
+    uint64_t submitted = 0, collected = 0;
     int16_t *d_in = nullptr, *h_in = nullptr; // dense [max_batch][2][128][128]
     CtuDev *d_ctus = nullptr, *h_ctus = nullptr;
     mlt_result *d_out = nullptr, *h_out = nullptr;
@@ -316,11 +328,12 @@ void gather_ctu(int16_t *dst, const int16_t *org, int org_stride, const int16_t 
     for (int y = 0; y < CTU; y++) memcpy(dst + (size_t)y * CTU, pred + (size_t)y * pred_stride, CTU * sizeof(int16_t));
 }
 
-void dense_descs(mlt_ctx *c, int n, const int32_t *pocqp, const mlt_ctu_desc *descs)
+void dense_descs(mlt_ctx *c, int n, const int32_t *pocqp, const mlt_ctu_desc *descs, int slot = 0)
 {
+    const mlt_ctx::HostSlot &S = c->slot[slot];
     for (int i = 0; i < n; i++) {
-        CtuDev &d = c->h_ctus[i];
-        d.org = c->d_in + (size_t)i * CTU_IN_ELEMS;
+        CtuDev &d = S.h_ctus[i];
+        d.org = S.d_in + (size_t)i * CTU_IN_ELEMS;
         d.pred = d.org + (size_t)CTU * CTU;
         d.org_stride = d.pred_stride = CTU;
         d.poc = descs ? descs[i].poc : pocqp[2 * i];
@@ -332,6 +345,7 @@ void dense_descs(mlt_ctx *c, int n, const int32_t *pocqp, const mlt_ctu_desc *de
 int run_host_batch(mlt_ctx *c, int n, mlt_result *out, bool upload_in)
 {
     cudaStream_t s = c->stream;
+    if (c->submitted != c->collected) return fail(c, MLT_E_STATE, "submitted batches must be collected first");
     if (upload_in) CU(cudaMemcpyAsync(c->d_in, c->h_in, (size_t)n * CTU_IN_ELEMS * sizeof(int16_t), cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(c->d_ctus, c->h_ctus, (size_t)n * sizeof(CtuDev), cudaMemcpyHostToDevice, s));
     int rc = run_network(c, c->d_ctus, n, c->d_out, s);
@@ -345,11 +359,14 @@ int run_host_batch(mlt_ctx *c, int n, mlt_result *out, bool upload_in)
 // Host batch of n CTUs, pipelined: chunk i+1 is staged / copied (copy stream) while chunk i computes (compute stream).
 // `src` != nullptr: dense caller buffer, copied straight from it (pinned or pageable, no intermediate host copy);
 // otherwise `descs` are gathered chunk by chunk into the pinned staging buffer first.
-int run_host_batch_chunked(mlt_ctx *c, int n, const int16_t *src, const mlt_ctu_desc *descs, const int32_t *pocqp, mlt_result *out)
+// Enqueues everything (descriptor upload, chunked H2D, kernels, D2H of the results into the slot's pinned buffer, `done`
+// event) without waiting for it.
+int enqueue_host_batch(mlt_ctx *c, int slot, int n, const int16_t *src, const mlt_ctu_desc *descs, const int32_t *pocqp)
 {
     cudaStream_t s = c->stream;
-    dense_descs(c, n, pocqp, descs);
-    CU(cudaMemcpyAsync(c->d_ctus, c->h_ctus, (size_t)n * sizeof(CtuDev), cudaMemcpyHostToDevice, s));
+    mlt_ctx::HostSlot &H = c->slot[slot];
+    dense_descs(c, n, pocqp, descs, slot);
+    CU(cudaMemcpyAsync(H.d_ctus, H.h_ctus, (size_t)n * sizeof(CtuDev), cudaMemcpyHostToDevice, s));
     // Chunk schedule: only the FIRST chunk's H2D is exposed (every later copy hides behind the previous chunks' kernels,
     // which are slower than PCIe), so the chunks start small (n / 16) and grow by 1.5x up to n / 4.
     int sizes[mlt_ctx::MAX_CHUNKS], nchunks = 0;
@@ -365,6 +382,18 @@ int run_host_batch_chunked(mlt_ctx *c, int n, const int16_t *src, const mlt_ctu_
             cur = cur * 3 / 2 < cap ? cur * 3 / 2 : cap;
         }
     }
+    if (const char *ov = getenv("MLT_CHUNKS")) { // measurement override: comma-separated chunk sizes summing to n
+        int tmp[mlt_ctx::MAX_CHUNKS], k = 0, sum = 0;
+        for (const char *q = ov; *q && k < mlt_ctx::MAX_CHUNKS;) {
+            tmp[k] = atoi(q);
+            sum += tmp[k++];
+            while (*q && *q != ',') q++;
+            if (*q == ',') q++;
+        }
+        bool ok = sum == n;
+        for (int i = 0; i < k; i++) ok = ok && tmp[i] > 0 && tmp[i] <= c->set[i & 1].cap;
+        if (ok) { nchunks = k; for (int i = 0; i < k; i++) sizes[i] = tmp[i]; }
+    }
     int per = 0;
     for (int i = 0; i < nchunks; i++) per = sizes[i] > per ? sizes[i] : per;
     const bool two = nchunks > 1 && !c->profiling; // chunks alternate between the two activation sets / compute streams
@@ -375,20 +404,30 @@ int run_host_batch_chunked(mlt_ctx *c, int n, const int16_t *src, const mlt_ctu_
         if (!src)
             for (int k = off; k < off + m; k++)
                 gather_ctu(c->h_in + (size_t)k * CTU_IN_ELEMS, descs[k].org, descs[k].org_stride, descs[k].pred, descs[k].pred_stride);
-        CU(cudaMemcpyAsync(c->d_in + (size_t)off * CTU_IN_ELEMS, from, (size_t)m * CTU_IN_ELEMS * sizeof(int16_t),
+        CU(cudaMemcpyAsync(H.d_in + (size_t)off * CTU_IN_ELEMS, from, (size_t)m * CTU_IN_ELEMS * sizeof(int16_t),
                            cudaMemcpyHostToDevice, c->copy_stream));
         CU(cudaEventRecord(c->ev_in[i], c->copy_stream));
         const int si = two ? (i & 1) : 0;
         cudaStream_t cs = si ? c->stream2 : s;
         CU(cudaStreamWaitEvent(cs, c->ev_in[i], 0));
-        const int rc = run_network(c, c->d_ctus + off, m, c->d_out + off, cs, si);
+        const int rc = run_network(c, H.d_ctus + off, m, H.d_out + off, cs, si);
         if (rc) { cudaStreamSynchronize(c->copy_stream); cudaStreamSynchronize(c->stream2); return rc; }
     }
     if (two) { CU(cudaEventRecord(c->ev_join, c->stream2)); CU(cudaStreamWaitEvent(s, c->ev_join, 0)); }
     c->last_n = n <= per ? n : 0; // debug_activation only sees a whole batch when it ran as one chunk
-    CU(cudaMemcpyAsync(c->h_out, c->d_out, (size_t)n * sizeof(mlt_result), cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
-    memcpy(out, c->h_out, (size_t)n * sizeof(mlt_result));
+    CU(cudaMemcpyAsync(H.h_out, H.d_out, (size_t)n * sizeof(mlt_result), cudaMemcpyDeviceToHost, s));
+    CU(cudaEventRecord(H.done, s));
+    H.n = n;
+    return MLT_OK;
+}
+
+int run_host_batch_chunked(mlt_ctx *c, int n, const int16_t *src, const mlt_ctu_desc *descs, const int32_t *pocqp, mlt_result *out)
+{
+    if (c->submitted != c->collected) return fail(c, MLT_E_STATE, "%llu submitted batch(es) not collected yet", (unsigned long long)(c->submitted - c->collected));
+    const int rc = enqueue_host_batch(c, 0, n, src, descs, pocqp);
+    if (rc) return rc;
+    CU(cudaEventSynchronize(c->slot[0].done));
+    memcpy(out, c->slot[0].h_out, (size_t)n * sizeof(mlt_result));
     return MLT_OK;
 }
 
@@ -437,6 +476,8 @@ void mlt_destroy(mlt_ctx *c)
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
+    if (c->slot[1].d_in) { cudaFree(c->slot[1].d_in); cudaFree(c->slot[1].d_ctus); cudaFree(c->slot[1].d_out); cudaFreeHost(c->slot[1].h_ctus); cudaFreeHost(c->slot[1].h_out); }
+    for (auto &H : c->slot) if (H.done) cudaEventDestroy(H.done);
     cudaFree(c->scratch_f); cudaFree(c->d_blob); cudaFree(c->d_in); cudaFree(c->d_ctus); cudaFree(c->d_out);
     cudaFree(c->d_dbg); cudaFree(c->d_pic);
     cudaFreeHost(c->h_in); cudaFreeHost(c->h_ctus); cudaFreeHost(c->h_out);
@@ -516,6 +557,9 @@ int mlt_create_ex(mlt_ctx **out, const char *weights_path, int cuda_device, int 
         CU(cudaHostAlloc(&c->h_in, (size_t)max_batch * CTU_IN_ELEMS * sizeof(int16_t), cudaHostAllocDefault));
         CU(cudaHostAlloc(&c->h_ctus, (size_t)max_batch * sizeof(CtuDev), cudaHostAllocDefault));
         CU(cudaHostAlloc(&c->h_out, (size_t)max_batch * sizeof(mlt_result), cudaHostAllocDefault));
+        c->slot[0].d_in = c->d_in; c->slot[0].d_ctus = c->d_ctus; c->slot[0].h_ctus = c->h_ctus;
+        c->slot[0].d_out = c->d_out; c->slot[0].h_out = c->h_out;
+        for (auto &H : c->slot) CU(cudaEventCreateWithFlags(&H.done, cudaEventDisableTiming));
         return MLT_OK;
     };
     rc = body();
@@ -595,6 +639,44 @@ int mlt_predict_batch_dense(mlt_ctx *c, int n, const int16_t *orgpred, const int
     if (n > c->max_batch) return fail(c, MLT_E_BATCH, "n=%d > max_batch=%d", n, c->max_batch);
     if (n == 0) return MLT_OK;
     return run_host_batch_chunked(c, n, orgpred, nullptr, pocqp, out);
+}
+
+int mlt_submit_batch_dense(mlt_ctx *c, int n, const int16_t *orgpred, const int32_t *pocqp)
+{
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (n < 1 || !orgpred || !pocqp) return fail(c, MLT_E_INVAL, "null argument / empty batch");
+    if (n > c->max_batch) return fail(c, MLT_E_BATCH, "n=%d > max_batch=%d", n, c->max_batch);
+    if (c->submitted - c->collected >= 2) return fail(c, MLT_E_STATE, "two batches already in flight: call mlt_collect first");
+    const int si = (int)(c->submitted & 1);
+    mlt_ctx::HostSlot &H = c->slot[si];
+    if (!H.d_in) { // second slot: allocated on first use
+        CU(cudaMalloc(&H.d_in, (size_t)c->max_batch * CTU_IN_ELEMS * sizeof(int16_t)));
+        CU(cudaMalloc(&H.d_ctus, (size_t)c->max_batch * sizeof(CtuDev)));
+        CU(cudaMalloc(&H.d_out, (size_t)c->max_batch * sizeof(mlt_result)));
+        CU(cudaHostAlloc(&H.h_ctus, (size_t)c->max_batch * sizeof(CtuDev), cudaHostAllocDefault));
+        CU(cudaHostAlloc(&H.h_out, (size_t)c->max_batch * sizeof(mlt_result), cudaHostAllocDefault));
+    }
+    rc = enqueue_host_batch(c, si, n, orgpred, nullptr, pocqp);
+    if (rc) return rc;
+    H.busy = true;
+    c->submitted++;
+    return MLT_OK;
+}
+
+int mlt_collect(mlt_ctx *c, mlt_result *out, int *n_out)
+{
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (!out) return fail(c, MLT_E_INVAL, "null argument");
+    if (c->submitted == c->collected) return fail(c, MLT_E_STATE, "no submitted batch to collect");
+    mlt_ctx::HostSlot &H = c->slot[c->collected & 1];
+    CU(cudaEventSynchronize(H.done));
+    memcpy(out, H.h_out, (size_t)H.n * sizeof(mlt_result));
+    if (n_out) *n_out = H.n;
+    H.busy = false;
+    c->collected++;
+    return MLT_OK;
 }
 
 int mlt_predict_batch_device(mlt_ctx *c, int n, const int16_t *d_orgpred, const int32_t *d_pocqp, mlt_result *d_out,

@@ -101,6 +101,16 @@ MLT_API int mlt_predict_batch(mlt_ctx *ctx, int n, const mlt_ctu_desc *descs, ml
 /* Dense host batch: orgpred[n][2][128][128] int16 (plane 0 = org, plane 1 = pred), pocqp[n][2]. */
 MLT_API int mlt_predict_batch_dense(mlt_ctx *ctx, int n, const int16_t *orgpred, const int32_t *pocqp, mlt_result *out);
 
+/* Pipelined form of mlt_predict_batch_dense for throughput runs over frames of independent encodes (north-star item 4;
+ * no counterpart in the reference, whose hook is one blocking call per CTU): mlt_submit_batch_dense enqueues the H2D
+ * copies, kernels and the D2H of the results and returns; mlt_collect blocks for the OLDEST submitted batch and copies
+ * its n results out.  At most two batches may be in flight (the second one's H2D runs while the first computes; a second
+ * set of input buffers is allocated on first use).  `orgpred` must stay valid and unchanged until that batch is
+ * collected (pinned memory recommended); `pocqp` is consumed before the call returns.  Synchronous calls are refused
+ * (MLT_E_STATE) while batches are in flight. */
+MLT_API int mlt_submit_batch_dense(mlt_ctx *ctx, int n, const int16_t *orgpred, const int32_t *pocqp);
+MLT_API int mlt_collect(mlt_ctx *ctx, mlt_result *out, int *n_out);
+
 /* Device-resident batch on the caller's stream (cudaStream_t passed as void*; NULL = default stream).
  * d_orgpred / d_pocqp / d_out are device pointers; asynchronous w.r.t. the host. */
 MLT_API int mlt_predict_batch_device(mlt_ctx *ctx, int n, const int16_t *d_orgpred, const int32_t *d_pocqp,

@@ -402,3 +402,42 @@ def test_full_size_batch_properties():
             m = OracleModel(sd)
             lg, sp = m.predict_batch(base[:16], pq[:16])
             assert np.abs(softmax_levels(first[:16]) - softmax_levels(lg)).max() <= PROB_TOL
+
+
+def test_pipelined_submit_collect_matches_the_synchronous_call():
+    """mlt_submit_batch_dense / mlt_collect: two batches in flight, results bit-identical to mlt_predict_batch_dense,
+    FIFO order, state errors reported (never a silent overwrite of a buffer in flight)."""
+    from fastintercu_vvc_b200 import MltError, MltPredictor
+    from fastintercu_vvc_b200.pack_weights import write_blob
+
+    with tempfile.NamedTemporaryFile(suffix=".mltw", delete=False) as f:
+        path = f.name
+    write_blob(ref_arch.make_state_dict(10), path)
+    base, pq = ref_arch.synth_ctus(24, 91)
+    batches = []
+    for k, n in enumerate((1100, 7, 1500, 1024)):  # chunked and single-pass batches mixed
+        idx = (np.arange(n) * (k + 3)) % 24
+        batches.append((np.ascontiguousarray(base[idx]), np.ascontiguousarray(pq[idx])))
+    with MltPredictor(path, device=0, max_batch=1500) as p:
+        want = [p.predict_batch_dense(o, q).copy() for o, q in batches]
+        with pytest.raises(MltError) as e:
+            p.collect()
+        assert e.value.rc == -8
+        p.submit_batch_dense(*batches[0])
+        p.submit_batch_dense(*batches[1])
+        with pytest.raises(MltError) as e:
+            p.submit_batch_dense(*batches[2])  # two already in flight
+        assert e.value.rc == -8
+        with pytest.raises(MltError) as e:
+            p.predict_batch_dense(*batches[2])  # synchronous calls are refused while batches are in flight
+        assert e.value.rc == -8
+        got0 = p.collect().copy()
+        p.submit_batch_dense(*batches[2])
+        got1 = p.collect().copy()
+        p.submit_batch_dense(*batches[3])
+        got2 = p.collect().copy()
+        got3 = p.collect().copy()
+        for g, w in zip((got0, got1, got2, got3), want):
+            assert g.tobytes() == w.tobytes()
+        assert p.predict_batch_dense(*batches[1]).tobytes() == want[1].tobytes()  # synchronous path usable again
+    os.unlink(path)
