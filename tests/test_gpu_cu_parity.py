@@ -206,3 +206,49 @@ def test_cu_large_batches_take_the_pipelined_path_and_stay_bit_identical(size):
     os.unlink(path)
     assert big.tobytes() == again.tobytes()
     assert big.tobytes() == small[idx].tobytes()
+
+
+def test_cpp_hook_cu_branch_matches_the_binding(ctx):
+    """The C++ hook mirror's smaller-CU branch (size-mask gate of EncCu.cpp:754, predictCu == elements()[0] of :916-919)
+    over the CUs of a picture, with picture-strided pointers, gives the ctypes binding's level-1 decisions."""
+    import subprocess
+
+    from fastintercu_vvc_b200 import write_cu_blob
+
+    size, sd, p = ctx
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hook = os.path.join(root, "fastintercu_vvc_b200", "hook")
+    exe = os.path.join(hook, "hook_cu_sim.bin")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", hook])
+    w, h, stride, poc, qp = 208, 120, 208 + 2 * 80 + 8, 7, 34  # VTM-like margins; partial CUs at the right / bottom edge
+    nx, ny = w // size, h // size
+    cus, _ = ref_arch.synth_cus(nx * ny, size, 55)
+    rng = np.random.RandomState(2)
+    org = rng.randint(0, 1024, (h, stride)).astype(np.int16)
+    pred = rng.randint(0, 1024, (h, stride)).astype(np.int16)
+    for j in range(ny):
+        for i in range(nx):
+            org[j * size : (j + 1) * size, i * size : (i + 1) * size] = cus[j * nx + i, 0]
+            pred[j * size : (j + 1) * size, i * size : (i + 1) * size] = cus[j * nx + i, 1]
+    with tempfile.NamedTemporaryFile(suffix=".mltw", delete=False) as f:
+        blob = f.name
+    write_cu_blob(sd, size, blob)
+    with tempfile.NamedTemporaryFile(suffix=".bin", delete=False) as f:
+        f.write(np.array([w, h, stride, poc, qp, size], np.int32).tobytes())
+        f.write(org.tobytes())
+        f.write(pred.tobytes())
+        path = f.name
+    try:
+        env = dict(os.environ, MLT_DEVICE="0", MLT_CU_SIZES=str(size), **{f"MLT_WEIGHTS_{size}": blob})
+        r = subprocess.run([exe, path], capture_output=True, text=True, timeout=120, env=env)
+        off = subprocess.run([exe, path], capture_output=True, text=True, timeout=120, env=dict(env, MLT_CU_SIZES=""))
+    finally:
+        os.unlink(path)
+        os.unlink(blob)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert off.returncode == 4 and off.stdout == ""  # gate as shipped by the reference: smaller CUs are not predicted
+    rows = [tuple(map(int, l.split())) for l in r.stdout.strip().splitlines()]
+    assert [(x, y) for x, y, _ in rows] == [(i * size, j * size) for j in range(ny) for i in range(nx)]
+    want = p.predict_batch_dense(cus, np.tile(np.array([[poc, qp]], np.int32), (nx * ny, 1)))["split"][:, 0]
+    assert [s for _, _, s in rows] == want.tolist()
