@@ -44,6 +44,12 @@ struct ConvCfg {
     static constexpr int CIN = CIN_, COUT = COUT_, STRIDE = STRIDE_, HOUT = HOUT_, XC = XC_, OUT_PAR = OUT_PAR_;
     static constexpr bool STRIP = (FLAGS_ & 1) != 0;
     static constexpr bool FLAT = STRIP && HOUT <= 4;
+    // FLAGS_ bits 1 / 2 (HILO_IN / HILO_OUT): the last two stages of the CU networks keep their activations as an fp16
+    // hi + lo PAIR (lo = fp16(x - hi), stored right behind the hi tensor): their small maps pool only 16 / 4 / 1 pixels,
+    // so the fp16 rounding of activations does not average out there (tools/emulate_cu_precision.py).  A hi+lo input
+    // costs nothing in weight traffic: the "tile pair" of the streamed-weight path becomes (hi box, lo box) of ONE tile,
+    // both accumulating into the same TMEM accumulator.
+    static constexpr bool HILO_IN = (FLAGS_ & 2) != 0, HILO_OUT = (FLAGS_ & 4) != 0;
     // XLO: the extra operand's weights come as an fp16 hi + lo pair (two MMA passes over the same activation stage): the
     // folded 1x1 shortcut weights are the largest single source of fp16 weight-rounding error and cost < 1 % to do exactly
     static constexpr int XP = 1 + XLO_;
@@ -143,6 +149,8 @@ struct ConvCfg {
     static_assert(NACC * ACC_COLS <= 512, "TMEM columns");
     static_assert(!FLAT || (TR * PITCH <= 128 && NB >= 1 && NB <= 256), "flat tile must fit the 128 accumulator rows");
     static_assert(!CENTER_ONLY || !RESIDENT, "centre-tap layers use the streamed-weight path");
+    static_assert(!HILO_IN || (!RESIDENT && STRIP), "hi+lo inputs ride on the tile-pair structure of the streamed-weight path");
+    static constexpr int TSTEP = HILO_IN ? 1 : TP; // tiles per pass
     static_assert(STRIP || (HOUT >= 8 && COUT != 96), "the CTU network has no small maps");
     static_assert(BLKW * 8 <= 256 && PROWS <= 256, "TMA box extents");
 
@@ -262,6 +270,23 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
                         for (int e = 0; e < 4; e++) h2[e] = hq[q * 4 + e];
                         *reinterpret_cast<uint4 *>(op + (size_t)q * ochunk) = ov;
                     }
+                    if constexpr (C::HILO_OUT) {
+                        // lo = fp16(relu(x) - hi), same layout, one whole tensor further on
+                        __half *lp = op + ochunk * (C::COUT / 8) * C::ONPL;
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            uint4 ov;
+                            __half2 *h2 = reinterpret_cast<__half2 *>(&ov);
+#pragma unroll
+                            for (int e = 0; e < 4; e++) {
+                                const float2 hf = __half22float2(hq[q * 4 + e]);
+                                float x0 = __uint_as_float(v[2 * (q * 4 + e)]), x1 = __uint_as_float(v[2 * (q * 4 + e) + 1]);
+                                if (p.relu) { x0 = fmaxf(x0, 0.0f); x1 = fmaxf(x1, 0.0f); }
+                                h2[e] = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+                            }
+                            *reinterpret_cast<uint4 *>(lp + (size_t)q * ochunk) = ov;
+                        }
+                    }
                 }
                 if constexpr (C::GAP) {
                     // Global-average-pool partial sums of this tile (fixed shuffle tree => bit-reproducible): a transpose-
@@ -371,24 +396,27 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
         } else
         // One pass = TP tiles (a PAIR when the weights are streamed): every weight slab fetched from L2 feeds the MMAs of
         // both tiles, which halves the L2 -> smem weight traffic that otherwise bounds the 128/256-channel layers.
-        for (int tile = blockIdx.x; tile < ntiles; tile += C::TP * gridDim.x) {
-            const int np = (C::TP == 2 && tile + (int)gridDim.x < ntiles) ? 2 : 1;
+        for (int tile = blockIdx.x; tile < ntiles; tile += C::TSTEP * gridDim.x) {
+            // HILO_IN: the pair is (hi box, lo box) of the SAME tile and both halves feed one accumulator
+            const int np = C::HILO_IN ? 2 : ((C::TP == 2 && tile + (int)gridDim.x < ntiles) ? 2 : 1);
+            const int nacc = C::HILO_IN ? 1 : np; // accumulators of this pass
             uint32_t d_tmem[C::TP];
 #pragma unroll
             for (int h = 0; h < C::TP; h++) {
-                if (h < np) {
+                if (h < nacc) {
                     const uint32_t acc = (acc_it + h) % C::NACC;
                     mbar_wait(&accEmpty[acc], (((acc_it + h) / C::NACC) & 1) ^ 1);
                     d_tmem[h] = tmem_base + acc * C::ACC_COLS;
                 }
             }
+            if constexpr (C::HILO_IN) d_tmem[C::TP - 1] = d_tmem[0];
             tc_fence_after();
             // accumulator := bias  (ones[128 x 16] x biasB[COUT x 16]^T, hi + lo fp16 split => ~fp32-exact bias)
             if constexpr (!C::BIAS_REG) {
                 if (elect_one_sync()) {
 #pragma unroll
                     for (int h = 0; h < C::TP; h++)
-                        if (h < np) umma_f16(d_tmem[h], umma_desc_pack(ones_lo, b_hi), umma_desc_pack(bias_lo, b_hi), idesc, 0);
+                        if (h < nacc) umma_f16(d_tmem[h], umma_desc_pack(ones_lo, b_hi), umma_desc_pack(bias_lo, b_hi), idesc, 0);
                 }
             }
 #pragma unroll 1
@@ -435,7 +463,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
                                     for (int ks = 0; ks < C::G / 16; ks++)
                                         umma_f16(d_tmem[h], umma_desc_pack(a_tap + ks * (2 * C::A_LBO / 16), a_hi),
                                                  umma_desc_pack(b_lo0 + ks * (2 * C::COUT), b_hi), idesc,
-                                                 (C::BIAS_REG && tap == C::TAP0 && ks == 0) ? (uint32_t)(cg != 0) : 1u);
+                                                 (C::BIAS_REG && tap == C::TAP0 && ks == 0 && !(C::HILO_IN && h == 1)) ? (uint32_t)(cg != 0) : 1u);
                                 }
                             }
                             umma_commit(&emptyB[bs]);
@@ -498,10 +526,10 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
             if (elect_one_sync()) {
 #pragma unroll
                 for (int h = 0; h < C::TP; h++)
-                    if (h < np) umma_commit(&accFull[(acc_it + h) % C::NACC]);
+                    if (h < nacc) umma_commit(&accFull[(acc_it + h) % C::NACC]);
             }
             __syncwarp();
-            acc_it += np;
+            acc_it += nacc;
         }
     } else if (warp == C::W_BLOAD) {
         // ======================= weight loader (bulk copies on the TMA engine), one elected lane issues
@@ -518,7 +546,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
             }
         } else {
             uint32_t b_it = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += C::TP * gridDim.x) { // once per pass (pair of tiles)
+            for (int tile = blockIdx.x; tile < ntiles; tile += C::TSTEP * gridDim.x) { // once per pass (pair of tiles)
 #pragma unroll 1
                 for (int s = 0; s < C::NCG * C::NTAPS + C::NXS * C::XP; s++, b_it++) {
                     const uint32_t bs = b_it % C::NBS;
@@ -540,14 +568,15 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
         // stride-2 conv]; the halo / zero padding comes from the TMA out-of-bounds fill
         if (lane == 0) { tma_prefetch_desc(&p.in_map); if (C::XC > 0) tma_prefetch_desc(&p.x_map); }
         uint32_t a_it = 0;
-        for (int tile0 = blockIdx.x; tile0 < ((C::RESIDENT && (p.dbg & 8)) ? 0 : ntiles); tile0 += C::TP * gridDim.x) {
-            const int np = (C::TP == 2 && tile0 + (int)gridDim.x < ntiles) ? 2 : 1;
+        for (int tile0 = blockIdx.x; tile0 < ((C::RESIDENT && (p.dbg & 8)) ? 0 : ntiles); tile0 += C::TSTEP * gridDim.x) {
+            const int np = C::HILO_IN ? 2 : ((C::TP == 2 && tile0 + (int)gridDim.x < ntiles) ? 2 : 1);
             // stage order of a pass: (step 0, tile 0), (step 0, tile 1), (step 1, tile 0), ... -- what the MMA issuer consumes
 #pragma unroll 1
             for (int it = 0; it < C::NCG + C::NXS; it++) {
 #pragma unroll 1
                 for (int h = 0; h < np; h++, a_it++) {
-                    const int ltile = tile0 + h * (int)gridDim.x;
+                    const int ltile = C::HILO_IN ? tile0 : tile0 + h * (int)gridDim.x;
+                    const int part = C::HILO_IN ? h : 0; // 0 = hi tensor, 1 = lo tensor (stored right behind it: plane index + planes)
                     const int tile = p.reverse ? ntiles - 1 - ltile : ltile;
                     int unit, oy0, ox0;
                     if constexpr (C::NB != 1 || C::FLAT) { unit = tile; oy0 = 0; ox0 = 0; }
@@ -574,17 +603,17 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
                             // strip layout: the image index is a box coordinate (first image of the tile), the last one the plane
                             const int ci = C::STRIP ? unit * C::NB : 0;
                             if constexpr (C::STRIDE == 1) {
-                                tma_load_5d(abase, &p.in_map, (ox0 - C::HALO) * 8, ci, oy0 - C::HALO, it * C::CH, C::STRIP ? 0 : unit, &fullA[st]);
+                                tma_load_5d(abase, &p.in_map, (ox0 - C::HALO) * 8, ci, oy0 - C::HALO, it * C::CH, C::STRIP ? part : unit, &fullA[st]);
                             } else {
 #pragma unroll
                                 for (int pl = 0; pl < 4; pl++)
                                     tma_load_5d(abase + pl * C::PLANE_STRIDE, &p.in_map, (ox0 - (pl & 1)) * 8, ci, oy0 - (pl >> 1),
-                                                it * C::CH, C::STRIP ? pl : unit * 4 + pl, &fullA[st]);
+                                                it * C::CH, C::STRIP ? pl + 4 * part : unit * 4 + pl, &fullA[st]);
                             }
                         } else {
                             mbar_arrive_expect_tx(&fullA[st], C::X_STAGE_BYTES);
                             tma_load_5d(abase, &p.x_map, ox0 * 8, C::STRIP ? unit * C::NB : 0, oy0, (it - C::NCG) * (C::GX / 8),
-                                        C::STRIP ? 0 : unit * p.x_unit_mul, &fullA[st]);
+                                        C::STRIP ? part * p.x_unit_mul : unit * p.x_unit_mul, &fullA[st]);
                         }
                     }
                     __syncwarp();

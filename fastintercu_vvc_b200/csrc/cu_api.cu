@@ -154,6 +154,7 @@ int run_network(mlt_cu_ctx *c, int n, const int16_t *d_orgpred, const int32_t *d
         const int a = 4 * (i + 1) + 4; // output of layer(i+1).1.conv2 = conv 4 * (i + 1) + 3
         hp.act[i] = c->act[a];
         hp.lay[i] = c->lay[a];
+        hp.hilo[i] = c->info[a - 1].hilo_out;
         hp.gap_part[i] = c->gap_part[i];
         hp.gap_count[i] = c->info[a - 1].gap_count;
         hp.fc_w[i] = secp<float>(c, SEC_FC_W + i);
@@ -275,7 +276,8 @@ int mlt_cu_create(mlt_cu_ctx **out, const char *weights_path, int cuda_device, i
         c->lay[0] = ActLayout{cu_size, 32, 1, 0, c->cap};
         for (int li = 0; li < CU_NCONV; li++) c->lay[li + 1] = ActLayout{c->info[li].hout, c->info[li].cout, c->info[li].out_par, 0, c->cap};
         for (int a = 0; a < CU_NACT; a++) {
-            const size_t bytes = c->lay[a].unit_elems() * sizeof(__half);
+            const bool hilo = a >= 1 && c->info[a - 1].hilo_out; // lo tensor right behind the hi tensor
+            const size_t bytes = c->lay[a].unit_elems() * sizeof(__half) * (hilo ? 2 : 1);
             CU(cudaMalloc(&c->act[a], bytes));
             CU(cudaMemsetAsync(c->act[a], 0, bytes, c->stream)); // images beyond a batch's n are read by the last tile: keep them finite
         }

@@ -56,6 +56,16 @@ __global__ void __launch_bounds__(NT) cu_head_kernel(const CuHeadParams p)
                         s[2 * e] += t.x;
                         s[2 * e + 1] += t.y;
                     }
+                    if (p.hilo[h]) { // fp16 hi + lo pair: the lo tensor sits one whole tensor further on
+                        const uint4 w = __ldg(reinterpret_cast<const uint4 *>(p.act[h] + L.unit_elems() + off));
+                        const __half2 *l2 = reinterpret_cast<const __half2 *>(&w);
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            const float2 t = __half22float2(l2[e]);
+                            s[2 * e] += t.x;
+                            s[2 * e + 1] += t.y;
+                        }
+                    }
                 }
 #pragma unroll
                 for (int e = 0; e < 8; e++) f[cj * 8 + e] = s[e] * inv;

@@ -25,7 +25,9 @@ struct CuSel {
     static constexpr int XLO = K == 1 ? 1 : 0;
     static constexpr int OUT_PAR = (K == 3 && L < 4 && H >= 2) ? 1 : 0; // feeds the next stage's stride-2 block
     static constexpr int X_PAR = (K == 1 && !FAKE_S2) ? 1 : 0;          // shortcut input = plane (even, even) of the stage input
-    using type = ConvCfg<CIN, P, STRIDE, H, XC, OUT_PAR, XLO, 1>;
+    // the last two stages (and the tensor that feeds them) carry fp16 hi + lo activation pairs (ConvCfg::HILO_*)
+    static constexpr int HILO_OUT = LI >= CU_HILO_FROM - 1 ? 1 : 0, HILO_IN = LI >= CU_HILO_FROM ? 1 : 0;
+    using type = ConvCfg<CIN, P, STRIDE, H, XC, OUT_PAR, XLO, 1 | (HILO_IN << 1) | (HILO_OUT << 2)>;
 };
 
 template <int S, int LI = 0, class F>
@@ -57,7 +59,7 @@ struct CuNetOps {
         return cu_dispatch<S>(li, [o](auto sel) {
             using C = typename decltype(sel)::type;
             *o = CuLayerInfo{C::CIN, C::COUT, C::STRIDE, C::HOUT, C::XC, C::OUT_PAR, C::NB, C::FLAT ? 1 : 0, C::G, C::XC > 0 ? C::GX : 0,
-                             C::GAP ? (C::NB == 2 ? 4 : C::TILES_PER_IMG * 4) : 0};
+                             C::GAP ? (C::NB == 2 ? 4 : C::TILES_PER_IMG * 4) : 0, C::HILO_OUT ? 1 : 0};
             return cudaSuccess;
         });
     }
@@ -67,16 +69,16 @@ struct CuNetOps {
             using Sel = decltype(sel);
             using C = typename Sel::type;
             if (in_l.strip <= 0 || in_l.C != C::CIN || in_l.H != C::HOUT * C::STRIDE || in_l.par != (C::STRIDE == 2)) return cudaErrorInvalidValue;
-            cudaError_t e = make_act_map(&p->in_map, in, in_l, 1, C::BLKW, C::NB, C::PROWS, C::CH);
+            cudaError_t e = make_act_map(&p->in_map, in, in_l, C::HILO_IN ? 2 : 1, C::BLKW, C::NB, C::PROWS, C::CH);
             if (e != cudaSuccess) return e;
             if constexpr (C::XC > 0) {
                 if (!x || !x_l || x_l->strip != in_l.strip || x_l->C != C::XC || x_l->hp() != C::HOUT || x_l->par != Sel::X_PAR) return cudaErrorInvalidValue;
-                e = make_act_map(&p->x_map, x, *x_l, 1, C::XBOXW, C::NB, C::TR, C::GX / 8);
+                e = make_act_map(&p->x_map, x, *x_l, C::HILO_IN ? 2 : 1, C::XBOXW, C::NB, C::TR, C::GX / 8);
                 if (e != cudaSuccess) return e;
             } else {
                 p->x_map = p->in_map;
             }
-            p->x_unit_mul = 1;
+            p->x_unit_mul = (C::XC > 0 && x_l) ? x_l->npl() : 1; // planes between the hi and the lo copy of the extra operand
             p->strip_cap = in_l.strip;
             return cudaSuccess;
         });

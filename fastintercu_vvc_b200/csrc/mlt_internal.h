@@ -114,10 +114,12 @@ cudaError_t make_act_map(CUtensorMap *tm, const __half *base, const ActLayout &L
 
 // ---- cu_net_*.cu / cu_stem.cu / cu_head.cu : the smaller-CU networks (64 / 32 / 16-px GapBigMltCuORPQ, mlt_cu_or_pq_arch.py:59-130)
 constexpr int CU_NCONV = 20, CU_NACT = 21, CU_NHEAD = 4, CU_NLOGIT = 15;
+constexpr int CU_HILO_FROM = 12; // convs >= 12 (layer3, layer4) read fp16 hi + lo activation pairs; conv 11 is the first to write one
 struct CuLayerInfo { // one 3x3 conv of the CU network at a given CU size (forward order, after conv1)
     int cin, cout, stride, hout, xc, out_par, nb, flat; // stride as executed (a stride-2 conv on a 1x1 map runs as stride 1)
     int g, gx;                                          // channels per weight slab of the main / extra operand (packer layout)
     int gap_count;                                      // pool partial vectors per image its epilogue writes (0: none)
+    int hilo_out;                                       // writes an fp16 hi + lo pair (lo tensor right behind the hi tensor)
 };
 cudaError_t cu_conv_init(int size);                    // opt in to large dynamic shared memory for this size's kernels
 cudaError_t cu_conv_info(int size, int layer, CuLayerInfo *info);
@@ -129,6 +131,7 @@ cudaError_t launch_cu_conv1(int size, const CtuDev *cus, int n, const __half *wo
 struct CuHeadParams {
     const __half *act[CU_NHEAD]; // outputs of layer1..layer4 (strip layouts)
     ActLayout lay[CU_NHEAD];
+    int hilo[CU_NHEAD];              // the stored activation is an fp16 hi + lo pair
     const float *gap_part[CU_NHEAD]; // maps >= 8x8: fp32 pool partial sums written by that conv's epilogue [image][gap_count][C], else nullptr
     int gap_count[CU_NHEAD];
     const float *fc_w[CU_NHEAD]; // [out][in]
