@@ -154,6 +154,40 @@ def cpu_reference_rate(budget_s: float, threads: int | None = None):
     return n / dt, torch.get_num_threads(), n, dt
 
 
+def cpu_reference_variants(budget_s: float = 3.0):
+    """The other two CPU figures SURVEY.md section 8d asks for: (ii) the hook AS WRITTEN -- torch::jit::load of the TorchScript
+    file on every call (EncCu.cpp:894-900) -- and a B = 120 frame batch through the same module (not something the
+    reference does; the best case for the CPU)."""
+    import torch
+
+    from oracle import ref_arch
+
+    torch.set_num_threads(len(os.sched_getaffinity(0)))
+    net = ref_arch.build_model(ref_arch.make_state_dict(10))
+    traced = torch.jit.trace(net, (torch.rand(1, 2, 128, 128), torch.rand(1), torch.rand(1)))
+    path = tempfile.NamedTemporaryFile(suffix=".pt", delete=False).name
+    traced.save(path)
+    orgpred, pocqp = ref_arch.synth_ctus(CTUS_PER_FRAME, 10)
+    x = torch.from_numpy(ref_arch.stage_numpy(orgpred))
+    poc, qp = torch.from_numpy(pocqp[:, 0].copy()), torch.from_numpy(pocqp[:, 1].copy())
+    with torch.no_grad():
+        n, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < budget_s or n < 3:
+            m = torch.jit.load(path)
+            m.eval()
+            m(x[n % 120 : n % 120 + 1], poc[n % 120 : n % 120 + 1], qp[n % 120 : n % 120 + 1])
+            n += 1
+        as_written = n / (time.perf_counter() - t0)
+        traced(x, poc, qp)
+        k, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < budget_s or k < 2:
+            traced(x, poc, qp)
+            k += 1
+        b120 = k * CTUS_PER_FRAME / (time.perf_counter() - t0)
+    os.unlink(path)
+    return as_written, b120
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -503,8 +537,11 @@ def main():
                                          f"{args.cu_frames} 1080p frames per step, device-resident and host-buffer (e2e) CUs/s")
         if not args.no_cpu_baseline and world == 1:
             r, cores, cn, cdt = cpu_reference_rate(args.cpu_budget)
+            aw, b120 = cpu_reference_variants(3.0)
             line["cpu_baseline"] = {"value": r, "unit": "CTU/s", "cores": cores, "kind": "port",
-                                    "sample": f"{cn} CTUs at B=1 through traced TorchScript (torch CPU fp32 = libtorch) in {cdt:.1f}s"}
+                                    "sample": f"{cn} CTUs at B=1 through traced TorchScript (torch CPU fp32 = libtorch) in {cdt:.1f}s",
+                                    "as_written_load_per_call": aw, "b120_frame_batch": b120,
+                                    "variants_note": "as_written = torch.jit.load on every call like EncCu.cpp:894-900; b120 = one 120-CTU frame per forward (CTU/s)"}
         print(json.dumps(line))
     pred.close()
     if world > 1:
