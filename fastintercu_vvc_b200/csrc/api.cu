@@ -17,7 +17,8 @@ namespace {
 constexpr uint32_t MLTW_MAGIC = 0x57544C4Du;
 enum : uint32_t {
     SEC_CONV1_F32 = 0x001, SEC_CONV1_UMMA = 0x002, SEC_STEM_CONV1 = 0x003, SEC_W_F16 = 0x100, SEC_BIAS_FUSED = 0x200, SEC_W_F32 = 0x300, SEC_BIAS = 0x400,
-    SEC_SC_W_F16 = 0x500, SEC_SC_W_F32 = 0x600, SEC_SC_BIAS = 0x700, SEC_FC_W = 0x800, SEC_FC_B = 0x900, SEC_BIAS_MMA = 0xA00, SEC_X_W_F16 = 0xB00
+    SEC_SC_W_F16 = 0x500, SEC_SC_W_F32 = 0x600, SEC_SC_BIAS = 0x700, SEC_FC_W = 0x800, SEC_FC_B = 0x900, SEC_BIAS_MMA = 0xA00, SEC_X_W_F16 = 0xB00,
+    SEC_W_SPLIT = 0xC00, SEC_X_SPLIT = 0xD00 // layer3 weights packed for the channel-split kernels
 };
 
 constexpr int NCONV = 16, NACT = 17, CTU = MLT_CTU_SIZE;
@@ -68,6 +69,7 @@ struct mlt_ctx {
         __half *act_h[NACT] = {}; // [0] (conv1's full output, parity-planar) exists only for the unfused engine / debug reads
         __half *act0q = nullptr;  // conv1's output at even rows / columns (input of layer0.0's shortcut), dense [n][4][64][64][8]
         ConvParams conv_p[NCONV]; // tensor maps + weight pointers of every tcgen05 conv, built once at create
+        ConvParams conv_split[NCONV]; // layer3 again for the channel-split kernels (small batches): split-packed weights
         float *gap_part[3] = {};  // pool partial sums written by convs 7 / 11 / 15: [cap][8 | 2 | 1 tiles][4][64 | 128 | 256]
         int cap = 0;              // images
     } set[2];
@@ -163,9 +165,11 @@ int load_blob(mlt_ctx *c, const char *path)
         ok = need(SEC_W_F16 + li, (size_t)9 * L.cin * L.cout * 2) && need(SEC_W_F32 + li, (size_t)9 * L.cin * L.cout * 4) &&
              need(SEC_BIAS + li, (size_t)L.cout * 4) && need(SEC_BIAS_FUSED + li, (size_t)L.cout * 4) &&
              need(SEC_BIAS_MMA + li, (size_t)L.cout * 32);
+        if (ok && li >= CONV_SPLIT_FIRST) ok = need(SEC_W_SPLIT + li, (size_t)9 * L.cin * L.cout * 2);
         if (ok && (li & 1)) { // second conv of a block: extra operand = shortcut conv (first block) or identity
             const int xc = L.sc >= 0 ? kLayers[li - 1].cin : L.cout;
             ok = need(SEC_X_W_F16 + li, (size_t)xc * L.cout * 2 * (L.sc >= 0 ? 2 : 1)); // shortcut weights: hi + lo
+            if (ok && li >= CONV_SPLIT_FIRST) ok = need(SEC_X_SPLIT + li, (size_t)xc * L.cout * 2 * (L.sc >= 0 ? 2 : 1));
         }
         if (ok && L.sc >= 0) {
             const int csc = kLayers[li - 1].cin;
@@ -272,7 +276,15 @@ int run_network(mlt_ctx *c, const CtuDev *ctus, int n, mlt_result *out, cudaStre
                 CU(cudaMemsetAsync(d_trace, 0, 1024 * sizeof(long long), s));
                 p.trace = d_trace;
             }
-            CU(launch_conv_umma(li, p, c->num_sms, s));
+            // layer3 on a small batch (fewer tiles than half the SMs): 256 output channels split over 4 CTAs per tile
+            static const bool no_split = getenv("MLT_NO_SPLIT") != nullptr; // A/B switch for measurements
+            const bool split = li >= CONV_SPLIT_FIRST && !no_split && (n + 1) / 2 * 2 <= c->num_sms && li != trace_layer;
+            if (split) {
+                ConvParams &q = S.conv_split[li];
+                q.nimg = n;
+                CU(launch_conv_umma(li + CONV_SPLIT_OFFSET, q, c->num_sms, s));
+            } else
+                CU(launch_conv_umma(li, p, c->num_sms, s));
             if (li == trace_layer && getenv("MLT_TRACE_DUMP")) {
                 static long long h[1024];
                 CU(cudaStreamSynchronize(s));
@@ -548,6 +560,11 @@ int mlt_create_ex(mlt_ctx **out, const char *weights_path, int cuda_device, int 
                 p.relu = 1;
                 p.dbg = getenv("MLT_DEBUG_FLAGS") ? atoi(getenv("MLT_DEBUG_FLAGS")) : 0;
                 p.reverse = getenv("MLT_NO_REVERSE") ? 0 : (li & 1); // the stem walks the images upwards, conv 1 downwards, conv 2 upwards, ...
+                if (li >= CONV_SPLIT_FIRST) {
+                    S.conv_split[li] = p;
+                    S.conv_split[li].w = secp<__half>(c, SEC_W_SPLIT + li);
+                    S.conv_split[li].x_w = conv2 ? secp<__half>(c, SEC_X_SPLIT + li) : nullptr;
+                }
             }
         }
         CU(cudaStreamSynchronize(c->stream));

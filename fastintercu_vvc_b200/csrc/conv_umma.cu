@@ -24,6 +24,11 @@ using L3a = ConvCfg<128, 256, 2, 8, 0, 0>;    // layer3.0.conv1
 using L3b = ConvCfg<256, 256, 1, 8, 128, 0, 1>; // layer3.0.conv2 + shortcut
 using L3c = ConvCfg<256, 256, 1, 8, 0, 0>;    // layer3.1.conv1
 using L3d = ConvCfg<256, 256, 1, 8, 256, 0>;  // layer3.1.conv2 + identity
+// small batches (fewer tiles than SMs): the same four layers with the 256 output channels split over 4 CTAs ("layers" 16..19)
+using L3aS = ConvCfg<128, 256, 2, 8, 0, 0, 0, 0, 4>;
+using L3bS = ConvCfg<256, 256, 1, 8, 128, 0, 1, 0, 4>;
+using L3cS = ConvCfg<256, 256, 1, 8, 0, 0, 0, 0, 4>;
+using L3dS = ConvCfg<256, 256, 1, 8, 256, 0, 0, 0, 4>;
 
 #define MLT_FOR_LAYER(li, F)                                                                                            \
     switch (li) {                                                                                                       \
@@ -31,6 +36,7 @@ using L3d = ConvCfg<256, 256, 1, 8, 256, 0>;  // layer3.1.conv2 + identity
     case 4: F(L1a); break;  case 5: F(L1b); break;  case 6: F(L1c); break;  case 7: F(L1d); break;                      \
     case 8: F(L2a); break;  case 9: F(L2b); break;  case 10: F(L2c); break; case 11: F(L2d); break;                     \
     case 12: F(L3a); break; case 13: F(L3b); break; case 14: F(L3c); break; case 15: F(L3d); break;                     \
+    case 16: F(L3aS); break; case 17: F(L3bS); break; case 18: F(L3cS); break; case 19: F(L3dS); break;                 \
     default: return cudaErrorInvalidValue;                                                                              \
     }
 
@@ -44,7 +50,7 @@ cudaError_t conv_umma_init()
 {
     cudaError_t e;
 #define MLT_INIT(C) if ((e = cudaFuncSetAttribute(conv_umma_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES)) != cudaSuccess) return e
-    for (int li = 0; li < 16; li++) { MLT_FOR_LAYER(li, MLT_INIT) }
+    for (int li = 0; li < 20; li++) { MLT_FOR_LAYER(li, MLT_INIT) }
 #undef MLT_INIT
     if (!g_encode) {
         cudaDriverEntryPointQueryResult q;
@@ -109,7 +115,8 @@ ActLayout conv_umma_out_layout(int layer)
     case 0: MLT_OUT(L0a); break;  case 1: MLT_OUT(L0b); break;  case 2: MLT_OUT(L0c); break;  case 3: MLT_OUT(L0d); break;
     case 4: MLT_OUT(L1a); break;  case 5: MLT_OUT(L1b); break;  case 6: MLT_OUT(L1c); break;  case 7: MLT_OUT(L1d); break;
     case 8: MLT_OUT(L2a); break;  case 9: MLT_OUT(L2b); break;  case 10: MLT_OUT(L2c); break; case 11: MLT_OUT(L2d); break;
-    case 12: MLT_OUT(L3a); break; case 13: MLT_OUT(L3b); break; case 14: MLT_OUT(L3c); break; case 15: MLT_OUT(L3d); break;
+    case 12: case 16: MLT_OUT(L3a); break; case 13: case 17: MLT_OUT(L3b); break; case 14: case 18: MLT_OUT(L3c); break;
+    case 15: case 19: MLT_OUT(L3d); break;
     default: break;
     }
 #undef MLT_OUT
@@ -121,7 +128,8 @@ static cudaError_t launch_one(const ConvParams &p, int num_sms, cudaStream_t s)
 {
     const int ntiles = C::num_tiles(p.nimg);
     if (ntiles <= 0) return cudaSuccess;
-    const int grid = ntiles < num_sms ? ntiles : num_sms; // persistent: one CTA per SM
+    // persistent: one CTA per SM (channel-split layers: a multiple of the split, so that the tile pair of a pass shares weights)
+    const int grid = ntiles < num_sms ? ntiles : num_sms / C::NSPLIT * C::NSPLIT;
     return launch_pdl(conv_umma_kernel<C>, dim3(grid), dim3(C::NTHREADS), C::SMEM_BYTES, s, p);
 }
 

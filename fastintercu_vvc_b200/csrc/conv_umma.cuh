@@ -39,9 +39,17 @@ namespace mlt {
 // CONSECUTIVE 16-byte positions (SBO = 128 B), tap (kh, kw) is again just a start-address shift, and the accumulator
 // rows that land on halo positions (x >= HOUT) are simply not stored -- M efficiency HOUT / (HOUT + 2), on < 15 % of
 // the network's FLOPs.
-template <int CIN_, int COUT_, int STRIDE_, int HOUT_, int XC_, int OUT_PAR_, int XLO_ = 0, int FLAGS_ = 0>
+// NSPLIT_ > 1 (small batches of the CTU network's last stage): a tile's COUT output channels are split over NSPLIT CTAs
+// ("items" = tile x split).  With fewer tiles than SMs every CTA otherwise streams the whole layer's weights (1.2 MB for
+// 256 -> 256) through one SM and issues all of the tile's MMAs alone; split four ways each CTA streams a quarter
+// ([split][cin_group][tap][G/8][NC][8], packed offline) and the four run on different SMs.  Per output element the MMA
+// sequence is unchanged, so results are bit-identical to the unsplit kernel.  Measured: 22 -> 19 us per layer at n = 1
+// (a deeper slab ring changes nothing: what remains is the per-slab issue loop, 72 iterations of wait / 2 MMAs / commit,
+// and ~8 us of launch + prologue + drain per kernel), single-CTU hook latency 177 -> 162 us.
+template <int CIN_, int COUT_, int STRIDE_, int HOUT_, int XC_, int OUT_PAR_, int XLO_ = 0, int FLAGS_ = 0, int NSPLIT_ = 1>
 struct ConvCfg {
     static constexpr int CIN = CIN_, COUT = COUT_, STRIDE = STRIDE_, HOUT = HOUT_, XC = XC_, OUT_PAR = OUT_PAR_;
+    static constexpr int NSPLIT = NSPLIT_, NC = COUT / NSPLIT; // output channels per CTA = GEMM N
     static constexpr bool STRIP = (FLAGS_ & 1) != 0;
     static constexpr bool FLAT = STRIP && HOUT <= 4;
     // FLAGS_ bits 1 / 2 (HILO_IN / HILO_OUT): the last two stages of the CU networks keep their activations as an fp16
@@ -84,10 +92,10 @@ struct ConvCfg {
     static constexpr int X_LBO = FLAT ? TR * PITCH * 16 : 128 * 16, X_SBO = 128;
     static constexpr int X_STAGE_BYTES = (GX / 8) * X_LBO;
     static constexpr int A_STAGE_BYTES = ((A_MAIN_BYTES > X_STAGE_BYTES ? A_MAIN_BYTES : X_STAGE_BYTES) + 127) / 128 * 128;
-    static constexpr int SLAB_BYTES = G * COUT * 2; // one (cin_group, tap) weight slab
-    static constexpr int X_SLAB_BYTES = GX * COUT * 2;
+    static constexpr int SLAB_BYTES = G * NC * 2; // one (cin_group, tap) weight slab
+    static constexpr int X_SLAB_BYTES = GX * NC * 2;
     static constexpr int W_MAIN_BYTES = NCG * 9 * SLAB_BYTES;
-    static constexpr int W_X_BYTES = XC * COUT * 2 * XP;
+    static constexpr int W_X_BYTES = XC * NC * 2 * XP;
     static constexpr bool RESIDENT = (W_MAIN_BYTES + W_X_BYTES) <= 84 * 1024 && !FLAT; // (FLAT: several cin groups -> streamed path)
     // weight-slab ring: deep enough that ring depth x MMA time per slab covers the ~2500-cycle L2 -> smem latency of a
     // bulk copy (one slab feeds G/16 MMAs of max(N/2, 32 + N/4) cycles), leaving room for >= MIN_NAS activation stages
@@ -112,8 +120,8 @@ struct ConvCfg {
     static constexpr int SPT_ = 1 + NXS; // A stages per tile
     static constexpr int NAS = !RESIDENT ? NAS_RAW : NAS_RAW / 2 * 2;
     static constexpr int NAS_HALF = NAS / 2;
-    static constexpr int NACC = (COUT <= 128) ? 4 : 2; // TMEM accumulator stages (NACC * ACC_COLS <= 512 columns)
-    static constexpr int ACC_COLS = (COUT == 96) ? 128 : COUT; // accumulator pitch in TMEM columns (power of two)
+    static constexpr int NACC = (NC <= 128) ? 4 : 2; // TMEM accumulator stages (NACC * ACC_COLS <= 512 columns)
+    static constexpr int ACC_COLS = (NC == 96) ? 128 : NC; // accumulator pitch in TMEM columns (power of two)
     // bias: for the smem-operand-bound 32/64-channel layers it is added in the epilogue from registers (an extra MMA
     // would cost 5 % / 3 % of the tile); for 128/256 channels it enters the accumulator through one K=16 MMA
     static constexpr bool BIAS_REG = COUT <= 64;
@@ -150,11 +158,12 @@ struct ConvCfg {
     static_assert(!FLAT || (TR * PITCH <= 128 && NB >= 1 && NB <= 256), "flat tile must fit the 128 accumulator rows");
     static_assert(!CENTER_ONLY || !RESIDENT, "centre-tap layers use the streamed-weight path");
     static_assert(!HILO_IN || (!RESIDENT && STRIP), "hi+lo inputs ride on the tile-pair structure of the streamed-weight path");
+    static_assert(NSPLIT == 1 || (!RESIDENT && !BIAS_REG && NC % 32 == 0 && !HILO_IN), "channel split: streamed-weight layers with the bias MMA");
     static constexpr int TSTEP = HILO_IN ? 1 : TP; // tiles per pass
     static_assert(STRIP || (HOUT >= 8 && COUT != 96), "the CTU network has no small maps");
     static_assert(BLKW * 8 <= 256 && PROWS <= 256, "TMA box extents");
 
-    __host__ __device__ static int num_tiles(int nimg) { return (NB != 1 || FLAT) ? (nimg + NB - 1) / NB : nimg * TILES_PER_IMG; }
+    __host__ __device__ static int num_tiles(int nimg) { return ((NB != 1 || FLAT) ? (nimg + NB - 1) / NB : nimg * TILES_PER_IMG) * NSPLIT; } // work items
 };
 
 // offset (in 16-byte units) of tap (kh, kw) inside the A stage
@@ -223,7 +232,8 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
         for (int tile = blockIdx.x + grp * gridDim.x; tile < ((C::RESIDENT && (p.dbg & 8)) ? 0 : ntiles); tile += 2 * gridDim.x, acc_it += 2) {
             // p.reverse: this layer walks the images in the opposite direction to the previous one, so that it starts on
             // the activations the previous kernel wrote last (still in the 126 MB L2) -- consecutive layers zig-zag
-            const int ptile = p.reverse ? ntiles - 1 - tile : tile;
+            const int pitem = p.reverse ? ntiles - 1 - tile : tile;
+            const int ptile = pitem / C::NSPLIT, n0 = (pitem % C::NSPLIT) * C::NC; // tile and first output channel of this item
             int img, oy, ox;
             if constexpr (C::NB != 1 || C::FLAT) { img = ptile * C::NB + h; oy = r; ox = c; }
             else {
@@ -245,7 +255,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
             mbar_wait(&accFull[acc], (acc_it / C::NACC) & 1);
             tc_fence_after();
 #pragma unroll(C::BIAS_REG ? 2 : 1)
-            for (int c0 = 0; c0 < ((p.dbg & 4) ? 0 : C::COUT); c0 += 32) {
+            for (int c0 = 0; c0 < ((p.dbg & 4) ? 0 : C::NC); c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + acc * C::ACC_COLS + c0, v);
                 tmem_ld_wait();
@@ -261,7 +271,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
                     hq[e] = p.relu ? __hmax2(t, zero2) : t; // max(round(x), 0) == round(max(x, 0))
                 }
                 if (valid) {
-                    __half *op = p.out + off + (size_t)(c0 / 8) * ochunk;
+                    __half *op = p.out + off + (size_t)((n0 + c0) / 8) * ochunk;
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
                         uint4 ov;
@@ -306,7 +316,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
                             }
                         }
                     };
-                    float *gp = p.gap_part + ((size_t)(ptile * C::NB + h) * 4 + wq) * C::COUT + c0;
+                    float *gp = p.gap_part + ((size_t)(ptile * C::NB + h) * 4 + wq) * C::COUT + n0 + c0;
                     if constexpr (C::NB == 1) {
                         fold(16, 16); fold(8, 8); fold(4, 4); fold(2, 2); fold(1, 1);
                         gp[lane] = gv[0]; // channel bits == lane bits
@@ -323,7 +333,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
     } else if (warp == C::W_MMA || (C::RESIDENT && warp == C::W_MMA2)) {
         // ======================= MMA issuer: the whole warp runs the (uniform) control flow and the waits,
         // one elected lane issues tcgen05.mma / tcgen05.commit
-        constexpr uint32_t idesc = umma_idesc_f16(128, C::COUT);
+        constexpr uint32_t idesc = umma_idesc_f16(128, C::NC);
         constexpr uint32_t a_hi = umma_desc_hi(C::A_SBO), b_hi = umma_desc_hi(128), x_hi = umma_desc_hi(C::X_SBO);
         const uint32_t ones_lo = umma_desc_lo(smem_u32(smem + C::OFF_ONES), 128 * 16);
         const uint32_t bias_lo = umma_desc_lo(smem_u32(smem + C::OFF_BIAS), C::COUT * 16);
@@ -414,9 +424,11 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
             // accumulator := bias  (ones[128 x 16] x biasB[COUT x 16]^T, hi + lo fp16 split => ~fp32-exact bias)
             if constexpr (!C::BIAS_REG) {
                 if (elect_one_sync()) {
+                    // (channel split: this pass's rows [split * NC, + NC) of the bias operand, 16 B per row)
+                    const uint32_t bias_n0 = (uint32_t)(((p.reverse ? ntiles - 1 - tile : tile) % C::NSPLIT) * C::NC);
 #pragma unroll
                     for (int h = 0; h < C::TP; h++)
-                        if (h < nacc) umma_f16(d_tmem[h], umma_desc_pack(ones_lo, b_hi), umma_desc_pack(bias_lo, b_hi), idesc, 0);
+                        if (h < nacc) umma_f16(d_tmem[h], umma_desc_pack(ones_lo, b_hi), umma_desc_pack(bias_lo + bias_n0, b_hi), idesc, 0);
                 }
             }
 #pragma unroll 1
@@ -454,7 +466,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
                         mbar_wait(&fullB[bs], (b_it / C::NBS) & 1);
                         tc_fence_after();
                         if (elect_one_sync()) {
-                            const uint32_t b_lo0 = umma_desc_lo(sB + bs * C::SLAB_BYTES, C::COUT * 16);
+                            const uint32_t b_lo0 = umma_desc_lo(sB + bs * C::SLAB_BYTES, C::NC * 16);
 #pragma unroll
                             for (int h = 0; h < C::TP; h++) {
                                 if (h < np) {
@@ -462,7 +474,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
 #pragma unroll
                                     for (int ks = 0; ks < C::G / 16; ks++)
                                         umma_f16(d_tmem[h], umma_desc_pack(a_tap + ks * (2 * C::A_LBO / 16), a_hi),
-                                                 umma_desc_pack(b_lo0 + ks * (2 * C::COUT), b_hi), idesc,
+                                                 umma_desc_pack(b_lo0 + ks * (2 * C::NC), b_hi), idesc,
                                                  (C::BIAS_REG && tap == C::TAP0 && ks == 0 && !(C::HILO_IN && h == 1)) ? (uint32_t)(cg != 0) : 1u);
                                 }
                             }
@@ -502,14 +514,14 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
                         }
                         if (elect_one_sync()) {
                             const uint32_t b_lo0 = C::RESIDENT ? umma_desc_lo(sB + C::W_MAIN_BYTES + (xs * C::XP + part) * C::X_SLAB_BYTES, C::COUT * 16)
-                                                               : umma_desc_lo(sB + bs * C::SLAB_BYTES, C::COUT * 16);
+                                                               : umma_desc_lo(sB + bs * C::SLAB_BYTES, C::NC * 16);
 #pragma unroll
                             for (int h = 0; h < C::TP; h++) {
                                 if (h < np) {
 #pragma unroll
                                     for (int ks = 0; ks < C::GX / 16; ks++)
                                         umma_f16(d_tmem[h], umma_desc_pack(a_lo0[h] + ks * (2 * C::X_LBO / 16), x_hi),
-                                                 umma_desc_pack(b_lo0 + ks * (2 * C::COUT), b_hi), idesc, 1);
+                                                 umma_desc_pack(b_lo0 + ks * (2 * C::NC), b_hi), idesc, 1);
                                 }
                             }
                             if constexpr (!C::RESIDENT) umma_commit(&emptyB[bs]);
@@ -547,6 +559,10 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
         } else {
             uint32_t b_it = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += C::TSTEP * gridDim.x) { // once per pass (pair of tiles)
+                // channel split: the weights are packed [split][cin_group][tap]... / [split][x slab]...
+                const int split = (p.reverse ? ntiles - 1 - tile : tile) % C::NSPLIT;
+                const uint8_t *gws = gw + (size_t)split * (C::NCG * 9 * C::SLAB_BYTES);
+                const uint8_t *gxs = gx + (size_t)split * (C::NXS * C::XP * C::X_SLAB_BYTES);
 #pragma unroll 1
                 for (int s = 0; s < C::NCG * C::NTAPS + C::NXS * C::XP; s++, b_it++) {
                     const uint32_t bs = b_it % C::NBS;
@@ -555,8 +571,8 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
                         const bool is_x = s >= C::NCG * C::NTAPS;
                         const uint32_t bytes = is_x ? C::X_SLAB_BYTES : C::SLAB_BYTES;
                         // packed [cin_group][9 taps]: slab (s / NTAPS) * 9 + TAP0 + s % NTAPS
-                        const uint8_t *src = is_x ? gx + (size_t)(s - C::NCG * C::NTAPS) * C::X_SLAB_BYTES
-                                                  : gw + (size_t)((s / C::NTAPS) * 9 + C::TAP0 + s % C::NTAPS) * C::SLAB_BYTES;
+                        const uint8_t *src = is_x ? gxs + (size_t)(s - C::NCG * C::NTAPS) * C::X_SLAB_BYTES
+                                                  : gws + (size_t)((s / C::NTAPS) * 9 + C::TAP0 + s % C::NTAPS) * C::SLAB_BYTES;
                         mbar_arrive_expect_tx(&fullB[bs], bytes);
                         bulk_g2s(sB + bs * C::SLAB_BYTES, src, bytes, &fullB[bs]);
                     }
@@ -577,7 +593,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
                 for (int h = 0; h < np; h++, a_it++) {
                     const int ltile = C::HILO_IN ? tile0 : tile0 + h * (int)gridDim.x;
                     const int part = C::HILO_IN ? h : 0; // 0 = hi tensor, 1 = lo tensor (stored right behind it: plane index + planes)
-                    const int tile = p.reverse ? ntiles - 1 - ltile : ltile;
+                    const int tile = (p.reverse ? ntiles - 1 - ltile : ltile) / C::NSPLIT;
                     int unit, oy0, ox0;
                     if constexpr (C::NB != 1 || C::FLAT) { unit = tile; oy0 = 0; ox0 = 0; }
                     else {

@@ -108,6 +108,9 @@ ActLayout conv_umma_out_layout(int layer); // layout of the activation conv `lay
 cudaError_t conv_umma_prepare(int layer, ConvParams *p, const __half *in, const ActLayout &in_l, const __half *x, const ActLayout *x_l,
                               size_t images);
 cudaError_t launch_conv_umma(int layer, const ConvParams &p, int num_sms, cudaStream_t s);
+// layers 12..15 (layer3) also exist with their 256 output channels split over 4 CTAs, as "layers" 16..19: used when a
+// batch has fewer tiles than SMs (p.w / p.x_w then point at the split-packed weights)
+constexpr int CONV_SPLIT_FIRST = 12, CONV_SPLIT_OFFSET = 4, CONV_SPLIT_WAYS = 4;
 // 5-D tiled tensor map over a chunk-planar activation tensor: dims (x*8, img, row, chunk, unit*plane), box (px, img, rows, chunks, 1)
 cudaError_t make_act_map(CUtensorMap *tm, const __half *base, const ActLayout &L, size_t units, int box_px, int box_img,
                          int box_rows, int box_chunks);

@@ -52,6 +52,9 @@ SEC_BIAS_MMA = 0xA00
 SEC_FC_W = 0x800
 SEC_FC_B = 0x900
 SEC_X_W_F16 = 0xB00
+SEC_W_SPLIT = 0xC00  # layer3 weights again, output channels split 4 ways: [split][cin_group][tap][G/8][Cout/4][8]
+SEC_X_SPLIT = 0xD00  # and their extra-operand slabs: [split][xc/gx][(hi, lo)][gx/8][Cout/4][8]
+SPLIT_LAYERS, SPLIT_WAYS = (12, 13, 14, 15), 4  # = CONV_SPLIT_* of csrc/mlt_internal.h
 ROUNDING = "diffused"  # "nearest" = independent round-to-nearest (tools/precision_ab.py compares the two)
 ALPHA = np.float32(1.0 / 1023)  # (float)(1.0/1023), bits 0x3A802008: cv::Mat::convertTo's alpha at EncCu.cpp:835-838
 
@@ -139,6 +142,14 @@ def pack_umma_b(w: np.ndarray, group: int) -> np.ndarray:
     t = quantize_fp16_diffused(w).reshape(cout, cin // group, group // 8, 8, kh * kw)  # [n][cg][j][e][t]
     t = t.transpose(1, 4, 2, 0, 3)  # [cg][t][j][n][e]
     return np.ascontiguousarray(t)
+
+
+def split_cout(packed: np.ndarray, ways: int) -> np.ndarray:
+    """[..., cout, 8] operand slabs -> [ways][..., cout / ways, 8]: the layout of the channel-split kernels (ConvCfg::NSPLIT),
+    where every CTA streams only its own quarter of each slab as one contiguous bulk copy."""
+    cout = packed.shape[-2]
+    t = packed.reshape(*packed.shape[:-2], ways, cout // ways, 8)
+    return np.ascontiguousarray(np.moveaxis(t, -3, 0))
 
 
 def bias_operand(b: np.ndarray) -> np.ndarray:
@@ -229,7 +240,10 @@ def build_sections(sd: dict) -> list:
         bn = prefix.replace("conv", "bn")
         wf, bf = fold_bn(sd[f"{prefix}.weight"], sd, bn)
         assert wf.shape == (cout, cin, 3, 3), (prefix, wf.shape)
-        add(SEC_W_F16 + li, pack_umma_b(wf, group), np.float16)
+        packed = pack_umma_b(wf, group)
+        add(SEC_W_F16 + li, packed, np.float16)
+        if li in SPLIT_LAYERS:
+            add(SEC_W_SPLIT + li, split_cout(packed, SPLIT_WAYS), np.float16)
         add(SEC_W_F32 + li, wf.transpose(2, 3, 1, 0).reshape(9, cin, cout), np.float32)
         add(SEC_BIAS + li, bf, np.float32)
         fused = bf
@@ -237,13 +251,19 @@ def build_sections(sd: dict) -> list:
             sp = prefix.rsplit(".", 1)[0] + ".shortcut"
             ws, bs = fold_bn(sd[f"{sp}.0.weight"], sd, f"{sp}.1")
             csc = ws.shape[1]
-            add(SEC_X_W_F16 + li, extra_operand_hilo(ws.reshape(cout, csc), min(csc, group)), np.float16)
+            xop = extra_operand_hilo(ws.reshape(cout, csc), min(csc, group))
+            add(SEC_X_W_F16 + li, xop, np.float16)
+            if li in SPLIT_LAYERS:
+                add(SEC_X_SPLIT + li, split_cout(xop, SPLIT_WAYS), np.float16)
             add(SEC_SC_W_F32 + sc, ws.reshape(cout, csc).T, np.float32)
             add(SEC_SC_BIAS + sc, bs, np.float32)
             fused = (bf.astype(np.float32) + bs.astype(np.float32)).astype(np.float32)
         elif li & 1:
             # identity residual of the second block (arch.py:44-57): one more K-slab with Wx = I, exact in fp16
-            add(SEC_X_W_F16 + li, extra_operand(np.eye(cout, dtype=np.float32), min(cout, group)), np.float16)
+            xop = extra_operand(np.eye(cout, dtype=np.float32), min(cout, group))
+            add(SEC_X_W_F16 + li, xop, np.float16)
+            if li in SPLIT_LAYERS:
+                add(SEC_X_SPLIT + li, split_cout(xop, SPLIT_WAYS), np.float16)
         add(SEC_BIAS_FUSED + li, fused, np.float32)
         add(SEC_BIAS_MMA + li, bias_operand(fused), np.float16)
     for i in range(3):
