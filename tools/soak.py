@@ -1,0 +1,46 @@
+"""Soak test (run on the B200 box): random batch sizes through every host entry point of the CTU and CU paths for a fixed
+wall time; every result must equal, bit for bit, the result of the same CTU / CU computed in a small reference batch.
+A timing-dependent race (like the shared-ring one fixed in round 1) shows up here as a mismatch or a launch failure.
+usage: python tools/soak.py [seconds per model]"""
+import os, sys, tempfile, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import fastintercu_vvc_b200 as pkg
+from fastintercu_vvc_b200.synth import make_cu_state_dict, make_state_dict, synth_ctus, synth_cus
+
+budget = float(sys.argv[1]) if len(sys.argv) > 1 else 20.0
+rng = np.random.RandomState(1234)
+blob = tempfile.NamedTemporaryFile(suffix=".mltw", delete=False).name
+
+def run(name, pred, base, pq, nmax, pipelined):
+    ref = pred.predict_batch_dense(base, pq).copy()
+    nb = len(base)
+    t_end, iters, total = time.time() + budget, 0, 0
+    while time.time() < t_end:
+        n = int(rng.choice([rng.randint(1, 9), rng.randint(9, 300), rng.randint(300, nmax + 1)]))
+        idx = rng.randint(0, nb, n)
+        op, q = np.ascontiguousarray(base[idx]), np.ascontiguousarray(pq[idx])
+        if pipelined and iters % 3 == 0:
+            pred.submit_batch_dense(op, q); pred.submit_batch_dense(op, q)
+            a = pred.collect().copy(); b = pred.collect().copy()
+            assert a.tobytes() == b.tobytes(), (name, n, "pipelined pair differs")
+            got = a
+        else:
+            got = pred.predict_batch_dense(op, q)
+        if got.tobytes() != ref[idx].tobytes():
+            bad = np.nonzero([got[i].tobytes() != ref[idx[i]].tobytes() for i in range(n)])[0]
+            raise SystemExit(f"{name}: MISMATCH at n={n}, {len(bad)} items, first {bad[:5]}")
+        iters += 1; total += n
+    print(f"{name}: {iters} batches, {total} items, all bit-identical to the reference batch", flush=True)
+
+pkg.write_blob(make_state_dict(10), blob)
+base, pq = synth_ctus(48, 77)
+with pkg.MltPredictor(blob, max_batch=4096) as p:
+    run("CTU 128", p, base, pq, 4096, True)
+for size, nmax in ((64, 8192), (32, 32768), (16, 65536)):
+    pkg.write_cu_blob(make_cu_state_dict(10, size), size, blob)
+    cus, cq = synth_cus(96, size, 78)
+    with pkg.MltCuPredictor(blob, size, max_batch=nmax) as p:
+        run(f"CU {size}", p, cus, cq, nmax, False)
+os.unlink(blob)
+print("soak ok")
