@@ -713,13 +713,15 @@ int mlt_predict_batch_device(mlt_ctx *c, int n, const int16_t *d_orgpred, const 
     static const bool no_slice = getenv("MLT_NO_SLICE") != nullptr; // A/B switch for measurements
     if (n < 2 * 240 || c->profiling || c->engine != 0 || no_slice) return run_network(c, c->d_ctus, n, d_out, s);
     // two slices on two streams: the inter-kernel gaps of one slice are filled by the other slice's kernels
-    const int n0 = (n + 1) / 2;
+    static const int nslices = getenv("MLT_SLICES") ? atoi(getenv("MLT_SLICES")) : 2; // measurement override (even, >= 2)
     CU(cudaEventRecord(c->ev_fork, s));
     CU(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
-    rc = run_network(c, c->d_ctus, n0, d_out, s, 0);
-    if (rc) return rc;
-    rc = run_network(c, c->d_ctus + n0, n - n0, d_out + n0, c->stream2, 1);
-    if (rc) return rc;
+    const int per = (n + nslices - 1) / nslices;
+    for (int i = 0, off = 0; off < n; i++, off += per) {
+        const int m = n - off < per ? n - off : per;
+        rc = run_network(c, c->d_ctus + off, m, d_out + off, (i & 1) ? c->stream2 : s, i & 1);
+        if (rc) return rc;
+    }
     CU(cudaEventRecord(c->ev_join, c->stream2));
     CU(cudaStreamWaitEvent(s, c->ev_join, 0));
     c->last_n = 0; // debug_activation only sees single-slice batches
