@@ -266,7 +266,7 @@ def cpu_cu_reference_rate(size: int, budget_s: float):
     return n / dt, torch.get_num_threads(), n, dt
 
 
-def bench_cu_models(local: int, frames: int, steps: int, warm: int, cpu_budget: float = 0.0):
+def bench_cu_models(local: int, frames: int, steps: int, warm: int, cpu_budget: float = 0.0, sizes=(64, 32, 16)):
     """Device-resident and host-buffer throughput of the 64 / 32 / 16-px CU models on all
     same-size CUs of `frames` 1080p frames per step.  Secondary numbers: the headline metric stays the CTU model."""
     import torch
@@ -277,7 +277,7 @@ def bench_cu_models(local: int, frames: int, steps: int, warm: int, cpu_budget: 
 
     out = {}
     stream = torch.cuda.current_stream()
-    for size in (64, 32, 16):
+    for size in sizes:
         n = frames * CTUS_PER_FRAME * (128 // size) ** 2
         blob = tempfile.NamedTemporaryFile(suffix=".mltw", delete=False).name
         pkg.write_cu_blob(make_cu_state_dict(10, size), size, blob)
@@ -342,6 +342,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cu-frames", type=int, default=8, help="1080p frames whose 64 / 32 / 16-px CUs form one step of the CU-model lines (0 = skip)")
     ap.add_argument("--cu-only", action="store_true", help="only the smaller-CU models (tuning runs)")
+    ap.add_argument("--cu-sizes", default="64,32,16", help="CU sizes of the CU-model lines (profiling runs pick one)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -365,7 +366,8 @@ def main():
     steps, warm = args.steps, max(args.warmup, 3)
     n = args.frames * CTUS_PER_FRAME
     if args.cu_only:
-        print(json.dumps({"metric": "mlt_cnn_cu_split_cus_per_s", "cu_models": bench_cu_models(local, args.cu_frames, max(steps // 5, 3), warm)}))
+        print(json.dumps({"metric": "mlt_cnn_cu_split_cus_per_s",
+                          "cu_models": bench_cu_models(local, args.cu_frames, max(steps // 5, 3), warm, sizes=tuple(int(x) for x in args.cu_sizes.split(",")))}))
         return 0
 
     # seeded random weights of the exact architecture (the trained .pt is not distributed with the reference)
