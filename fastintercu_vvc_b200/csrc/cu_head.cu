@@ -14,64 +14,73 @@ __device__ __forceinline__ int feat_off(int h) { return h == 0 ? 0 : (h == 1 ? 6
 __device__ __forceinline__ int logit_off(int l) { return l == 0 ? 0 : (l == 1 ? 2 : (l == 2 ? 5 : (l == 3 ? 9 : 15))); }
 } // namespace
 
-// One WARP per CU (8 CUs per block): the pooled inputs are tiny -- fp32 partial sums left by the conv epilogues for maps
-// >= 8x8 (conv_umma.cuh GAP), or the stored fp16 activation of a map <= 4x4 -- so a block per CU would be all launch and
-// scheduling overhead (measured: 1.07 ms of 3.9 ms for 61,440 16-px CUs).
+// Eight CUs per block.  Pooling: maps >= 8x8 come as fp32 partial sums left by the conv epilogues (conv_umma.cuh GAP; one
+// warp per CU adds them, lanes across channels); maps <= 4x4 are pooled from the stored fp16 strip-layout activation
+// (+ its lo tensor where the layer writes hi + lo pairs) with thread = (CU, 8-channel chunk), CU fastest, so that a warp
+// reads runs of consecutive CUs (the strip layout keeps the same pixel of consecutive CUs hp * 16 B apart).  Then one
+// warp per CU for the FC heads.  A block per CU (first version) or a warp per CU with lanes across chunks (second) were
+// all launch overhead / uncoalesced 16-byte reads: 1.07 and 0.43 ms of a 61,440-CU step.
 __global__ void __launch_bounds__(NT) cu_head_kernel(const CuHeadParams p)
 {
-    __shared__ float s_feat[NT / 32][FEAT_TOTAL];
-    __shared__ float s_logits[NT / 32][CU_NLOGIT + 1];
+    constexpr int CPB = NT / 32; // CUs per block
+    __shared__ float s_feat[CPB][FEAT_TOTAL];
+    __shared__ float s_logits[CPB][CU_NLOGIT + 1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n = blockIdx.x * (NT / 32) + warp;
+    const int n0 = blockIdx.x * CPB;
     griddep_launch_dependents();
     griddep_wait(); // PDL: activations come from the previous kernels of the stream
-    if (n >= p.n) return; // (no block-level barrier below: warps are independent)
-    float *feat = s_feat[warp], *logits = s_logits[warp];
     for (int h = 0; h < CU_NHEAD; h++) {
         const ActLayout L = p.lay[h];
         const float inv = 1.0f / (float)(L.H * L.H);
-        float *f = feat + feat_off(h);
         if (p.gap_part[h] != nullptr) {
-            // maps >= 8x8: add the per-(tile, lane quadrant) fp32 partial sums in a fixed order
-            const int cnt = p.gap_count[h];
-            const float *g = p.gap_part[h] + (size_t)n * cnt * L.C;
-            for (int c = lane; c < L.C; c += 32) {
-                float t = 0.0f;
-                for (int k = 0; k < cnt; k++) t += g[k * L.C + c];
-                f[c] = t * inv;
+            // add the per-(tile, lane quadrant) fp32 partial sums of CU n0 + warp in a fixed order
+            const int n = n0 + warp, cnt = p.gap_count[h];
+            if (n < p.n) {
+                const float *g = p.gap_part[h] + (size_t)n * cnt * L.C;
+                for (int c = lane; c < L.C; c += 32) {
+                    float t = 0.0f;
+                    for (int k = 0; k < cnt; k++) t += g[k * L.C + c];
+                    s_feat[warp][feat_off(h) + c] = t * inv;
+                }
             }
         } else {
-            // maps <= 4x4: pool the stored strip-layout activation; lane = 8-channel chunk, pixels in order
             const int hp = L.hp(), npix = L.npl() * hp * hp, nch = L.C / 8;
-            for (int cj = lane; cj < nch; cj += 32) {
+            const int cu = threadIdx.x % CPB, n = n0 + cu;
+            for (int cj = threadIdx.x / CPB; cj < nch; cj += NT / CPB) {
                 float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                for (int q = 0; q < npix; q++) {
-                    const int pl = q / (hp * hp), y = (q / hp) % hp, x = q % hp;
-                    const size_t off = ((((size_t)pl * nch + cj) * hp + y) * L.strip + n) * hp * 8 + (size_t)x * 8;
-                    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p.act[h] + off));
-                    const __half2 *h2 = reinterpret_cast<const __half2 *>(&v);
-#pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        const float2 t = __half22float2(h2[e]);
-                        s[2 * e] += t.x;
-                        s[2 * e + 1] += t.y;
-                    }
-                    if (p.hilo[h]) { // fp16 hi + lo pair: the lo tensor sits one whole tensor further on
-                        const uint4 w = __ldg(reinterpret_cast<const uint4 *>(p.act[h] + L.unit_elems() + off));
-                        const __half2 *l2 = reinterpret_cast<const __half2 *>(&w);
+                if (n < p.n) {
+                    for (int q = 0; q < npix; q++) { // pixels in a fixed order
+                        const int pl = q / (hp * hp), y = (q / hp) % hp, x = q % hp;
+                        const size_t off = ((((size_t)pl * nch + cj) * hp + y) * L.strip + n) * hp * 8 + (size_t)x * 8;
+                        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p.act[h] + off));
+                        const __half2 *h2 = reinterpret_cast<const __half2 *>(&v);
 #pragma unroll
                         for (int e = 0; e < 4; e++) {
-                            const float2 t = __half22float2(l2[e]);
+                            const float2 t = __half22float2(h2[e]);
                             s[2 * e] += t.x;
                             s[2 * e + 1] += t.y;
+                        }
+                        if (p.hilo[h]) { // fp16 hi + lo pair: the lo tensor sits one whole tensor further on
+                            const uint4 w = __ldg(reinterpret_cast<const uint4 *>(p.act[h] + L.unit_elems() + off));
+                            const __half2 *l2 = reinterpret_cast<const __half2 *>(&w);
+#pragma unroll
+                            for (int e = 0; e < 4; e++) {
+                                const float2 t = __half22float2(l2[e]);
+                                s[2 * e] += t.x;
+                                s[2 * e + 1] += t.y;
+                            }
                         }
                     }
                 }
 #pragma unroll
-                for (int e = 0; e < 8; e++) f[cj * 8 + e] = s[e] * inv;
+                for (int e = 0; e < 8; e++) s_feat[cu][feat_off(h) + cj * 8 + e] = s[e] * inv;
             }
         }
     }
+    __syncthreads();
+    const int n = n0 + warp;
+    if (n >= p.n) return; // (no block-level barrier below: warps are independent)
+    float *feat = s_feat[warp], *logits = s_logits[warp];
     __syncwarp();
     const float poc = (float)p.cus[n].poc, qp = (float)p.cus[n].qp; // raw ints promoted by torch.cat (mlt_cu_or_pq_arch.py:100-101,110)
     for (int o = 0; o < CU_NLOGIT; o++) {
