@@ -8,7 +8,8 @@
 // row-strip of a 64-px CU, one row-strip of a 32-px CU or two whole 16-px CUs.  Small CTAs on purpose: the kernel is a
 // chain of latencies (global loads -> expansion -> 16 MMAs -> TMEM reads -> stores), so throughput comes from CTAs in
 // flight, and 128 TMEM columns per CTA let four of them overlap on an SM (8 tiles / 256 columns: two; measured 342 us
-// for 3840 64-px CUs).
+// for 3840 64-px CUs, 288 us with 4 tiles; 2 tiles / 64 columns / 128 threads measured no faster: what remains is the
+// scattered 64-byte store segments of the strip layout on a 64x64 map, see profiles/r01/README.md).
 // Output: activation 0, fp16, parity-planar STRIP layout [plane][4 chunks][size/2][cap][size/2][8] (conv_umma.cuh).
 #include "conv_umma.cuh"
 #include "mlt_internal.h"
