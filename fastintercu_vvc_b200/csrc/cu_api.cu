@@ -16,7 +16,7 @@ using namespace mlt;
 namespace {
 
 constexpr uint32_t MLTW_MAGIC = 0x57544C4Du;
-enum : uint32_t { SEC_CONV1_UMMA = 0x002, SEC_W_F16 = 0x100, SEC_BIAS_FUSED = 0x200, SEC_FC_W = 0x800, SEC_FC_B = 0x900, SEC_BIAS_MMA = 0xA00, SEC_X_W_F16 = 0xB00 };
+enum : uint32_t { SEC_CONV1_UMMA = 0x002, SEC_STEM_CONV1 = 0x003, SEC_W_F16 = 0x100, SEC_BIAS_FUSED = 0x200, SEC_FC_W = 0x800, SEC_FC_B = 0x900, SEC_BIAS_MMA = 0xA00, SEC_X_W_F16 = 0xB00 };
 constexpr int FC_IN[CU_NHEAD] = {66, 98, 130, 258}, FC_OUT[CU_NHEAD] = {2, 3, 4, 6};
 
 struct Section { const uint8_t *dev = nullptr; size_t bytes = 0; };
@@ -33,6 +33,11 @@ struct mlt_cu_ctx {
     CuLayerInfo info[CU_NCONV];
     ActLayout lay[CU_NACT];
     __half *act[CU_NACT] = {};
+    // 64- / 32-px networks: staging + conv1 + layer0.0.conv1 run as the fused stem kernel (stem_umma.cu); conv1's output
+    // (act[0]) is then only materialised for debug reads, and `act0q` holds its even / even quarter for layer0.0's shortcut
+    bool fused = false;
+    __half *act0q = nullptr;
+    ActLayout lay0q;
     float *gap_part[CU_NHEAD] = {}; // fp32 pool partial sums of the head-feeding convs on maps >= 8x8
     ConvParams conv_p[CU_NCONV];
     int16_t *d_in = nullptr, *h_in = nullptr; // dense [cap][2][size][size]
@@ -100,7 +105,7 @@ int load_blob(mlt_cu_ctx *c, const char *path)
         c->sec[id].bytes = nb;
     }
     auto need = [&](uint32_t id, size_t bytes) { return c->sec[id].dev != nullptr && c->sec[id].bytes == bytes; };
-    bool ok = need(SEC_CONV1_UMMA, 2 * 4 * 32 * 16);
+    bool ok = need(SEC_CONV1_UMMA, 2 * 4 * 32 * 16) && need(SEC_STEM_CONV1, 4 * 1024);
     for (int li = 0; li < CU_NCONV && ok; li++) {
         const CuLayerInfo &L = c->info[li];
         ok = need(SEC_W_F16 + li, (size_t)9 * L.cin * L.cout * 2) && need(SEC_BIAS_FUSED + li, (size_t)L.cout * 4) &&
@@ -130,14 +135,18 @@ int run_network(mlt_cu_ctx *c, int n, const int16_t *d_orgpred, const int32_t *d
 {
     cu_dense_descs_kernel<<<(n + 255) / 256, 256, 0, s>>>(c->d_cus, d_orgpred, d_pocqp, n, c->size);
     CU(cudaGetLastError());
-    CU(launch_cu_conv1(c->size, c->d_cus, n, secp<__half>(c, SEC_CONV1_UMMA), c->act[0], c->cap, s));
+    if (c->fused)
+        CU(launch_cu_stem_umma(c->size, c->d_cus, n, secp<__half>(c, SEC_STEM_CONV1), secp<__half>(c, SEC_W_F16 + 0),
+                               secp<float>(c, SEC_BIAS_FUSED + 0), c->act0q, c->act[1], c->cap, c->num_sms, s));
+    else
+        CU(launch_cu_conv1(c->size, c->d_cus, n, secp<__half>(c, SEC_CONV1_UMMA), c->act[0], c->cap, s));
     c->launches += 2;
     static const int stop_after = getenv("MLT_CU_STOP_AFTER") ? atoi(getenv("MLT_CU_STOP_AFTER")) : -1; // debug: run conv1 + this many convs, then synchronise
     if (stop_after >= 0) {
         const cudaError_t e = cudaStreamSynchronize(s);
         if (e != cudaSuccess) return fail(c, MLT_E_CUDA, "conv1 of the %d-px network (n=%d): %s", c->size, n, cudaGetErrorString(e));
     }
-    for (int li = 0; li < CU_NCONV; li++) {
+    for (int li = c->fused ? 1 : 0; li < CU_NCONV; li++) {
         if (stop_after >= 0 && li >= stop_after) { c->last_n = n; return MLT_OK; }
         ConvParams &p = c->conv_p[li];
         p.nimg = n;
@@ -236,6 +245,7 @@ void mlt_cu_destroy(mlt_cu_ctx *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (__half *a : c->act) cudaFree(a);
+    cudaFree(c->act0q);
     for (float *g : c->gap_part) cudaFree(g);
     cudaFree(c->d_blob); cudaFree(c->d_in); cudaFree(c->d_pq); cudaFree(c->d_cus); cudaFree(c->d_out); cudaFree(c->d_dbg);
     cudaFreeHost(c->h_in); cudaFreeHost(c->h_pq); cudaFreeHost(c->h_out);
@@ -272,6 +282,8 @@ int mlt_cu_create(mlt_cu_ctx **out, const char *weights_path, int cuda_device, i
         if (r) return r;
         CU(conv_umma_init()); // resolves cuTensorMapEncodeTiled
         CU(cu_conv_init(cu_size));
+        CU(stem_umma_init());
+        c->fused = cu_size >= 32 && getenv("MLT_CU_UNFUSED") == nullptr; // a 16-px CU is smaller than one stem work unit
         // every activation is ONE strip over the whole batch: [plane][C/8][row][cap images][x][8] fp16
         c->lay[0] = ActLayout{cu_size, 32, 1, 0, c->cap};
         for (int li = 0; li < CU_NCONV; li++) c->lay[li + 1] = ActLayout{c->info[li].hout, c->info[li].cout, c->info[li].out_par, 0, c->cap};
@@ -281,11 +293,19 @@ int mlt_cu_create(mlt_cu_ctx **out, const char *weights_path, int cuda_device, i
             CU(cudaMalloc(&c->act[a], bytes));
             CU(cudaMemsetAsync(c->act[a], 0, bytes, c->stream)); // images beyond a batch's n are read by the last tile: keep them finite
         }
+        c->lay0q = ActLayout{cu_size / 2, 32, 0, 0, c->cap};
+        if (c->fused) {
+            CU(cudaMalloc(&c->act0q, c->lay0q.unit_elems() * sizeof(__half)));
+            CU(cudaMemsetAsync(c->act0q, 0, c->lay0q.unit_elems() * sizeof(__half), c->stream));
+        }
         memset(c->conv_p, 0, sizeof c->conv_p);
         for (int li = 0; li < CU_NCONV; li++) {
             ConvParams &p = c->conv_p[li];
             const bool has_x = c->info[li].xc > 0; // second conv of a block: X = the block's input = activation li - 1
-            CU(cu_conv_prepare(cu_size, li, &p, c->act[li], c->lay[li], has_x ? c->act[li - 1] : nullptr, has_x ? &c->lay[li - 1] : nullptr));
+            // fused stem: layer0.0.conv2's shortcut reads conv1's even / even quarter instead of plane 0 of conv1's output
+            const __half *xp = has_x ? ((li == 1 && c->fused) ? c->act0q : c->act[li - 1]) : nullptr;
+            const ActLayout *xl = has_x ? ((li == 1 && c->fused) ? &c->lay0q : &c->lay[li - 1]) : nullptr;
+            CU(cu_conv_prepare(cu_size, li, &p, c->act[li], c->lay[li], xp, xl));
             p.w = secp<__half>(c, SEC_W_F16 + li);
             p.bias = secp<__half>(c, SEC_BIAS_MMA + li);
             p.bias_f32 = secp<float>(c, SEC_BIAS_FUSED + li);
@@ -388,6 +408,8 @@ int64_t mlt_cu_debug_activation(mlt_cu_ctx *c, int layer, float *out, int64_t ca
         c->dbg_bytes = elems * sizeof(float);
     }
     cudaStream_t s = c->stream;
+    if (layer == 0 && c->fused) // the fused stem never materialises conv1's output: recompute it with the standalone kernel
+        CU(launch_cu_conv1(c->size, c->d_cus, c->last_n, secp<__half>(c, SEC_CONV1_UMMA), c->act[0], c->cap, s));
     CU(launch_unpack_act(c->act[layer], c->d_dbg, c->last_n, L, s));
     CU(cudaMemcpyAsync(out, c->d_dbg, elems * sizeof(float), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));

@@ -26,7 +26,7 @@ struct CuSel {
     static constexpr int OUT_PAR = (K == 3 && L < 4 && H >= 2) ? 1 : 0; // feeds the next stage's stride-2 block
     static constexpr int X_PAR = (K == 1 && !FAKE_S2) ? 1 : 0;          // shortcut input = plane (even, even) of the stage input
     // the last two stages (and the tensor that feeds them) carry fp16 hi + lo activation pairs (ConvCfg::HILO_*)
-    static constexpr int HILO_OUT = LI >= CU_HILO_FROM - 1 ? 1 : 0, HILO_IN = LI >= CU_HILO_FROM ? 1 : 0;
+    static constexpr int HILO_OUT = LI >= cu_hilo_from(S) - 1 ? 1 : 0, HILO_IN = LI >= cu_hilo_from(S) ? 1 : 0;
     using type = ConvCfg<CIN, P, STRIDE, H, XC, OUT_PAR, XLO, 1 | (HILO_IN << 1) | (HILO_OUT << 2)>;
 };
 
@@ -72,7 +72,7 @@ struct CuNetOps {
             cudaError_t e = make_act_map(&p->in_map, in, in_l, C::HILO_IN ? 2 : 1, C::BLKW, C::NB, C::PROWS, C::CH);
             if (e != cudaSuccess) return e;
             if constexpr (C::XC > 0) {
-                if (!x || !x_l || x_l->strip != in_l.strip || x_l->C != C::XC || x_l->hp() != C::HOUT || x_l->par != Sel::X_PAR) return cudaErrorInvalidValue;
+                if (!x || !x_l || x_l->strip != in_l.strip || x_l->C != C::XC || x_l->hp() != C::HOUT || (x_l->par != 0 && x_l->par != Sel::X_PAR)) return cudaErrorInvalidValue; // (par: plane 0 is read)
                 e = make_act_map(&p->x_map, x, *x_l, C::HILO_IN ? 2 : 1, C::XBOXW, C::NB, C::TR, C::GX / 8);
                 if (e != cudaSuccess) return e;
             } else {

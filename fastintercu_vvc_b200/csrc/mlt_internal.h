@@ -61,6 +61,10 @@ cudaError_t stem_umma_init();
 cudaError_t launch_stem_umma(const CtuDev *ctus, int n, const __half *w1 /*SEC_STEM_CONV1*/, const __half *w0, const float *bias /*fp32*/,
                              __half *act0q /*conv1 at even rows/cols [n][4][64][64][8]*/, __half *act1, int num_sms, cudaStream_t s);
 
+// the same fused stem for the 64- / 32-px CU networks (strip-layout outputs; a 16-px CU is smaller than one work unit)
+cudaError_t launch_cu_stem_umma(int size, const CtuDev *cus, int n, const __half *w1, const __half *w0, const float *bias, __half *act0q,
+                                __half *act1, int cap, int num_sms, cudaStream_t s);
+
 // ---- conv_simt.cu : fp32 CUDA-core cross-check engine (tests only; never a fallback)
 cudaError_t launch_conv_simt(const float *in, const float *w /*[k*k][cin][cout]*/, const float *bias, const float *res,
                              float *out, int nimg, int hin, int cin, int cout, int ksize, int stride, int relu,
@@ -117,7 +121,10 @@ cudaError_t make_act_map(CUtensorMap *tm, const __half *base, const ActLayout &L
 
 // ---- cu_net_*.cu / cu_stem.cu / cu_head.cu : the smaller-CU networks (64 / 32 / 16-px GapBigMltCuORPQ, mlt_cu_or_pq_arch.py:59-130)
 constexpr int CU_NCONV = 20, CU_NACT = 21, CU_NHEAD = 4, CU_NLOGIT = 15;
-constexpr int CU_HILO_FROM = 12; // convs >= 12 (layer3, layer4) read fp16 hi + lo activation pairs; conv 11 is the first to write one
+// first conv that READS fp16 hi + lo activation pairs (the conv before it is the first to write one): layer2 on for the
+// 64- / 32-px networks, layer3 on for the 16-px one -- what keeps max |dprob| <= 8.6e-4 on 2048 CUs per size with the
+// fused stem's single-fp16 conv1 weights (profiles/r01/precision_cu_2048.log)
+constexpr int cu_hilo_from(int size) { return size == 16 ? 12 : 8; }
 struct CuLayerInfo { // one 3x3 conv of the CU network at a given CU size (forward order, after conv1)
     int cin, cout, stride, hout, xc, out_par, nb, flat; // stride as executed (a stride-2 conv on a 1x1 map runs as stride 1)
     int g, gx;                                          // channels per weight slab of the main / extra operand (packer layout)

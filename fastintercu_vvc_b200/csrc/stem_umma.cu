@@ -55,6 +55,9 @@ static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
 __device__ __forceinline__ uint32_t absdiff16(uint32_t o, uint32_t p) { return o > p ? o - p : p - o; } // cv::absdiff, CV_16U
 
+// S = block size in luma samples: 128 (the CTU network: outputs in the dense per-CTU layout [ctu][4][64][64][8]) or 64 / 32
+// (the smaller-CU networks: outputs in the STRIP layout [4 chunks][S/2 rows][cap images][S/2][8], conv_umma.cuh) --
+// (S / 32)^2 work units per block.  A 16-px CU is smaller than one work unit and keeps the unfused conv1 kernel.
 struct StemParams {
     const CtuDev *ctus;
     const __half *w1;   // conv1 operand variants (SEC_STEM_CONV1)
@@ -63,11 +66,19 @@ struct StemParams {
     __half *act0q;      // conv1 output at even rows / even columns: dense chunk-planar [ctu][4][64][64][8]
     __half *act1;       // layer0.0.conv1 output: dense chunk-planar [ctu][4][64][64][8]
     int n;
+    int cap;            // strip layouts (S < 128): images per strip
 };
 
+template <int S>
 __global__ void __launch_bounds__(stem::NTHREADS, 1) stem_umma_kernel(const StemParams p)
 {
     using namespace stem;
+    constexpr int OH = S / 2, UW = S / 32, UPI = UW * UW; // output map size; work units per row / per block
+    // element offset of output pixel (oy, ox), channel chunk 0, of block `b` and the stride between channel chunks
+    auto out_off = [&](int b, int oy, int ox) -> size_t {
+        return S == 128 ? (size_t)b * (4 * OH * OH * 8) + (size_t)(oy * OH + ox) * 8 : ((size_t)(oy * p.cap + b) * OH + ox) * 8;
+    };
+    const size_t out_chunk = S == 128 ? (size_t)OH * OH * 8 : (size_t)OH * p.cap * OH * 8;
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + OFF_BAR);
     uint64_t *ep_full = bars, *ep_empty = bars + 2, *c1_full = bars + 4, *c1_empty = bars + 16;
@@ -75,7 +86,7 @@ __global__ void __launch_bounds__(stem::NTHREADS, 1) stem_umma_kernel(const Stem
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_TMEM);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int total_units = p.n * 16;
+    const int total_units = p.n * UPI;
 
     if (tid == 0) {
         for (int i = 0; i < 2; i++) {
@@ -124,14 +135,14 @@ __global__ void __launch_bounds__(stem::NTHREADS, 1) stem_umma_kernel(const Stem
         }
         auto load_window = [&](int u, uint4 (&vo)[2], uint4 (&vp)[2]) {
             // rows Y = 2*oy0 - 2 + t (t < 35), columns X = 2*ox0 - 8 + c (c < 48); outside the CTU = conv1's zero padding
-            const int ctu = u >> 4, oy0 = ((u >> 2) & 3) * 16, ox0 = (u & 3) * 16;
+            const int ctu = u / UPI, oy0 = ((u % UPI) / UW) * 16, ox0 = ((u % UPI) % UW) * 16;
             const CtuDev d = p.ctus[ctu];
 #pragma unroll
             for (int k = 0; k < 2; k++) {
                 const int i = st + k * 128, t = i / 6, vx = i % 6;
                 const int Y = 2 * oy0 - 2 + t, X = 2 * ox0 - 8 + vx * 8;
                 vo[k] = vp[k] = make_uint4(0, 0, 0, 0);
-                if (i < NV && Y >= 0 && Y < 128 && X >= 0 && X < 128) {
+                if (i < NV && Y >= 0 && Y < S && X >= 0 && X < S) {
                     vo[k] = __ldg(reinterpret_cast<const uint4 *>(d.org + (size_t)Y * d.org_stride + X));
                     vp[k] = __ldg(reinterpret_cast<const uint4 *>(d.pred + (size_t)Y * d.pred_stride + X));
                 }
@@ -258,7 +269,7 @@ __global__ void __launch_bounds__(stem::NTHREADS, 1) stem_umma_kernel(const Stem
         const int wq = warp & 3, hsel = (warp - W_E1) >> 2; // TMEM lane quadrant; which of the NE1/4 tile subsets
         uint32_t ul = 0;
         for (int u = blockIdx.x; u < total_units; u += gridDim.x, ul++) {
-            const int ctu = u >> 4, oy0 = ((u >> 2) & 3) * 16, ox0 = (u & 3) * 16;
+            const int ctu = u / UPI, oy0 = ((u % UPI) / UW) * 16, ox0 = ((u % UPI) % UW) * 16;
             const uint32_t buf = ul & 1;
             mbar_wait(&patch_empty[buf], ((ul >> 1) & 1) ^ 1);
             uint8_t *patch = smem + OFF_PATCH + buf * PATCH_BYTES;
@@ -293,9 +304,9 @@ __global__ void __launch_bounds__(stem::NTHREADS, 1) stem_umma_kernel(const Stem
                         *reinterpret_cast<uint4 *>(patch + plane * P_PLANE + q * P_LBO + e * 16) = ov[q];
                     }
                     if (plane == 0 && i < 16 && j < 16) { // conv1 at (2*(oy0+i), 2*(ox0+j)): input of layer0.0's 1x1 stride-2 shortcut
-                        __half *op = p.act0q + (size_t)ctu * (4 * 64 * 64 * 8) + (size_t)((oy0 + i) * 64 + ox0 + j) * 8;
+                        __half *op = p.act0q + out_off(ctu, oy0 + i, ox0 + j);
 #pragma unroll
-                        for (int q = 0; q < 4; q++) *reinterpret_cast<uint4 *>(op + (size_t)q * (64 * 64 * 8)) = ov[q];
+                        for (int q = 0; q < 4; q++) *reinterpret_cast<uint4 *>(op + (size_t)q * out_chunk) = ov[q];
                     }
                 }
             }
@@ -311,7 +322,7 @@ __global__ void __launch_bounds__(stem::NTHREADS, 1) stem_umma_kernel(const Stem
         for (int j = 0; j < 32; j++) bias_r[j] = __ldg(p.bias + j);
         uint32_t ul = 0;
         for (int u = blockIdx.x; u < total_units; u += gridDim.x, ul++) {
-            const int ctu = u >> 4, oy0 = ((u >> 2) & 3) * 16, ox0 = (u & 3) * 16;
+            const int ctu = u / UPI, oy0 = ((u % UPI) / UW) * 16, ox0 = ((u % UPI) % UW) * 16;
             const uint32_t buf = ul & 1;
             mbar_wait(&d_full[buf], (ul >> 1) & 1);
             tc_fence_after();
@@ -321,7 +332,7 @@ __global__ void __launch_bounds__(stem::NTHREADS, 1) stem_umma_kernel(const Stem
                 tmem_ld32(tmem + ((uint32_t)(wq * 32) << 16) + TM_D + buf * 64 + half * 32, v);
                 tmem_ld_wait();
                 const __half2 zero2 = __float2half2_rn(0.0f);
-                __half *op = p.act1 + (size_t)ctu * (4 * 64 * 64 * 8) + (size_t)((oy0 + r) * 64 + ox0 + half * 8 + c) * 8;
+                __half *op = p.act1 + out_off(ctu, oy0 + r, ox0 + half * 8 + c);
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     uint4 ov;
@@ -330,7 +341,7 @@ __global__ void __launch_bounds__(stem::NTHREADS, 1) stem_umma_kernel(const Stem
                     for (int x = 0; x < 4; x++)
                         h2[x] = __hmax2(__floats2half2_rn(__uint_as_float(v[q * 8 + x * 2]) + bias_r[q * 8 + x * 2],
                                                           __uint_as_float(v[q * 8 + x * 2 + 1]) + bias_r[q * 8 + x * 2 + 1]), zero2);
-                    *reinterpret_cast<uint4 *>(op + (size_t)q * (64 * 64 * 8)) = ov;
+                    *reinterpret_cast<uint4 *>(op + (size_t)q * out_chunk) = ov;
                 }
             }
             tc_fence_before();
@@ -349,16 +360,32 @@ __global__ void __launch_bounds__(stem::NTHREADS, 1) stem_umma_kernel(const Stem
 
 cudaError_t stem_umma_init()
 {
-    return cudaFuncSetAttribute(stem_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, stem::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(stem_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, stem::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_umma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, stem::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_umma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, stem::SMEM_BYTES);
+    return e;
 }
 
 cudaError_t launch_stem_umma(const CtuDev *ctus, int n, const __half *w1, const __half *w0, const float *bias, __half *act0q,
                              __half *act1, int num_sms, cudaStream_t s)
 {
     if (n <= 0) return cudaSuccess;
-    StemParams p{ctus, w1, w0, bias, act0q, act1, n};
+    StemParams p{ctus, w1, w0, bias, act0q, act1, n, 0};
     const int units = n * 16;
-    return launch_pdl(stem_umma_kernel, dim3(units < num_sms ? units : num_sms), dim3(stem::NTHREADS), stem::SMEM_BYTES, s, p);
+    return launch_pdl(stem_umma_kernel<128>, dim3(units < num_sms ? units : num_sms), dim3(stem::NTHREADS), stem::SMEM_BYTES, s, p);
+}
+
+// the same stem for a 64- or 32-px CU network: act0q / act1 are strips of `cap` images (S/2 x S/2 x 32, not parity-planar)
+cudaError_t launch_cu_stem_umma(int size, const CtuDev *cus, int n, const __half *w1, const __half *w0, const float *bias, __half *act0q,
+                                __half *act1, int cap, int num_sms, cudaStream_t s)
+{
+    if (n <= 0) return cudaSuccess;
+    StemParams p{cus, w1, w0, bias, act0q, act1, n, cap};
+    const int units = n * (size / 32) * (size / 32);
+    const dim3 grid(units < num_sms ? units : num_sms), block(stem::NTHREADS);
+    if (size == 64) return launch_pdl(stem_umma_kernel<64>, grid, block, stem::SMEM_BYTES, s, p);
+    if (size == 32) return launch_pdl(stem_umma_kernel<32>, grid, block, stem::SMEM_BYTES, s, p);
+    return cudaErrorInvalidValue;
 }
 
 } // namespace mlt

@@ -309,6 +309,7 @@ def build_cu_sections(sd: dict, size: int) -> list:
     w = sd["conv1.weight"].astype(np.float32)  # [32][2][3][3], no BN / bias (mlt_cu_or_pq_arch.py:105)
     add(SEC_CONV1_F32, w.transpose(2, 3, 1, 0).reshape(9, 2, 32), np.float32)
     add(SEC_CONV1_UMMA, conv1_operand(w), np.float16)
+    add(SEC_STEM_CONV1, stem_conv1_operand(w), np.float16)  # the 64- / 32-px networks run the fused stem (csrc/stem_umma.cu)
     for li, (prefix, cin, cout, stride, hout, group, xc, gx, kind) in enumerate(cu_conv_table(size)):
         wf, bf = fold_bn(sd[f"{prefix}.weight"], sd, prefix.replace("conv", "bn"))
         assert wf.shape == (cout, cin, 3, 3), (prefix, wf.shape)

@@ -5,10 +5,10 @@ the CPU oracle (oracle/ref_arch.MltCuNet, oracle/mltcnn_oracle.c) and the golden
 mlt_cu_or_pq_arch.py (tests/golden/cu_logits_seed10.npz, tools/gen_golden_cu.py).
 
 Bars: every conv layer within fp16 rounding of the fp32 oracle; probabilities max |diff| <= 1e-3 vs fp32 (the CTU model's
-bar; measured 8.4e-4 / 7.9e-4 / 4.7e-4 on 256 CUs and 8.6e-4 / 9.8e-4 / 6.5e-4 on 2048 CUs per size,
-profiles/r01/precision_cu_2048.log -- reached by carrying the activations of the last two stages as fp16 hi + lo pairs,
-ConvCfg::HILO_*: their 4x4 / 2x2 / 1x1 maps average out almost none of the fp16 activation rounding); decisions equal
-except within a tie margin; every entry point bit-identical per CU; results independent of batch size and position.
+bar; measured 7.1e-4 / 8.6e-4 / 6.5e-4 on 2048 CUs per size, profiles/r01/precision_cu_2048.log -- reached by carrying the
+activations of the deep stages as fp16 hi + lo pairs, ConvCfg::HILO_*: their 4x4 / 2x2 / 1x1 maps average out almost none
+of the fp16 activation rounding); decisions equal except within a tie margin; every entry point bit-identical per CU;
+results independent of batch size and position.
 """
 import os
 import tempfile
