@@ -63,6 +63,11 @@ EXPORTS = {
     "mlt_collect": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
     "mlt_begin_picture": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
     "mlt_predict_ctu_in_picture": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "mlt_pin_host_buffer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    "mlt_unpin_host_buffer": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mlt_picture_ctu_count": (C.c_int, [C.c_void_p]),
+    "mlt_predict_picture": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
+    "mlt_debug_picture_pred": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "mlt_set_engine": (C.c_int, [C.c_void_p, C.c_int]),
     "mlt_launch_count": (C.c_uint64, [C.c_void_p]),
     "mlt_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
@@ -228,6 +233,50 @@ class MltPredictor:
             self._lib.mlt_predict_ctu_in_picture(self._h, int(x), int(y), pp, ps, int(qp), out.ctypes.data), "mlt_predict_ctu_in_picture"
         )
         return out[0]
+
+    def pin_host_buffer(self, a: np.ndarray):
+        """Page-lock the memory behind `a` (its base allocation must outlive the pin); see mlt_pin_host_buffer."""
+        self._check(self._lib.mlt_pin_host_buffer(self._h, C.c_void_p(a.ctypes.data), C.c_uint64(a.nbytes)), "mlt_pin_host_buffer")
+
+    def unpin_host_buffer(self, a: np.ndarray):
+        self._check(self._lib.mlt_unpin_host_buffer(self._h, C.c_void_p(a.ctypes.data)), "mlt_unpin_host_buffer")
+
+    # -- frame-level pre-pass
+    def picture_ctu_count(self) -> int:
+        n = self._lib.mlt_picture_ctu_count(self._h)
+        if n < 0:
+            self._check(n, "mlt_picture_ctu_count")
+        return n
+
+    def predict_picture(self, ref_luma: np.ndarray, slice_qp: int, mv: np.ndarray | None = None, ctu_qp: np.ndarray | None = None) -> np.ndarray:
+        """All eligible CTUs of the picture begun, in raster order, from integer-MV prediction out of `ref_luma`."""
+        if ref_luma.dtype != np.int16 or ref_luma.ndim != 2 or ref_luma.strides[1] != 2:
+            raise ValueError("ref_luma must be an int16 2-D view")
+        n = self.picture_ctu_count()
+        if mv is not None:
+            mv = np.ascontiguousarray(mv, np.int16)
+            if mv.shape != (n, 2):
+                raise ValueError(f"mv must be [{n}, 2]")
+        if ctu_qp is not None:
+            ctu_qp = np.ascontiguousarray(ctu_qp, np.int32)
+            if ctu_qp.shape != (n,):
+                raise ValueError(f"ctu_qp must be [{n}]")
+        out = np.zeros(n, RESULT_DTYPE)
+        rc = self._lib.mlt_predict_picture(
+            self._h, ref_luma.ctypes.data, ref_luma.strides[0] // 2, mv.ctypes.data if mv is not None else None,
+            ctu_qp.ctypes.data if ctu_qp is not None else None, int(slice_qp), out.ctypes.data, n,
+        )
+        if rc < 0:
+            self._check(rc, "mlt_predict_picture")
+        return out[:rc]
+
+    def debug_picture_pred(self) -> np.ndarray:
+        n = self.picture_ctu_count()
+        out = np.zeros((n, CTU, CTU), np.int16)
+        rc = self._lib.mlt_debug_picture_pred(self._h, out.ctypes.data, n)
+        if rc < 0:
+            self._check(rc, "mlt_debug_picture_pred")
+        return out[:rc]
 
     # -- test hooks
     def set_engine(self, engine: int):

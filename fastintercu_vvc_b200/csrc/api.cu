@@ -98,6 +98,9 @@ struct mlt_ctx {
     size_t pic_capacity = 0;
     int pic_pitch = 0, pic_w = 0, pic_h = 0, pic_poc = 0;
     bool pic_valid = false;
+    int16_t *d_ref = nullptr; // reference-picture luma of the frame-level pre-pass (mlt_predict_picture), same pitch as d_pic
+    size_t ref_capacity = 0;
+    PicCtu *d_pic_ctus = nullptr, *h_pic_ctus = nullptr; // eligible CTUs of the picture: position + integer MV
     int last_n = 0;
     uint64_t launches = 0;
     bool profiling = false;
@@ -491,8 +494,8 @@ void mlt_destroy(mlt_ctx *c)
     if (c->slot[1].d_in) { cudaFree(c->slot[1].d_in); cudaFree(c->slot[1].d_ctus); cudaFree(c->slot[1].d_out); cudaFreeHost(c->slot[1].h_ctus); cudaFreeHost(c->slot[1].h_out); }
     for (auto &H : c->slot) if (H.done) cudaEventDestroy(H.done);
     cudaFree(c->scratch_f); cudaFree(c->d_blob); cudaFree(c->d_in); cudaFree(c->d_ctus); cudaFree(c->d_out);
-    cudaFree(c->d_dbg); cudaFree(c->d_pic);
-    cudaFreeHost(c->h_in); cudaFreeHost(c->h_ctus); cudaFreeHost(c->h_out);
+    cudaFree(c->d_dbg); cudaFree(c->d_pic); cudaFree(c->d_ref); cudaFree(c->d_pic_ctus);
+    cudaFreeHost(c->h_pic_ctus); cudaFreeHost(c->h_in); cudaFreeHost(c->h_ctus); cudaFreeHost(c->h_out);
     for (cudaEvent_t e : c->prof_ev) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : c->ev_in) if (e) cudaEventDestroy(e);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -770,6 +773,91 @@ int mlt_predict_ctu_in_picture(mlt_ctx *c, int x, int y, const int16_t *pred, in
     d.poc = c->pic_poc;
     d.qp = qp;
     return run_host_batch(c, 1, out, false);
+}
+
+int mlt_pin_host_buffer(mlt_ctx *c, const void *ptr, uint64_t bytes)
+{
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (!ptr || !bytes) return fail(c, MLT_E_INVAL, "null buffer");
+    const cudaError_t e = cudaHostRegister(const_cast<void *>(ptr), (size_t)bytes, cudaHostRegisterDefault);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return MLT_OK; }
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(c, MLT_E_CUDA, "cudaHostRegister: %s", cudaGetErrorString(e)); }
+    return MLT_OK;
+}
+
+int mlt_unpin_host_buffer(mlt_ctx *c, const void *ptr)
+{
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (!ptr) return fail(c, MLT_E_INVAL, "null buffer");
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    const cudaError_t e = cudaHostUnregister(const_cast<void *>(ptr));
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(c, MLT_E_INVAL, "cudaHostUnregister: %s", cudaGetErrorString(e)); }
+    return MLT_OK;
+}
+
+int mlt_picture_ctu_count(const mlt_ctx *c)
+{
+    if (!c) return MLT_E_INVAL;
+    if (!c->pic_valid) return MLT_E_STATE;
+    return (c->pic_w / CTU) * (c->pic_h / CTU); // CTUs lying fully inside the picture (EncCu.cpp:755)
+}
+
+int mlt_predict_picture(mlt_ctx *c, const int16_t *ref_luma, int ref_stride, const int16_t *mv, const int32_t *ctu_qp, int slice_qp,
+                        mlt_result *out, int capacity)
+{
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (!c->pic_valid) return fail(c, MLT_E_STATE, "mlt_begin_picture has not been called");
+    if (!ref_luma || !out || ref_stride < c->pic_w) return fail(c, MLT_E_INVAL, "bad reference picture");
+    const int cols = c->pic_w / CTU, n = cols * (c->pic_h / CTU);
+    if (n > c->max_batch) return fail(c, MLT_E_BATCH, "picture has %d eligible CTUs > max_batch=%d", n, c->max_batch);
+    if (capacity < n) return fail(c, MLT_E_INVAL, "out holds %d results, the picture has %d eligible CTUs", capacity, n);
+    if (c->submitted != c->collected) return fail(c, MLT_E_STATE, "submitted batches must be collected first");
+    cudaStream_t s = c->stream;
+    const size_t need = (size_t)c->pic_pitch * c->pic_h;
+    if (need > c->ref_capacity) {
+        if (c->d_ref) cudaFree(c->d_ref);
+        c->d_ref = nullptr;
+        c->ref_capacity = 0;
+        CU(cudaMalloc(&c->d_ref, need * sizeof(int16_t)));
+        c->ref_capacity = need;
+    }
+    if (!c->d_pic_ctus) {
+        CU(cudaMalloc(&c->d_pic_ctus, (size_t)c->max_batch * sizeof(PicCtu)));
+        CU(cudaMallocHost(&c->h_pic_ctus, (size_t)c->max_batch * sizeof(PicCtu)));
+    }
+    CU(cudaMemcpy2DAsync(c->d_ref, (size_t)c->pic_pitch * sizeof(int16_t), ref_luma, (size_t)ref_stride * sizeof(int16_t),
+                         (size_t)c->pic_w * sizeof(int16_t), c->pic_h, cudaMemcpyHostToDevice, s));
+    for (int i = 0; i < n; i++) {
+        const int x = (i % cols) * CTU, y = (i / cols) * CTU;
+        c->h_pic_ctus[i] = PicCtu{x, y, mv ? mv[2 * i] : 0, mv ? mv[2 * i + 1] : 0};
+        CtuDev &d = c->h_ctus[i];
+        d.org = c->d_pic + (size_t)y * c->pic_pitch + x; // read in place: CTU columns are 256-byte aligned
+        d.org_stride = c->pic_pitch;
+        d.pred = c->d_in + (size_t)i * CTU_IN_ELEMS + (size_t)CTU * CTU;
+        d.pred_stride = CTU;
+        d.poc = c->pic_poc;
+        d.qp = ctu_qp ? ctu_qp[i] : slice_qp;
+    }
+    CU(cudaMemcpyAsync(c->d_pic_ctus, c->h_pic_ctus, (size_t)n * sizeof(PicCtu), cudaMemcpyHostToDevice, s));
+    CU(launch_picture_pred(c->d_ref, c->pic_pitch, c->pic_w, c->pic_h, c->d_pic_ctus, n, c->d_in, s));
+    c->launches++;
+    rc = run_host_batch(c, n, out, false);
+    return rc ? rc : n;
+}
+
+int mlt_debug_picture_pred(mlt_ctx *c, int16_t *out, int capacity)
+{
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (!c->pic_valid || !c->d_pic_ctus) return fail(c, MLT_E_STATE, "no picture pre-pass has run");
+    const int n = (c->pic_w / CTU) * (c->pic_h / CTU);
+    if (!out || capacity < n) return fail(c, MLT_E_INVAL, "out too small");
+    CU(cudaMemcpy2D(out, (size_t)CTU * CTU * sizeof(int16_t), c->d_in + (size_t)CTU * CTU, CTU_IN_ELEMS * sizeof(int16_t),
+                    (size_t)CTU * CTU * sizeof(int16_t), n, cudaMemcpyDeviceToHost));
+    return n;
 }
 
 int mlt_debug_stage(mlt_ctx *c, int n, const mlt_ctu_desc *descs, float *out)

@@ -165,6 +165,11 @@ struct HeadParams {
 cudaError_t launch_head_h(const HeadParams &p, cudaStream_t s);
 cudaError_t launch_head_f(const HeadParams &p, cudaStream_t s);
 
+// ---- picture_pred.cu : frame-level pre-pass -- integer-MV prediction blocks for every eligible CTU of a picture from one
+// reference luma plane with replicated borders (Picture.cpp:1117); writes plane 1 of the dense [n][2][128][128] batch
+struct PicCtu { int32_t x, y, mvx, mvy; }; // CTU position and MV in luma samples
+cudaError_t launch_picture_pred(const int16_t *ref, int pitch, int w, int h, const PicCtu *ctus, int n, int16_t *out, cudaStream_t s);
+
 // ---- misc
 cudaError_t launch_unpack_act(const __half *in, float *out, int nimg, const ActLayout &L, cudaStream_t s);
 

@@ -107,7 +107,46 @@ int SplitPredictor::predict(const int16_t *org, int orgStride, const int16_t *pr
 
 bool SplitPredictor::beginPicture(const int16_t *orgLuma, int stride, int width, int height, int poc)
 {
+    m_picSplit.clear(); // decisions of the previous picture must never leak into this one
+    m_picCols = m_picRows = 0;
+    m_picW = width;
+    m_picH = height;
     return m_ctx && mlt_begin_picture(m_ctx, orgLuma, stride, width, height, poc) == MLT_OK;
+}
+
+bool SplitPredictor::prepassFromEnv()
+{
+    const char *s = std::getenv("MLT_PREPASS");
+    return s && std::strcmp(s, "0") != 0;
+}
+
+bool SplitPredictor::prepassPicture(const int16_t *refLuma, int refStride, const int16_t *mv, int sliceQp)
+{
+    m_picSplit.clear();
+    m_picCols = m_picRows = 0;
+    if (!m_ctx) return false;
+    const int n = mlt_picture_ctu_count(m_ctx);
+    if (n <= 0) return false;
+    std::vector<mlt_result> res((size_t)n);
+    const int got = mlt_predict_picture(m_ctx, refLuma, refStride, mv, nullptr, sliceQp, res.data(), n);
+    if (got != n) {
+        std::fprintf(stderr, "error\n"); // EncCu.cpp:925; every CTU of this picture then runs full RDO
+        return false;
+    }
+    m_picCols = m_picW / MLT_CTU_SIZE;
+    m_picRows = m_picH / MLT_CTU_SIZE;
+    if (m_picCols * m_picRows != n) { m_picCols = m_picRows = 0; return false; }
+    m_picSplit.resize((size_t)n);
+    for (int i = 0; i < n; i++) m_picSplit[(size_t)i] = res[(size_t)i].split_l3;
+    return true;
+}
+
+int SplitPredictor::pictureSplit(int cux, int cuy) const
+{
+    if (m_picSplit.empty() || cux < 0 || cuy < 0 || (cux % MLT_CTU_SIZE) || (cuy % MLT_CTU_SIZE)) return -1;
+    const int col = cux / MLT_CTU_SIZE, row = cuy / MLT_CTU_SIZE;
+    if (col >= m_picCols || row >= m_picRows) return -1; // partial CTU at the right / bottom edge: not eligible
+    return m_picSplit[(size_t)row * m_picCols + col];
 }
 
 int SplitPredictor::predictInPicture(int cux, int cuy, const int16_t *pred, int predStride, int qp)

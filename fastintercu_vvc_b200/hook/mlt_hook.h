@@ -8,6 +8,8 @@
 //   at::kCUDA / model path EncCu.cpp:804,899     env MLT_DEVICE / MLT_WEIGHTS (MLT_DISABLE=1 -> anchor run)
 //   jit::load per CTU      EncCu.cpp:894-905     SplitPredictor::instance() loads the MLTW blob ONCE
 //   staging + forward      EncCu.cpp:806-921     SplitPredictor::predict(org, stride, pred, stride, poc, qp)
+//   (none: pred comes from RDO, :820-830)        SplitPredictor::prepassPicture(ref, ...) + pictureSplit(x, y): whole
+//                                                frame in one batch before the CTU loop (env MLT_PREPASS=1)
 //   error convention       EncCu.cpp:694,923     any failure -> "error\n" on stderr, returns -1 (full RDO)
 //   consumer               EncModeCtrl.cpp:110   unchanged in VTM; restated below only so tests can pin it
 #pragma once
@@ -42,6 +44,15 @@ public:
     bool beginPicture(const int16_t *orgLuma, int stride, int width, int height, int poc);
     int predictInPicture(int cux, int cuy, const int16_t *pred, int predStride, int qp);
 
+    // Frame-level pre-pass, called once per inter picture from EncSlice::encodeCtus after
+    // beginPicture: every eligible CTU (gate of EncCu.cpp:755) is inferred in ONE batch from a neighbour-independent
+    // prediction -- integer-MV motion compensation out of `refLuma` (border-replicated, Picture.cpp:1117); `mv` = [n][2]
+    // (x, y) per eligible CTU in raster order or nullptr for zero MV.  xCompressCU then reads pictureSplit(cux, cuy)
+    // instead of calling predict(): -1 when the CTU is not eligible / no pre-pass ran for this picture / it failed.
+    bool prepassPicture(const int16_t *refLuma, int refStride, const int16_t *mv, int sliceQp);
+    int pictureSplit(int cux, int cuy) const;
+    static bool prepassFromEnv(); // env MLT_PREPASS=1
+
     // Smaller CUs (cuw = 64 / 32 / 16): the hook's `elements()[0]` branch (EncCu.cpp:916-919) == argmax of the FIRST head
     // of the per-size model MLTORPQ_splitMode_<cuw> (EncCu.cpp:899); weights from env MLT_WEIGHTS_<cuw>, loaded once on
     // first use.  -1 on failure or when that size has no weights.
@@ -57,6 +68,8 @@ private:
     mlt_cu_ctx *m_cu[3] = {nullptr, nullptr, nullptr}; // 64, 32, 16
     bool m_cuTried[3] = {false, false, false};
     bool m_disabled = false;
+    std::vector<int> m_picSplit; // pre-pass decisions of the current picture, eligible CTUs in raster order
+    int m_picCols = 0, m_picRows = 0, m_picW = 0, m_picH = 0;
 };
 
 // ---- restatement of the consumer's semantics (EncModeCtrl.cpp:95-149), used by tests only ------------------

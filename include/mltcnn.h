@@ -123,6 +123,29 @@ MLT_API int mlt_begin_picture(mlt_ctx *ctx, const int16_t *org_luma, int stride,
 MLT_API int mlt_predict_ctu_in_picture(mlt_ctx *ctx, int x, int y, const int16_t *pred, int pred_stride, int qp,
                                mlt_result *out);
 
+/* Frame-level pre-pass (no counterpart in the reference, whose `pred` is the RDO loop's own
+ * best AFFINE / MERGE_SKIP prediction, EncCu.cpp:820-830, and therefore serialises the calls CTU by CTU): after
+ * mlt_begin_picture, infer EVERY eligible CTU of the picture (128x128, fully inside, EncCu.cpp:755; raster order) in one
+ * batch at the top of EncSlice::encodeCtus (EncSlice.cpp:1479), from a neighbour-independent prediction built on the
+ * device: pred(x, y) = ref(clamp(x + mvx, 0, w-1), clamp(y + mvy, 0, h-1)) -- integer-sample motion compensation from
+ * a reference luma plane (e.g. slice->getRefPic(REF_PIC_LIST_0, 0)->getRecoBuf().Y(), EncSlice.cpp:1562) whose border
+ * is extended by sample replication as Picture::extendPicBorder does (Picture.cpp:1117).
+ * ref_luma: width x height of the picture begun, ref_stride in samples.  mv: [n][2] (x, y) integer luma-sample MVs per
+ * eligible CTU, or NULL = zero MV.  ctu_qp: [n] per-CTU QPs, or NULL = slice_qp for all (currTestMode.qp, EncCu.cpp:807).
+ * Returns the number of results written (== mlt_picture_ctu_count) or a negative code.  This changes the encoder's
+ * decisions relative to the reference hook (different pred) and needs its own BD-rate study; the per-CTU calls above
+ * remain the exact drop-in. */
+MLT_API int mlt_picture_ctu_count(const mlt_ctx *ctx);
+MLT_API int mlt_predict_picture(mlt_ctx *ctx, const int16_t *ref_luma, int ref_stride, const int16_t *mv, const int32_t *ctu_qp,
+                        int slice_qp, mlt_result *out, int capacity);
+
+/* Optional: page-lock a long-lived host buffer (VTM allocates a Picture's PelStorage once and keeps it for the whole
+ * encode, Picture.cpp Picture::create) so that mlt_begin_picture / mlt_predict_picture / the batch calls DMA straight
+ * out of it instead of going through the driver's pageable staging.  Plain wrappers, so the host side needs no CUDA
+ * headers; unpin before the buffer is freed.  Pinning the same range twice is not an error. */
+MLT_API int mlt_pin_host_buffer(mlt_ctx *ctx, const void *ptr, uint64_t bytes);
+MLT_API int mlt_unpin_host_buffer(mlt_ctx *ctx, const void *ptr);
+
 /* ---- introspection / test hooks (not needed by the encoder) ---- */
 MLT_API const char *mlt_strerror(int rc);
 MLT_API const char *mlt_last_error(const mlt_ctx *ctx); /* detail of the last failure ("" if none) */
@@ -140,6 +163,9 @@ MLT_API int mlt_get_profile(mlt_ctx *ctx, float *ms, int capacity);
 /* Bit-exactness probe of the staging arithmetic (EncCu.cpp:810-867) run on the GPU:
  * out = fp32 [n][2][128][128] (channel 0 = org/1023, channel 1 = |org-pred|/1023, clamped). */
 MLT_API int mlt_debug_stage(mlt_ctx *ctx, int n, const mlt_ctu_desc *descs, float *out);
+/* The prediction blocks the last mlt_predict_picture built on the device: out = int16 [n][128][128] (bit-exactness
+ * probe of the pre-pass gather).  Returns n or a negative code. */
+MLT_API int mlt_debug_picture_pred(mlt_ctx *ctx, int16_t *out, int capacity);
 /* Copy back an intermediate activation of the last batch as fp32 NHWC [n][H][W][C];
  * layer = 0 (conv1 out) .. 16 (layer3.1 out).  Returns the element count, or a negative code. */
 MLT_API int64_t mlt_debug_activation(mlt_ctx *ctx, int layer, float *out, int64_t capacity);

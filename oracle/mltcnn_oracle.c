@@ -402,3 +402,28 @@ void mlto_predict_batch(const mlto_model *m, int n, const int16_t *orgpred, cons
     batch_worker(&jobs[0]);
     for (int t = 1; t < nthreads; t++) pthread_join(th[t], NULL);
 }
+
+/* ---- frame-level pre-pass (see mltcnn_oracle.h) ---------------------------------------------------------------- */
+int mlto_picture_ctus(int w, int h, int32_t *xy, int cap)
+{
+    int n = 0;
+    /* raster order of EncSlice::encodeCtus (EncSlice.cpp:1529); gate of EncCu.cpp:755 */
+    for (int y = 0; y + MLTO_CTU <= h; y += MLTO_CTU)
+        for (int x = 0; x + MLTO_CTU <= w; x += MLTO_CTU) {
+            if (n < cap) { xy[2 * n] = x; xy[2 * n + 1] = y; }
+            n++;
+        }
+    return n;
+}
+
+static int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+void mlto_picture_pred(const int16_t *ref, int ref_stride, int w, int h, int x, int y, int mvx, int mvy, int16_t *pred)
+{
+    /* reading outside the picture returns the nearest border sample: that is what the replicated margins of a
+     * reference picture hold (Picture.cpp:1117) */
+    for (int r = 0; r < MLTO_CTU; r++) {
+        const int16_t *row = ref + (size_t)clampi(y + r + mvy, 0, h - 1) * ref_stride;
+        for (int c = 0; c < MLTO_CTU; c++) pred[r * MLTO_CTU + c] = row[clampi(x + c + mvx, 0, w - 1)];
+    }
+}

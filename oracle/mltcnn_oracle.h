@@ -68,6 +68,17 @@ void mlto_cu_forward(const mlto_model *m, int size, const float *x, int poc, int
 void mlto_cu_predict_batch(const mlto_model *m, int size, int n, const int16_t *orgpred, const int32_t *pocqp,
                            float *logits, int nthreads);
 
+/* ---- frame-level pre-pass (the library's mlt_predict_picture).  The reference has no such
+ * pass; what is restated here are the two reference behaviours it is built from: the eligibility gate of EncCu.cpp:755
+ * (a 128x128 CTU lying fully inside the picture, raster order as EncSlice::encodeCtus walks them, EncSlice.cpp:1529) and
+ * integer-sample motion compensation from a reference picture whose border is extended by sample replication
+ * (Picture::extendPicBorder, Picture.cpp:1117). */
+/* xy: [cap][2] luma positions of the eligible CTUs; returns their number */
+int mlto_picture_ctus(int w, int h, int32_t *xy, int cap);
+/* pred[r][c] = ref[clamp(y + r + mvy, 0, h-1)][clamp(x + c + mvx, 0, w-1)], r, c in [0, 128) */
+void mlto_picture_pred(const int16_t *ref, int ref_stride, int w, int h, int x, int y, int mvx, int mvy,
+                       int16_t *pred /* [128*128] dense */);
+
 #ifdef __cplusplus
 }
 #endif

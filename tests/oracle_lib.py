@@ -30,8 +30,28 @@ def lib():
         L.mlto_cu_stage.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         L.mlto_cu_forward.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.mlto_cu_predict_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.mlto_picture_ctus.restype = C.c_int
+        L.mlto_picture_ctus.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.mlto_picture_pred.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         _LIB = L
     return _LIB
+
+
+def picture_ctus(w: int, h: int) -> np.ndarray:
+    """Luma positions [n, 2] of the CTUs the gate of EncCu.cpp:755 lets through, raster order."""
+    n = lib().mlto_picture_ctus(w, h, None, 0)
+    xy = np.zeros((n, 2), np.int32)
+    lib().mlto_picture_ctus(w, h, xy.ctypes.data, n)
+    return xy
+
+
+def picture_pred(ref: np.ndarray, x: int, y: int, mvx: int = 0, mvy: int = 0) -> np.ndarray:
+    """Integer-MV prediction block of the CTU at (x, y) from a border-replicated reference plane (frame-level pre-pass)."""
+    assert ref.dtype == np.int16 and ref.ndim == 2 and ref.strides[1] == 2
+    h, w = ref.shape
+    out = np.zeros((128, 128), np.int16)
+    lib().mlto_picture_pred(ref.ctypes.data, ref.strides[0] // 2, w, h, int(x), int(y), int(mvx), int(mvy), out.ctypes.data)
+    return out
 
 
 class OracleModel:

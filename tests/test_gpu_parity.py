@@ -315,6 +315,133 @@ def test_cpp_hook_drives_the_library_like_the_encoder(pred, blob):
         assert a == want and b == want
 
 
+# ------------------------------------------------------------------------------- frame-level pre-pass (section 8f rank 2)
+def _prepass_picture(w, h, seed):
+    """org + reference luma as strided views (VTM PelStorage with margins) and per-CTU integer MVs that cover: zero,
+    aligned, odd / even sub-word shifts, and windows hanging over every picture border."""
+    from tests.oracle_lib import picture_ctus
+
+    rng = np.random.RandomState(seed)
+    base = (rng.randint(0, 1024, (h // 8 + 1, w // 8 + 1)).repeat(8, 0).repeat(8, 1)[:h, :w] * 3 // 4 + rng.randint(0, 256, (h, w))).astype(np.int16)
+    margin = 16
+    obuf = np.zeros((h + 2 * margin, w + 2 * margin + 3), np.int16)
+    rbuf = np.zeros_like(obuf)
+    org = obuf[margin : margin + h, margin : margin + w]
+    ref = rbuf[margin : margin + h, margin : margin + w]
+    org[:] = base
+    ref[:] = np.clip(np.roll(base, (1, 2), (0, 1)).astype(np.int32) + rng.randint(-12, 13, (h, w)), 0, 1023).astype(np.int16)
+    xy = picture_ctus(w, h)
+    n = len(xy)
+    mv = rng.randint(-24, 25, (n, 2)).astype(np.int16)
+    special = [(0, 0), (8, 0), (-8, 16), (1, 0), (2, 0), (7, -1), (-3, 5), (-150, -140), (160, 150), (-129, 0), (0, 2000), (4000, -4000)]
+    for i, v in enumerate(special[:n]):
+        mv[i] = v
+    return org, ref, xy, mv
+
+
+@pytest.mark.parametrize("w,h", [(416, 240), (1920, 1080)])
+def test_picture_prepass_gather_is_bit_exact(blob, oracle, w, h):
+    """The device-built prediction blocks of mlt_predict_picture == the oracle's integer-MV gather, every sample."""
+    from fastintercu_vvc_b200 import MltPredictor
+    from tests.oracle_lib import picture_pred
+
+    org, ref, xy, mv = _prepass_picture(w, h, 21)
+    with MltPredictor(blob, device=0, max_batch=len(xy)) as p:
+        p.begin_picture(org, poc=5)
+        assert p.picture_ctu_count() == len(xy)
+        for mvs in (None, mv):
+            res = p.predict_picture(ref, 37, mv=mvs)
+            assert len(res) == len(xy)
+            got = p.debug_picture_pred()
+            for i, (x, y) in enumerate(xy):
+                mx, my = (0, 0) if mvs is None else mvs[i]
+                assert np.array_equal(got[i], picture_pred(ref, x, y, mx, my)), (i, x, y, mx, my)
+
+
+def test_picture_prepass_equals_per_ctu_calls(blob):
+    """One frame-level batch == the drop-in per-CTU call fed the same prediction blocks: bit-identical results, in the
+    raster order of EncSlice::encodeCtus; per-CTU QPs honoured; errors reported, never computed around."""
+    from fastintercu_vvc_b200 import MltError, MltPredictor
+    from tests.oracle_lib import picture_pred
+
+    w, h = 1920, 1080
+    org, ref, xy, mv = _prepass_picture(w, h, 22)
+    n = len(xy)
+    assert n == 120
+    qps = np.random.RandomState(1).randint(22, 46, n).astype(np.int32)
+    with MltPredictor(blob, device=0, max_batch=160) as p:
+        with pytest.raises(MltError):
+            p.predict_picture(ref, 32)  # no picture begun
+        p.begin_picture(org, poc=9)
+        before = p.launch_count
+        res = p.predict_picture(ref, 0, mv=mv, ctu_qp=qps)
+        assert p.launch_count - before == 18  # gather + stem + 15 convs + head: one batch, not 120 calls
+        ctus = [(org[y : y + 128, x : x + 128], picture_pred(ref, x, y, *mv[i]), 9, int(qps[i])) for i, (x, y) in enumerate(xy)]
+        want = p.predict_batch(ctus)
+        assert res.tobytes() == want.tobytes()
+        one = p.predict_ctu(*ctus[77])
+        assert one.tobytes() == res[77].tobytes()
+        same_qp = p.predict_picture(ref, 31)
+        want0 = p.predict_batch([(o, picture_pred(ref, x, y), 9, 31) for (o, _, _, _), (x, y) in zip(ctus, xy)])
+        assert same_qp.tobytes() == want0.tobytes()
+        # page-locked picture buffers (mlt_pin_host_buffer, what a patched VTM does once per Picture): same bytes out
+        for buf in (org.base, ref.base):
+            p.pin_host_buffer(buf)
+            p.pin_host_buffer(buf)  # pinning twice is not an error
+        p.begin_picture(org, poc=9)
+        assert p.predict_picture(ref, 0, mv=mv, ctu_qp=qps).tobytes() == res.tobytes()
+        for buf in (org.base, ref.base):
+            p.unpin_host_buffer(buf)
+        with pytest.raises(MltError):
+            p.unpin_host_buffer(ref.base)  # not pinned any more
+    with MltPredictor(blob, device=0, max_batch=64) as small:
+        small.begin_picture(org, poc=9)
+        with pytest.raises(MltError) as e:
+            small.predict_picture(ref, 32)
+        assert e.value.rc == -7  # MLT_E_BATCH: 120 eligible CTUs > max_batch
+
+
+def test_cpp_hook_prepass_drives_the_library(pred, blob):
+    """The C++ hook's prepassPicture / pictureSplit pair over a 416x240 picture: decisions of
+    the eligible CTUs equal the per-CTU drop-in call on the same prediction, partial CTUs carry none."""
+    from tests.oracle_lib import picture_pred
+
+    hook = os.path.join(ROOT, "fastintercu_vvc_b200", "hook")
+    exe = os.path.join(hook, "hook_prepass_sim.bin")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", hook])
+    w, h, poc, qp = 416, 240, 6, 38
+    org, ref, xy, mv = _prepass_picture(w, h, 23)
+    stride = org.strides[0] // 2
+    full_o = np.zeros((h, stride), np.int16)
+    full_r = np.zeros((h, stride), np.int16)
+    full_o[:, :w] = org
+    full_r[:, :w] = ref
+    for has_mv in (0, 1):
+        with tempfile.NamedTemporaryFile(suffix=".bin", delete=False) as f:
+            f.write(np.array([w, h, stride, poc, qp, has_mv], np.int32).tobytes())
+            f.write(full_o.tobytes())
+            f.write(full_r.tobytes())
+            if has_mv:
+                f.write(mv.tobytes())
+            path = f.name
+        try:
+            env = dict(os.environ, MLT_WEIGHTS=blob, MLT_DEVICE="0")
+            r = subprocess.run([exe, path], capture_output=True, text=True, timeout=120, env=env)
+        finally:
+            os.unlink(path)
+        assert r.returncode == 0, r.stdout + r.stderr
+        rows = [tuple(map(int, l.split())) for l in r.stdout.strip().splitlines()]
+        assert len(rows) == 4 * 2  # the whole CTU raster, partial CTUs included
+        elig = [row for row in rows if row[2]]
+        assert [(x, y) for x, y, _, _ in elig] == [tuple(v) for v in xy]
+        assert all(s == -1 for _, _, e, s in rows if not e)
+        for i, (x, y, _, s) in enumerate(elig):
+            m = mv[i] if has_mv else (0, 0)
+            want = pred.predict_ctu(org[y : y + 128, x : x + 128], picture_pred(ref, x, y, *m), poc, qp)["split_l3"]
+            assert s == want
+
+
 def test_device_resident_batch_via_torch(pred, ctus):
     import torch
 

@@ -120,3 +120,31 @@ def test_torch_restatement_equals_reference_arch_file(sd):
     b = ref_arch.forward_logits(ref_arch.build_model(sd), x, pocqp, batch=1)
     assert np.array_equal(a, b)
     assert sum(p.numel() for p in ref.parameters()) == 2797403
+
+
+# ------------------------------------------------------------------------------- frame-level pre-pass (section 8f rank 2)
+def test_picture_ctu_raster_follows_the_gate():
+    """Eligible CTUs per picture = the counts SURVEY.md section 8d derives from EncCu.cpp:755, raster order."""
+    from tests.oracle_lib import picture_ctus
+
+    for (w, h), want in (((416, 240), 3), ((1920, 1080), 120), ((3840, 2160), 480), ((127, 500), 0), ((128, 128), 1)):
+        xy = picture_ctus(w, h)
+        assert len(xy) == want
+        ref = [(x, y) for y in range(0, h, 128) for x in range(0, w, 128) if x + 128 <= w and y + 128 <= h]
+        assert [tuple(v) for v in xy] == ref
+
+
+def test_picture_pred_equals_padded_reference_window():
+    """Integer-MV prediction from a border-replicated plane: the C restatement against numpy's edge padding, which is
+    what Picture::extendPicBorder (Picture.cpp:1117) builds around every reference picture."""
+    from tests.oracle_lib import picture_pred
+
+    rng = np.random.RandomState(3)
+    w, h, m = 416, 240, 300
+    buf = rng.randint(0, 1024, (h, w + 24)).astype(np.int16)
+    ref = buf[:, 5 : 5 + w]  # strided view
+    padded = np.pad(ref, m, mode="edge")
+    for (x, y, mvx, mvy) in ((0, 0, 0, 0), (128, 0, 3, -2), (256, 0, -7, 5), (0, 0, -200, -150), (256, 0, 290, 250), (128, 0, 8, 16), (256, 0, 33, 113)):
+        got = picture_pred(ref, x, y, mvx, mvy)
+        want = padded[m + y + mvy : m + y + mvy + 128, m + x + mvx : m + x + mvx + 128]
+        assert np.array_equal(got, want), (x, y, mvx, mvy)
