@@ -86,6 +86,8 @@ EXPORTS.update({
     "mlt_cu_predict": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "mlt_cu_predict_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "mlt_cu_predict_batch_dense": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mlt_cu_submit_batch_dense": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "mlt_cu_collect": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
     "mlt_cu_predict_batch_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mlt_cu_last_error": (C.c_char_p, [C.c_void_p]),
     "mlt_cu_size": (C.c_int, [C.c_void_p]),
@@ -383,6 +385,23 @@ class MltCuPredictor:
         self._check(self._lib.mlt_cu_predict_batch_dense(self._h, n, orgpred.ctypes.data, pocqp.ctypes.data, out.ctypes.data),
                     "mlt_cu_predict_batch_dense")
         return out
+
+    def submit_batch_dense(self, orgpred: np.ndarray, pocqp: np.ndarray):
+        """Pipelined form: enqueue and return; at most two batches in flight.  `orgpred` must stay alive and unchanged
+        until the matching collect()."""
+        n = len(orgpred)
+        if orgpred.dtype != np.int16 or orgpred.shape[1:] != (2, self.size, self.size) or not orgpred.flags.c_contiguous:
+            raise ValueError("orgpred must be C-contiguous int16 [n,2,size,size]")
+        pocqp = np.ascontiguousarray(pocqp, np.int32)
+        self._check(self._lib.mlt_cu_submit_batch_dense(self._h, n, orgpred.ctypes.data, pocqp.ctypes.data), "mlt_cu_submit_batch_dense")
+
+    def collect(self, out: np.ndarray | None = None) -> np.ndarray:
+        """Blocks for the oldest submitted batch; returns its results (a view of `out` when given)."""
+        if out is None:
+            out = np.zeros(self.max_batch, CU_RESULT_DTYPE)
+        n = C.c_int(0)
+        self._check(self._lib.mlt_cu_collect(self._h, out.ctypes.data, C.byref(n)), "mlt_cu_collect")
+        return out[: n.value]
 
     def predict_batch_device(self, n: int, d_orgpred: int, d_pocqp: int, d_out: int, stream: int = 0):
         self._check(self._lib.mlt_cu_predict_batch_device(self._h, int(n), C.c_void_p(d_orgpred), C.c_void_p(d_pocqp), C.c_void_p(d_out),

@@ -385,8 +385,14 @@ int enqueue_host_batch(mlt_ctx *c, int slot, int n, const int16_t *src, const ml
     // Chunk schedule: only the FIRST chunk's H2D is exposed (every later copy hides behind the previous chunks' kernels,
     // which are slower than PCIe), so the chunks start small (n / 16) and grow by 1.5x up to n / 4.
     int sizes[mlt_ctx::MAX_CHUNKS], nchunks = 0;
-    if (n < 1024) sizes[nchunks++] = n;
-    else {
+    // A pipelined batch submitted while another one is still in flight hides its whole copy under that batch's kernels:
+    // two equal chunks (the two activation sets / compute streams, like a device-resident batch), no growing schedule.
+    const bool hidden = c->submitted != c->collected;
+    if (n < 1024 && !(hidden && n >= 2 * 240)) sizes[nchunks++] = n;
+    else if (hidden && n / 2 <= c->set[1].cap) {
+        sizes[nchunks++] = n - n / 2;
+        sizes[nchunks++] = n / 2;
+    } else {
         const int cap = n / 4 < c->set[1].cap ? n / 4 : c->set[1].cap;
         for (int rem = n, cur = n / 16 > 120 ? n / 16 : 120; rem > 0;) {
             int m = rem < cur ? rem : cur;

@@ -44,6 +44,18 @@ struct mlt_cu_ctx {
     int32_t *d_pq = nullptr, *h_pq = nullptr; // [cap][2]
     CtuDev *d_cus = nullptr;
     mlt_cu_result *d_out = nullptr, *h_out = nullptr;
+    // Host-batch slots: slot 0 = the buffers above (every synchronous call); slot 1 is allocated on the first
+    // mlt_cu_submit_batch_dense so that two batches can be in flight (the H2D of batch k + 1 runs while batch k computes).
+    // The activation strips are shared: all kernels are ordered on the one compute stream.
+    struct HostSlot {
+        int16_t *d_in = nullptr;
+        int32_t *d_pq = nullptr, *h_pq = nullptr;
+        mlt_cu_result *d_out = nullptr, *h_out = nullptr;
+        cudaEvent_t done = nullptr;
+        int n = 0;
+        bool busy = false;
+    } slot[2];
+    uint64_t submitted = 0, collected = 0;
     float *d_dbg = nullptr;
     size_t dbg_bytes = 0;
     int last_n = 0;
@@ -185,40 +197,60 @@ int check_ctx(mlt_cu_ctx *c)
     return MLT_OK;
 }
 
-// h_in[0..n) / h_pq[0..n) are filled: upload, run, download, wait
-int run_host_batch(mlt_cu_ctx *c, int n, const int16_t *src, const int32_t *pq, mlt_cu_result *out)
+// Enqueue one dense host batch into `slot` without waiting for it: pocqp (via the slot's pinned buffer) and the chunked
+// H2D copies on the copy stream, the kernels on the compute stream, the D2H of the results into the slot's pinned buffer
+// and the `done` event.  `pipelined` = a batch of the submit / collect API (every copy goes to the copy stream so that it
+// can run under the previous batch's kernels).
+int enqueue_host_batch(mlt_cu_ctx *c, int slot_idx, int n, const int16_t *src, const int32_t *pq, bool pipelined)
 {
     cudaStream_t s = c->stream;
+    mlt_cu_ctx::HostSlot &H = c->slot[slot_idx];
     const size_t per = (size_t)2 * c->size * c->size;
-    CU(cudaMemcpyAsync(c->d_pq, pq, (size_t)n * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    if (pq != H.h_pq) memcpy(H.h_pq, pq, (size_t)n * 2 * sizeof(int32_t)); // consumed before the call returns
     // Large batches are pipelined in three chunks (n/8, 3n/8, n/2): chunk i + 1 is copied (copy stream) while chunk i
     // computes, so only the first, small copy is exposed.  Few chunks on purpose: every pass over the 23 kernels has a
     // latency floor of ~0.25 ms (the last stages stream megabytes of weights through a handful of CTAs), which six
     // finer chunks paid six times (measured).  The strip buffers are reused by every chunk (their kernels are ordered
     // on the compute stream).
     int sizes[mlt_cu_ctx::MAX_CHUNKS], nchunks = 0;
-    if ((size_t)n * per * sizeof(int16_t) < ((size_t)8 << 20)) sizes[nchunks++] = n; // < 8 MiB: one copy, one pass
+    // A pipelined batch submitted while another one is still in flight needs no chunks: its whole copy hides under that
+    // batch's kernels, and one pass avoids paying the latency floor three times.
+    const bool hidden = pipelined && c->submitted != c->collected;
+    if (hidden || (size_t)n * per * sizeof(int16_t) < ((size_t)8 << 20)) sizes[nchunks++] = n; // < 8 MiB: one copy, one pass
     else {
         sizes[0] = n / 8;
         sizes[1] = 3 * (n / 8);
         sizes[2] = n - sizes[0] - sizes[1];
         nchunks = 3;
     }
+    const bool side = nchunks > 1 || pipelined;
+    CU(cudaMemcpyAsync(H.d_pq, H.h_pq, (size_t)n * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, side ? c->copy_stream : s));
     for (int i = 0, off = 0; i < nchunks; off += sizes[i], i++) {
         const int m = sizes[i];
-        CU(cudaMemcpyAsync(c->d_in + (size_t)off * per, src + (size_t)off * per, (size_t)m * per * sizeof(int16_t), cudaMemcpyHostToDevice,
-                           nchunks > 1 ? c->copy_stream : s));
-        if (nchunks > 1) {
+        CU(cudaMemcpyAsync(H.d_in + (size_t)off * per, src + (size_t)off * per, (size_t)m * per * sizeof(int16_t), cudaMemcpyHostToDevice,
+                           side ? c->copy_stream : s));
+        if (side) {
             CU(cudaEventRecord(c->ev_in[i], c->copy_stream));
             CU(cudaStreamWaitEvent(s, c->ev_in[i], 0));
         }
-        const int rc = run_network(c, m, c->d_in + (size_t)off * per, c->d_pq + (size_t)off * 2, c->d_out + off, s);
+        const int rc = run_network(c, m, H.d_in + (size_t)off * per, H.d_pq + (size_t)off * 2, H.d_out + off, s);
         if (rc) { cudaStreamSynchronize(c->copy_stream); return rc; }
     }
     c->last_n = nchunks == 1 ? n : 0; // debug_activation only sees a batch that ran as one pass
-    CU(cudaMemcpyAsync(c->h_out, c->d_out, (size_t)n * sizeof(mlt_cu_result), cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
-    memcpy(out, c->h_out, (size_t)n * sizeof(mlt_cu_result));
+    CU(cudaMemcpyAsync(H.h_out, H.d_out, (size_t)n * sizeof(mlt_cu_result), cudaMemcpyDeviceToHost, s));
+    CU(cudaEventRecord(H.done, s));
+    H.n = n;
+    return MLT_OK;
+}
+
+// one blocking host batch through slot 0
+int run_host_batch(mlt_cu_ctx *c, int n, const int16_t *src, const int32_t *pq, mlt_cu_result *out)
+{
+    if (c->submitted != c->collected) return fail(c, MLT_E_STATE, "%llu submitted batch(es) not collected yet", (unsigned long long)(c->submitted - c->collected));
+    const int rc = enqueue_host_batch(c, 0, n, src, pq, false);
+    if (rc) return rc;
+    CU(cudaEventSynchronize(c->slot[0].done));
+    memcpy(out, c->slot[0].h_out, (size_t)n * sizeof(mlt_cu_result));
     return MLT_OK;
 }
 
@@ -247,6 +279,11 @@ void mlt_cu_destroy(mlt_cu_ctx *c)
     for (__half *a : c->act) cudaFree(a);
     cudaFree(c->act0q);
     for (float *g : c->gap_part) cudaFree(g);
+    if (c->slot[1].d_in) {
+        cudaFree(c->slot[1].d_in); cudaFree(c->slot[1].d_pq); cudaFree(c->slot[1].d_out);
+        cudaFreeHost(c->slot[1].h_pq); cudaFreeHost(c->slot[1].h_out);
+    }
+    for (auto &H : c->slot) if (H.done) cudaEventDestroy(H.done);
     cudaFree(c->d_blob); cudaFree(c->d_in); cudaFree(c->d_pq); cudaFree(c->d_cus); cudaFree(c->d_out); cudaFree(c->d_dbg);
     cudaFreeHost(c->h_in); cudaFreeHost(c->h_pq); cudaFreeHost(c->h_out);
     for (cudaEvent_t e : c->ev_in) if (e) cudaEventDestroy(e);
@@ -328,6 +365,9 @@ int mlt_cu_create(mlt_cu_ctx **out, const char *weights_path, int cuda_device, i
         CU(cudaHostAlloc(&c->h_in, (size_t)max_batch * per * sizeof(int16_t), cudaHostAllocDefault));
         CU(cudaHostAlloc(&c->h_pq, (size_t)max_batch * 2 * sizeof(int32_t), cudaHostAllocDefault));
         CU(cudaHostAlloc(&c->h_out, (size_t)max_batch * sizeof(mlt_cu_result), cudaHostAllocDefault));
+        c->slot[0].d_in = c->d_in; c->slot[0].d_pq = c->d_pq; c->slot[0].h_pq = c->h_pq;
+        c->slot[0].d_out = c->d_out; c->slot[0].h_out = c->h_out;
+        for (auto &H : c->slot) CU(cudaEventCreateWithFlags(&H.done, cudaEventDisableTiming));
         CU(cudaStreamSynchronize(c->stream));
         return MLT_OK;
     };
@@ -377,6 +417,45 @@ int mlt_cu_predict_batch_dense(mlt_cu_ctx *c, int n, const int16_t *orgpred, con
     if (n > c->cap) return fail(c, MLT_E_BATCH, "n=%d > max_batch=%d", n, c->cap);
     if (n == 0) return MLT_OK;
     return run_host_batch(c, n, orgpred, pocqp, out);
+}
+
+int mlt_cu_submit_batch_dense(mlt_cu_ctx *c, int n, const int16_t *orgpred, const int32_t *pocqp)
+{
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (n <= 0 || !orgpred || !pocqp) return fail(c, MLT_E_INVAL, "bad argument");
+    if (n > c->cap) return fail(c, MLT_E_BATCH, "n=%d > max_batch=%d", n, c->cap);
+    if (c->submitted - c->collected >= 2) return fail(c, MLT_E_STATE, "two batches are already in flight: collect one first");
+    const int si = (int)(c->submitted & 1);
+    mlt_cu_ctx::HostSlot &H = c->slot[si];
+    if (!H.d_in) { // second slot, first use
+        const size_t per = (size_t)2 * c->size * c->size;
+        CU(cudaMalloc(&H.d_in, (size_t)c->cap * per * sizeof(int16_t)));
+        CU(cudaMalloc(&H.d_pq, (size_t)c->cap * 2 * sizeof(int32_t)));
+        CU(cudaMalloc(&H.d_out, (size_t)c->cap * sizeof(mlt_cu_result)));
+        CU(cudaHostAlloc(&H.h_pq, (size_t)c->cap * 2 * sizeof(int32_t), cudaHostAllocDefault));
+        CU(cudaHostAlloc(&H.h_out, (size_t)c->cap * sizeof(mlt_cu_result), cudaHostAllocDefault));
+    }
+    rc = enqueue_host_batch(c, si, n, orgpred, pocqp, true);
+    if (rc) return rc;
+    H.busy = true;
+    c->submitted++;
+    return MLT_OK;
+}
+
+int mlt_cu_collect(mlt_cu_ctx *c, mlt_cu_result *out, int *n_out)
+{
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (!out) return fail(c, MLT_E_INVAL, "null argument");
+    if (c->submitted == c->collected) return fail(c, MLT_E_STATE, "no batch in flight");
+    mlt_cu_ctx::HostSlot &H = c->slot[c->collected & 1];
+    CU(cudaEventSynchronize(H.done));
+    memcpy(out, H.h_out, (size_t)H.n * sizeof(mlt_cu_result));
+    if (n_out) *n_out = H.n;
+    H.busy = false;
+    c->collected++;
+    return MLT_OK;
 }
 
 int mlt_cu_predict_batch_device(mlt_cu_ctx *c, int n, const int16_t *d_orgpred, const int32_t *d_pocqp, mlt_cu_result *d_out,

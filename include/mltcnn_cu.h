@@ -49,6 +49,12 @@ MLT_API int mlt_cu_predict(mlt_cu_ctx *ctx, const int16_t *org, int org_stride, 
 MLT_API int mlt_cu_predict_batch(mlt_cu_ctx *ctx, int n, const mlt_ctu_desc *descs, mlt_cu_result *out);
 /* Dense host batch: orgpred[n][2][size][size] int16 (plane 0 = org, 1 = pred), pocqp[n][2]. */
 MLT_API int mlt_cu_predict_batch_dense(mlt_cu_ctx *ctx, int n, const int16_t *orgpred, const int32_t *pocqp, mlt_cu_result *out);
+/* Pipelined form of mlt_cu_predict_batch_dense (same contract as mlt_submit_batch_dense / mlt_collect in mltcnn.h): at
+ * most two batches in flight, the H2D copy of batch k + 1 runs under batch k's kernels; `orgpred` must stay valid and
+ * unchanged until that batch is collected (pinned memory recommended), `pocqp` is consumed before the call returns;
+ * synchronous calls are refused (MLT_E_STATE) while batches are in flight. */
+MLT_API int mlt_cu_submit_batch_dense(mlt_cu_ctx *ctx, int n, const int16_t *orgpred, const int32_t *pocqp);
+MLT_API int mlt_cu_collect(mlt_cu_ctx *ctx, mlt_cu_result *out, int *n_out);
 /* Device-resident batch on the caller's stream (cudaStream_t as void*); asynchronous w.r.t. the host. */
 MLT_API int mlt_cu_predict_batch_device(mlt_cu_ctx *ctx, int n, const int16_t *d_orgpred, const int32_t *d_pocqp,
                                         mlt_cu_result *d_out, void *cuda_stream);

@@ -252,3 +252,47 @@ def test_cpp_hook_cu_branch_matches_the_binding(ctx):
     assert [(x, y) for x, y, _ in rows] == [(i * size, j * size) for j in range(ny) for i in range(nx)]
     want = p.predict_batch_dense(cus, np.tile(np.array([[poc, qp]], np.int32), (nx * ny, 1)))["split"][:, 0]
     assert [s for _, _, s in rows] == want.tolist()
+
+
+@pytest.mark.parametrize("size", [64, 16])
+def test_cu_pipelined_submit_collect_matches_the_synchronous_call(size):
+    """mlt_cu_submit_batch_dense / mlt_cu_collect (two batches in flight, second input slot) == the blocking call, byte for
+    byte, in submission order; the call-sequence errors are reported."""
+    import tempfile
+
+    import fastintercu_vvc_b200 as pkg
+    from fastintercu_vvc_b200 import MltError
+    from fastintercu_vvc_b200.synth import make_cu_state_dict, synth_cus
+
+    with tempfile.NamedTemporaryFile(suffix=".mltw", delete=False) as f:
+        path = f.name
+    try:
+        pkg.write_cu_blob(make_cu_state_dict(10, size), size, path)
+        big = 2 * (8 << 20) // (4 * size * size) + 37  # > 8 MiB of input: the three-chunk schedule
+        with pkg.MltCuPredictor(path, size, device=0, max_batch=big) as p:
+            batches = []
+            for k, n in enumerate((big, 129, big - 511, 1, 640)):
+                cus, pq = synth_cus(n, size, 300 + k)
+                batches.append((np.ascontiguousarray(cus), np.ascontiguousarray(pq)))
+            want = [p.predict_batch_dense(c, q).copy() for c, q in batches]
+            with pytest.raises(MltError):
+                p.collect()  # nothing in flight
+            got = []
+            p.submit_batch_dense(*batches[0])
+            for c, q in batches[1:]:
+                p.submit_batch_dense(c, q)
+                got.append(p.collect().copy())
+            with pytest.raises(MltError):
+                p.predict_batch_dense(*batches[3])  # synchronous calls are refused while a batch is in flight
+            p.submit_batch_dense(*batches[3])
+            with pytest.raises(MltError):
+                p.submit_batch_dense(*batches[3])  # a third batch in flight
+            got.append(p.collect().copy())
+            extra = p.collect().copy()
+            assert len(got) == len(want)
+            for g, w in zip(got, want):
+                assert g.tobytes() == w.tobytes()
+            assert extra.tobytes() == want[3].tobytes()
+            assert p.predict_batch_dense(*batches[1]).tobytes() == want[1].tobytes()  # and the blocking call works again
+    finally:
+        os.unlink(path)
