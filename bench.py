@@ -326,12 +326,27 @@ def bench_cu_models(local: int, frames: int, steps: int, warm: int, cpu_budget: 
         for _ in range(100):
             pred.predict(o1, p1, int(hpq[0, 0]), int(hpq[0, 1]))
         one_us = (time.perf_counter() - t0) / 100 * 1e6
+        # frame-level pre-pass at this CU size: all size x size blocks of ONE 1080p picture, planes in page-locked host memory
+        prng = np.random.RandomState(size)
+        p_org = torch.from_numpy(prng.randint(0, 1024, (1080, 1920)).astype(np.int16)).pin_memory().numpy()
+        p_ref = torch.from_numpy(np.clip(np.roll(p_org, (1, 1), (0, 1)).astype(np.int32) + prng.randint(-8, 9, p_org.shape), 0, 1023).astype(np.int16)).pin_memory().numpy()
+        n_pic = (1920 // size) * (1080 // size)
+        p_mv = prng.randint(-16, 17, (n_pic, 2)).astype(np.int16)
+        for _ in range(3):
+            pred.predict_picture(p_org, p_ref, 3, 32, mv=p_mv)
+        t0 = time.perf_counter()
+        for _ in range(20):
+            pred.predict_picture(p_org, p_ref, 3, 32, mv=p_mv)
+        pic_ms = (time.perf_counter() - t0) / 20 * 1e3
         fl = cu_flops(size)
         out[str(size)] = {"cus_per_step": n, "ms_per_step": ms, "cus_per_s": n / (ms * 1e-3), "e2e_cus_per_s": n / e2e_s,
                           "e2e_api": "mlt_cu_submit_batch_dense + mlt_cu_collect (two batches in flight)", "e2e_sync_call_cus_per_s": n / e2e_sync_s,
                           "flop_per_cu": fl, "tflops": n * fl / (ms * 1e-3) / 1e12, "gpu_launches_per_step": launches // steps,
                           "cu_latency_us": one_us, "h2d_bytes_per_step": int(n * (4 * size * size + 8)),
-                          "d2h_bytes_per_step": int(n * CU_RESULT_DTYPE.itemsize)}
+                          "d2h_bytes_per_step": int(n * CU_RESULT_DTYPE.itemsize),
+                          "picture_prepass": {"cus": n_pic, "ms_per_picture": pic_ms, "serial_hook_calls_ms": one_us * n_pic * 1e-3,
+                                              "note": "mlt_cu_predict_picture: every block of one 1920x1080 picture in one batch (planes pinned, "
+                                                      "gather on the device) vs one blocking mlt_cu_predict per CU"}}
         pred.close()
         del d_in, d_pq, d_out
         torch.cuda.empty_cache()

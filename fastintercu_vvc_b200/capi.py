@@ -88,6 +88,9 @@ EXPORTS.update({
     "mlt_cu_predict_batch_dense": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mlt_cu_submit_batch_dense": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "mlt_cu_collect": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
+    "mlt_cu_picture_cu_count": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+    "mlt_cu_predict_picture": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                         C.c_void_p, C.c_int]),
     "mlt_cu_predict_batch_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mlt_cu_last_error": (C.c_char_p, [C.c_void_p]),
     "mlt_cu_size": (C.c_int, [C.c_void_p]),
@@ -402,6 +405,27 @@ class MltCuPredictor:
         n = C.c_int(0)
         self._check(self._lib.mlt_cu_collect(self._h, out.ctypes.data, C.byref(n)), "mlt_cu_collect")
         return out[: n.value]
+
+    def predict_picture(self, org_luma: np.ndarray, ref_luma: np.ndarray, poc: int, qp: int, mv: np.ndarray | None = None) -> np.ndarray:
+        """Every size x size block of the picture's CU raster (fully inside the picture), raster order, in one batch;
+        pred = integer-MV prediction out of `ref_luma` built on the device."""
+        for a in (org_luma, ref_luma):
+            if a.dtype != np.int16 or a.ndim != 2 or a.strides[1] != 2 or a.shape != org_luma.shape:
+                raise ValueError("org_luma / ref_luma must be int16 2-D views of the same shape")
+        h, w = org_luma.shape
+        n = self._lib.mlt_cu_picture_cu_count(self.size, w, h)
+        if mv is not None:
+            mv = np.ascontiguousarray(mv, np.int16)
+            if mv.shape != (n, 2):
+                raise ValueError(f"mv must be [{n}, 2]")
+        out = np.zeros(max(n, 1), CU_RESULT_DTYPE)
+        rc = self._lib.mlt_cu_predict_picture(
+            self._h, org_luma.ctypes.data, org_luma.strides[0] // 2, ref_luma.ctypes.data, ref_luma.strides[0] // 2, w, h, int(poc),
+            mv.ctypes.data if mv is not None else None, int(qp), out.ctypes.data, len(out),
+        )
+        if rc < 0:
+            self._check(rc, "mlt_cu_predict_picture")
+        return out[:rc]
 
     def predict_batch_device(self, n: int, d_orgpred: int, d_pocqp: int, d_out: int, stream: int = 0):
         self._check(self._lib.mlt_cu_predict_batch_device(self._h, int(n), C.c_void_p(d_orgpred), C.c_void_p(d_pocqp), C.c_void_p(d_out),

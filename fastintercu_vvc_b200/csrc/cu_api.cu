@@ -56,6 +56,8 @@ struct mlt_cu_ctx {
         bool busy = false;
     } slot[2];
     uint64_t submitted = 0, collected = 0;
+    int16_t *d_pic = nullptr, *d_mv = nullptr; // mlt_cu_predict_picture: org + reference luma planes (same pitch), per-CU MVs
+    size_t pic_capacity = 0;
     float *d_dbg = nullptr;
     size_t dbg_bytes = 0;
     int last_n = 0;
@@ -285,6 +287,7 @@ void mlt_cu_destroy(mlt_cu_ctx *c)
     }
     for (auto &H : c->slot) if (H.done) cudaEventDestroy(H.done);
     cudaFree(c->d_blob); cudaFree(c->d_in); cudaFree(c->d_pq); cudaFree(c->d_cus); cudaFree(c->d_out); cudaFree(c->d_dbg);
+    cudaFree(c->d_pic); cudaFree(c->d_mv);
     cudaFreeHost(c->h_in); cudaFreeHost(c->h_pq); cudaFreeHost(c->h_out);
     for (cudaEvent_t e : c->ev_in) if (e) cudaEventDestroy(e);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -456,6 +459,50 @@ int mlt_cu_collect(mlt_cu_ctx *c, mlt_cu_result *out, int *n_out)
     H.busy = false;
     c->collected++;
     return MLT_OK;
+}
+
+int mlt_cu_picture_cu_count(int cu_size, int width, int height)
+{
+    if ((cu_size != 64 && cu_size != 32 && cu_size != 16) || width < 0 || height < 0) return MLT_E_INVAL;
+    return (width / cu_size) * (height / cu_size); // CUs of the size's raster lying fully inside the picture (EncCu.cpp:755)
+}
+
+int mlt_cu_predict_picture(mlt_cu_ctx *c, const int16_t *org_luma, int org_stride, const int16_t *ref_luma, int ref_stride, int width,
+                           int height, int poc, const int16_t *mv, int qp, mlt_cu_result *out, int capacity)
+{
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (!org_luma || !ref_luma || !out || width < c->size || height < c->size || org_stride < width || ref_stride < width)
+        return fail(c, MLT_E_INVAL, "bad picture geometry");
+    const int n = (width / c->size) * (height / c->size);
+    if (n > c->cap) return fail(c, MLT_E_BATCH, "picture has %d %d-px CUs > max_batch=%d", n, c->size, c->cap);
+    if (capacity < n) return fail(c, MLT_E_INVAL, "out holds %d results, the picture has %d CUs", capacity, n);
+    if (c->submitted != c->collected) return fail(c, MLT_E_STATE, "submitted batches must be collected first");
+    cudaStream_t s = c->stream;
+    const int pitch = (width + 7) & ~7; // rows 16-byte aligned on the device
+    const size_t plane = (size_t)pitch * height;
+    if (2 * plane > c->pic_capacity) {
+        if (c->d_pic) cudaFree(c->d_pic);
+        c->d_pic = nullptr;
+        c->pic_capacity = 0;
+        CU(cudaMalloc(&c->d_pic, 2 * plane * sizeof(int16_t)));
+        c->pic_capacity = 2 * plane;
+    }
+    if (mv && !c->d_mv) CU(cudaMalloc(&c->d_mv, (size_t)c->cap * 2 * sizeof(int16_t)));
+    int16_t *d_org = c->d_pic, *d_ref = c->d_pic + plane;
+    CU(cudaMemcpy2DAsync(d_org, (size_t)pitch * sizeof(int16_t), org_luma, (size_t)org_stride * sizeof(int16_t), (size_t)width * sizeof(int16_t),
+                         height, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpy2DAsync(d_ref, (size_t)pitch * sizeof(int16_t), ref_luma, (size_t)ref_stride * sizeof(int16_t), (size_t)width * sizeof(int16_t),
+                         height, cudaMemcpyHostToDevice, s));
+    if (mv) CU(cudaMemcpyAsync(c->d_mv, mv, (size_t)n * 2 * sizeof(int16_t), cudaMemcpyHostToDevice, s));
+    CU(launch_picture_cu_gather(d_org, d_ref, pitch, width, height, c->size, n, mv ? c->d_mv : nullptr, poc, qp, c->d_in, c->d_pq, s));
+    c->launches++;
+    rc = run_network(c, n, c->d_in, c->d_pq, c->d_out, s);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(c->h_out, c->d_out, (size_t)n * sizeof(mlt_cu_result), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s)); // also: the caller's planes / mv may be reused after return
+    memcpy(out, c->h_out, (size_t)n * sizeof(mlt_cu_result));
+    return n;
 }
 
 int mlt_cu_predict_batch_device(mlt_cu_ctx *c, int n, const int16_t *d_orgpred, const int32_t *d_pocqp, mlt_cu_result *d_out,

@@ -169,6 +169,10 @@ cudaError_t launch_head_f(const HeadParams &p, cudaStream_t s);
 // reference luma plane with replicated borders (Picture.cpp:1117); writes plane 1 of the dense [n][2][128][128] batch
 struct PicCtu { int32_t x, y, mvx, mvy; }; // CTU position and MV in luma samples
 cudaError_t launch_picture_pred(const int16_t *ref, int pitch, int w, int h, const PicCtu *ctus, int n, int16_t *out, cudaStream_t s);
+// the smaller-CU form: every size x size block of the picture's CU raster as a dense [n][2][size][size] batch (plane 0 = org
+// block, plane 1 = integer-MV prediction, mv = device [n][2] or nullptr) + its (poc, qp) pairs
+cudaError_t launch_picture_cu_gather(const int16_t *org, const int16_t *ref, int pitch, int w, int h, int size, int n, const int16_t *mv, int poc,
+                                     int qp, int16_t *out, int32_t *pocqp, cudaStream_t s);
 
 // ---- misc
 cudaError_t launch_unpack_act(const __half *in, float *out, int nimg, const ActLayout &L, cudaStream_t s);

@@ -68,29 +68,73 @@ SplitPredictor::~SplitPredictor()
         if (c) mlt_cu_destroy(c);
 }
 
-int SplitPredictor::predictCu(int cuw, const int16_t *org, int orgStride, const int16_t *pred, int predStride, int poc, int qp)
+mlt_cu_ctx *SplitPredictor::cuContext(int idx, int cuw, int minBatch)
 {
-    const int idx = cuw == 64 ? 0 : (cuw == 32 ? 1 : (cuw == 16 ? 2 : -1));
-    if (idx < 0 || m_disabled) return -1;
+    if (m_cuTried[idx] && m_cu[idx] && minBatch > m_cuCap[idx]) { // a picture pre-pass needs a larger batch than the per-CU calls
+        mlt_cu_destroy(m_cu[idx]);
+        m_cu[idx] = nullptr;
+        m_cuTried[idx] = false;
+    }
     if (!m_cuTried[idx]) { // the reference re-loads MLTORPQ_splitMode_<cuw>.pt on every call (EncCu.cpp:894-900); here: once
         m_cuTried[idx] = true;
         char name[32];
         std::snprintf(name, sizeof name, "MLT_WEIGHTS_%d", cuw);
         const char *weights = std::getenv(name), *dev = std::getenv("MLT_DEVICE");
-        const int rc = weights ? mlt_cu_create(&m_cu[idx], weights, dev ? std::atoi(dev) : 0, cuw, 1024) : MLT_E_IO;
+        m_cuCap[idx] = minBatch > 1024 ? minBatch : 1024;
+        const int rc = weights ? mlt_cu_create(&m_cu[idx], weights, dev ? std::atoi(dev) : 0, cuw, m_cuCap[idx]) : MLT_E_IO;
         if (rc != MLT_OK) {
             std::fprintf(stderr, "error loading the model\n");
             std::fprintf(stderr, "mlt_hook: %s -> %d (%s)\n", name, rc, mlt_strerror(rc));
             m_cu[idx] = nullptr;
         }
     }
-    if (!m_cu[idx]) return -1;
+    return m_cu[idx];
+}
+
+int SplitPredictor::predictCu(int cuw, const int16_t *org, int orgStride, const int16_t *pred, int predStride, int poc, int qp)
+{
+    const int idx = cuw == 64 ? 0 : (cuw == 32 ? 1 : (cuw == 16 ? 2 : -1));
+    if (idx < 0 || m_disabled) return -1;
+    mlt_cu_ctx *ctx = cuContext(idx, cuw, 1);
+    if (!ctx) return -1;
     mlt_cu_result r;
-    if (mlt_cu_predict(m_cu[idx], org, orgStride, pred, predStride, poc, qp, &r) != MLT_OK) {
+    if (mlt_cu_predict(ctx, org, orgStride, pred, predStride, poc, qp, &r) != MLT_OK) {
         std::fprintf(stderr, "error\n"); // EncCu.cpp:925
         return -1;
     }
     return r.split[0];
+}
+
+bool SplitPredictor::prepassPictureCu(int cuw, const int16_t *orgLuma, int orgStride, const int16_t *refLuma, int refStride, int width,
+                                      int height, int poc, const int16_t *mv, int sliceQp)
+{
+    const int idx = cuw == 64 ? 0 : (cuw == 32 ? 1 : (cuw == 16 ? 2 : -1));
+    if (idx < 0 || m_disabled) return false;
+    m_cuSplit[idx].clear();
+    m_cuCols[idx] = m_cuRows[idx] = 0;
+    const int n = mlt_cu_picture_cu_count(cuw, width, height);
+    if (n <= 0) return false;
+    mlt_cu_ctx *ctx = cuContext(idx, cuw, n);
+    if (!ctx) return false;
+    std::vector<mlt_cu_result> res((size_t)n);
+    if (mlt_cu_predict_picture(ctx, orgLuma, orgStride, refLuma, refStride, width, height, poc, mv, sliceQp, res.data(), n) != n) {
+        std::fprintf(stderr, "error\n"); // EncCu.cpp:925; the CUs of this size then run full RDO
+        return false;
+    }
+    m_cuCols[idx] = width / cuw;
+    m_cuRows[idx] = height / cuw;
+    m_cuSplit[idx].resize((size_t)n);
+    for (int i = 0; i < n; i++) m_cuSplit[idx][(size_t)i] = res[(size_t)i].split[0]; // the hook's elements()[0] branch (EncCu.cpp:916-919)
+    return true;
+}
+
+int SplitPredictor::pictureSplitCu(int cuw, int cux, int cuy) const
+{
+    const int idx = cuw == 64 ? 0 : (cuw == 32 ? 1 : (cuw == 16 ? 2 : -1));
+    if (idx < 0 || m_cuSplit[idx].empty() || cux < 0 || cuy < 0 || (cux % cuw) || (cuy % cuw)) return -1;
+    const int col = cux / cuw, row = cuy / cuw;
+    if (col >= m_cuCols[idx] || row >= m_cuRows[idx]) return -1;
+    return m_cuSplit[idx][(size_t)row * m_cuCols[idx] + col];
 }
 
 int SplitPredictor::predict(const int16_t *org, int orgStride, const int16_t *pred, int predStride, int poc, int qp)
@@ -109,6 +153,7 @@ bool SplitPredictor::beginPicture(const int16_t *orgLuma, int stride, int width,
 {
     m_picSplit.clear(); // decisions of the previous picture must never leak into this one
     m_picCols = m_picRows = 0;
+    for (int i = 0; i < 3; i++) { m_cuSplit[i].clear(); m_cuCols[i] = m_cuRows[i] = 0; }
     m_picW = width;
     m_picH = height;
     return m_ctx && mlt_begin_picture(m_ctx, orgLuma, stride, width, height, poc) == MLT_OK;

@@ -58,6 +58,13 @@ public:
     // first use.  -1 on failure or when that size has no weights.
     int predictCu(int cuw, const int16_t *org, int orgStride, const int16_t *pred, int predStride, int poc, int qp);
 
+    // The pre-pass for one smaller CU size (cuw = 64 / 32 / 16): every cuw x cuw block of the size's raster inside the picture
+    // in one batch (mlt_cu_predict_picture); pictureSplitCu reads the level-1 argmax (what predictCu returns) of the block
+    // whose top-left corner is (cux, cuy), or -1.  beginPicture() forgets these tables as well.
+    bool prepassPictureCu(int cuw, const int16_t *orgLuma, int orgStride, const int16_t *refLuma, int refStride, int width, int height,
+                          int poc, const int16_t *mv, int sliceQp);
+    int pictureSplitCu(int cuw, int cux, int cuy) const;
+
     ~SplitPredictor();
     SplitPredictor(const SplitPredictor &) = delete;
     SplitPredictor &operator=(const SplitPredictor &) = delete;
@@ -67,9 +74,13 @@ private:
     mlt_ctx *m_ctx = nullptr;
     mlt_cu_ctx *m_cu[3] = {nullptr, nullptr, nullptr}; // 64, 32, 16
     bool m_cuTried[3] = {false, false, false};
+    int m_cuCap[3] = {0, 0, 0};
     bool m_disabled = false;
     std::vector<int> m_picSplit; // pre-pass decisions of the current picture, eligible CTUs in raster order
     int m_picCols = 0, m_picRows = 0, m_picW = 0, m_picH = 0;
+    std::vector<int> m_cuSplit[3]; // per size: pre-pass decisions of the current picture, raster order
+    int m_cuCols[3] = {0, 0, 0}, m_cuRows[3] = {0, 0, 0};
+    mlt_cu_ctx *cuContext(int idx, int cuw, int minBatch);
 };
 
 // ---- restatement of the consumer's semantics (EncModeCtrl.cpp:95-149), used by tests only ------------------

@@ -55,6 +55,17 @@ MLT_API int mlt_cu_predict_batch_dense(mlt_cu_ctx *ctx, int n, const int16_t *or
  * synchronous calls are refused (MLT_E_STATE) while batches are in flight. */
 MLT_API int mlt_cu_submit_batch_dense(mlt_cu_ctx *ctx, int n, const int16_t *orgpred, const int32_t *pocqp);
 MLT_API int mlt_cu_collect(mlt_cu_ctx *ctx, mlt_cu_result *out, int *n_out);
+/* Frame-level pre-pass for one CU size (the CTU form and its rationale are in mltcnn.h,
+ * mlt_predict_picture): every cu_size x cu_size block of the picture's raster that lies fully inside the picture (the
+ * gate of EncCu.cpp:755 at cuw = cuh = cu_size; raster order, width / cu_size blocks per row) is inferred in ONE batch.
+ * Block i: org = the picture's original luma block, pred = integer-sample motion compensation out of `ref_luma` with
+ * replicated borders (Picture.cpp:1117) by mv[i] (x, y) -- mv = NULL: zero MV.  Both planes are width x height; they
+ * are gathered into the dense batch on the device.  Returns the number of results written
+ * (== mlt_cu_picture_cu_count) or a negative code.  Changes the encoder's decisions relative to the reference hook
+ * (different pred); the per-CU calls above remain the exact drop-in. */
+MLT_API int mlt_cu_picture_cu_count(int cu_size, int width, int height);
+MLT_API int mlt_cu_predict_picture(mlt_cu_ctx *ctx, const int16_t *org_luma, int org_stride, const int16_t *ref_luma, int ref_stride,
+                                   int width, int height, int poc, const int16_t *mv, int qp, mlt_cu_result *out, int capacity);
 /* Device-resident batch on the caller's stream (cudaStream_t as void*); asynchronous w.r.t. the host. */
 MLT_API int mlt_cu_predict_batch_device(mlt_cu_ctx *ctx, int n, const int16_t *d_orgpred, const int32_t *d_pocqp,
                                         mlt_cu_result *d_out, void *cuda_stream);

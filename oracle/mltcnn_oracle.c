@@ -418,12 +418,17 @@ int mlto_picture_ctus(int w, int h, int32_t *xy, int cap)
 
 static int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
-void mlto_picture_pred(const int16_t *ref, int ref_stride, int w, int h, int x, int y, int mvx, int mvy, int16_t *pred)
+void mlto_picture_block_pred(const int16_t *ref, int ref_stride, int w, int h, int size, int x, int y, int mvx, int mvy, int16_t *pred)
 {
     /* reading outside the picture returns the nearest border sample: that is what the replicated margins of a
      * reference picture hold (Picture.cpp:1117) */
-    for (int r = 0; r < MLTO_CTU; r++) {
+    for (int r = 0; r < size; r++) {
         const int16_t *row = ref + (size_t)clampi(y + r + mvy, 0, h - 1) * ref_stride;
-        for (int c = 0; c < MLTO_CTU; c++) pred[r * MLTO_CTU + c] = row[clampi(x + c + mvx, 0, w - 1)];
+        for (int c = 0; c < size; c++) pred[r * size + c] = row[clampi(x + c + mvx, 0, w - 1)];
     }
+}
+
+void mlto_picture_pred(const int16_t *ref, int ref_stride, int w, int h, int x, int y, int mvx, int mvy, int16_t *pred)
+{
+    mlto_picture_block_pred(ref, ref_stride, w, h, MLTO_CTU, x, y, mvx, mvy, pred);
 }

@@ -78,6 +78,9 @@ int mlto_picture_ctus(int w, int h, int32_t *xy, int cap);
 /* pred[r][c] = ref[clamp(y + r + mvy, 0, h-1)][clamp(x + c + mvx, 0, w-1)], r, c in [0, 128) */
 void mlto_picture_pred(const int16_t *ref, int ref_stride, int w, int h, int x, int y, int mvx, int mvy,
                        int16_t *pred /* [128*128] dense */);
+/* the same for a size x size block (the smaller-CU pre-pass, mlt_cu_predict_picture); pred = [size*size] dense */
+void mlto_picture_block_pred(const int16_t *ref, int ref_stride, int w, int h, int size, int x, int y, int mvx, int mvy,
+                             int16_t *pred);
 
 #ifdef __cplusplus
 }

@@ -33,6 +33,7 @@ def lib():
         L.mlto_picture_ctus.restype = C.c_int
         L.mlto_picture_ctus.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int]
         L.mlto_picture_pred.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.mlto_picture_block_pred.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -45,12 +46,15 @@ def picture_ctus(w: int, h: int) -> np.ndarray:
     return xy
 
 
-def picture_pred(ref: np.ndarray, x: int, y: int, mvx: int = 0, mvy: int = 0) -> np.ndarray:
-    """Integer-MV prediction block of the CTU at (x, y) from a border-replicated reference plane (frame-level pre-pass)."""
+def picture_pred(ref: np.ndarray, x: int, y: int, mvx: int = 0, mvy: int = 0, size: int = 128) -> np.ndarray:
+    """Integer-MV prediction block (size x size, top-left at (x, y)) from a border-replicated reference plane (frame-level pre-pass)."""
     assert ref.dtype == np.int16 and ref.ndim == 2 and ref.strides[1] == 2
     h, w = ref.shape
-    out = np.zeros((128, 128), np.int16)
-    lib().mlto_picture_pred(ref.ctypes.data, ref.strides[0] // 2, w, h, int(x), int(y), int(mvx), int(mvy), out.ctypes.data)
+    out = np.zeros((size, size), np.int16)
+    if size == 128:
+        lib().mlto_picture_pred(ref.ctypes.data, ref.strides[0] // 2, w, h, int(x), int(y), int(mvx), int(mvy), out.ctypes.data)
+    else:
+        lib().mlto_picture_block_pred(ref.ctypes.data, ref.strides[0] // 2, w, h, size, int(x), int(y), int(mvx), int(mvy), out.ctypes.data)
     return out
 
 

@@ -249,9 +249,10 @@ def test_cpp_hook_cu_branch_matches_the_binding(ctx):
     assert r.returncode == 0, r.stdout + r.stderr
     assert off.returncode == 4 and off.stdout == ""  # gate as shipped by the reference: smaller CUs are not predicted
     rows = [tuple(map(int, l.split())) for l in r.stdout.strip().splitlines()]
-    assert [(x, y) for x, y, _ in rows] == [(i * size, j * size) for j in range(ny) for i in range(nx)]
+    assert [(x, y) for x, y, _, _ in rows] == [(i * size, j * size) for j in range(ny) for i in range(nx)]
     want = p.predict_batch_dense(cus, np.tile(np.array([[poc, qp]], np.int32), (nx * ny, 1)))["split"][:, 0]
-    assert [s for _, _, s in rows] == want.tolist()
+    assert [s for _, _, s, _ in rows] == want.tolist()
+    assert [s for _, _, _, s in rows] == want.tolist()  # the picture pre-pass (zero MV out of the same pred plane) agrees
 
 
 @pytest.mark.parametrize("size", [64, 16])
@@ -294,5 +295,53 @@ def test_cu_pipelined_submit_collect_matches_the_synchronous_call(size):
                 assert g.tobytes() == w.tobytes()
             assert extra.tobytes() == want[3].tobytes()
             assert p.predict_batch_dense(*batches[1]).tobytes() == want[1].tobytes()  # and the blocking call works again
+    finally:
+        os.unlink(path)
+
+
+@pytest.mark.parametrize("size", [64, 32, 16])
+def test_cu_picture_prepass_equals_the_dense_batch(size):
+    """mlt_cu_predict_picture (org + reference planes gathered into the batch ON THE DEVICE, integer MVs, replicated
+    borders) == mlt_cu_predict_batch_dense fed the oracle's gather of the same picture, byte for byte, raster order."""
+    import tempfile
+
+    import fastintercu_vvc_b200 as pkg
+    from fastintercu_vvc_b200 import MltError
+    from fastintercu_vvc_b200.synth import make_cu_state_dict
+    from tests.oracle_lib import picture_pred
+
+    rng = np.random.RandomState(40 + size)
+    w, h, margin = 416, 240, 8
+    base = (rng.randint(0, 1024, (h // 8 + 1, w // 8 + 1)).repeat(8, 0).repeat(8, 1)[:h, :w] * 3 // 4 + rng.randint(0, 256, (h, w))).astype(np.int16)
+    obuf = np.zeros((h + 2 * margin, w + 2 * margin + 5), np.int16)
+    rbuf = np.zeros_like(obuf)
+    org, ref = obuf[margin : margin + h, margin : margin + w], rbuf[margin : margin + h, margin : margin + w]
+    org[:] = base
+    ref[:] = np.clip(np.roll(base, (2, 1), (0, 1)).astype(np.int32) + rng.randint(-12, 13, (h, w)), 0, 1023).astype(np.int16)
+    cols, rows = w // size, h // size
+    n = cols * rows
+    mv = rng.randint(-20, 21, (n, 2)).astype(np.int16)
+    for i, v in enumerate([(0, 0), (8, 0), (1, 0), (-3, 5), (-500, -300), (500, 300), (7, -1), (-8, 16)][:n]):
+        mv[i] = v
+    with tempfile.NamedTemporaryFile(suffix=".mltw", delete=False) as f:
+        path = f.name
+    try:
+        pkg.write_cu_blob(make_cu_state_dict(10, size), size, path)
+        with pkg.MltCuPredictor(path, size, device=0, max_batch=n) as p:
+            for mvs in (None, mv):
+                got = p.predict_picture(org, ref, poc=4, qp=35, mv=mvs)
+                assert len(got) == n
+                dense = np.empty((n, 2, size, size), np.int16)
+                for i in range(n):
+                    x, y = (i % cols) * size, (i // cols) * size
+                    mx, my = (0, 0) if mvs is None else mvs[i]
+                    dense[i, 0] = org[y : y + size, x : x + size]
+                    dense[i, 1] = picture_pred(ref, x, y, mx, my, size=size)
+                want = p.predict_batch_dense(dense, np.tile(np.array([[4, 35]], np.int32), (n, 1)))
+                assert got.tobytes() == want.tobytes()
+        with pkg.MltCuPredictor(path, size, device=0, max_batch=n - 1) as small:
+            with pytest.raises(MltError) as e:
+                small.predict_picture(org, ref, 4, 35)
+            assert e.value.rc == -7  # MLT_E_BATCH
     finally:
         os.unlink(path)

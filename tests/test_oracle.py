@@ -148,3 +148,7 @@ def test_picture_pred_equals_padded_reference_window():
         got = picture_pred(ref, x, y, mvx, mvy)
         want = padded[m + y + mvy : m + y + mvy + 128, m + x + mvx : m + x + mvx + 128]
         assert np.array_equal(got, want), (x, y, mvx, mvy)
+    for size, (x, y, mvx, mvy) in ((64, (320, 128, 9, -3)), (32, (384, 192, 40, 60)), (16, (400, 224, -1, 1)), (16, (0, 0, -17, -33))):
+        got = picture_pred(ref, x, y, mvx, mvy, size=size)
+        want = padded[m + y + mvy : m + y + mvy + size, m + x + mvx : m + x + mvx + size]
+        assert np.array_equal(got, want), (size, x, y, mvx, mvy)
