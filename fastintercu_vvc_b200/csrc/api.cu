@@ -387,7 +387,8 @@ int enqueue_host_batch(mlt_ctx *c, int slot, int n, const int16_t *src, const ml
     int sizes[mlt_ctx::MAX_CHUNKS], nchunks = 0;
     // A pipelined batch submitted while another one is still in flight hides its whole copy under that batch's kernels:
     // two equal chunks (the two activation sets / compute streams, like a device-resident batch), no growing schedule.
-    const bool hidden = c->submitted != c->collected;
+    static const bool no_hidden = getenv("MLT_NO_HIDDEN") != nullptr; // A/B switch for measurements
+    const bool hidden = c->submitted != c->collected && !no_hidden;
     if (n < 1024 && !(hidden && n >= 2 * 240)) sizes[nchunks++] = n;
     else if (hidden && n / 2 <= c->set[1].cap) {
         sizes[nchunks++] = n - n / 2;
