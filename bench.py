@@ -552,6 +552,17 @@ def main():
         pred.begin_picture(pic_org, 3)
         pred.predict_picture(pic_ref, 32, mv=pic_mv)
     prepass_pinned_ms = (time.perf_counter() - t0) / 20 * 1e3
+    # the same with the MVs estimated on the device first (integer full search, +-8 samples), reference plane uploaded once
+    for _ in range(3):
+        pred.begin_picture(pic_org, 3)
+        me_mv, _ = pred.estimate_picture_mv(pic_ref, 8)
+        pred.predict_picture(None, 32, mv=me_mv)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        pred.begin_picture(pic_org, 3)
+        me_mv, _ = pred.estimate_picture_mv(pic_ref, 8)
+        pred.predict_picture(None, 32, mv=me_mv)
+    prepass_me_ms = (time.perf_counter() - t0) / 20 * 1e3
     pred.unpin_host_buffer(pic_org)
     pred.unpin_host_buffer(pic_ref)
 
@@ -602,7 +613,7 @@ def main():
                              "note": "BASELINE config 2 taken literally: ONE 1080p frame (120 CTUs) per call, back to back"},
             "ctu_latency_us": ctu_us,
             "picture_prepass": {"ctus": CTUS_PER_FRAME, "ms_per_picture": prepass_pinned_ms, "ctus_per_s": CTUS_PER_FRAME / (prepass_pinned_ms * 1e-3),
-                                "ms_per_picture_pageable": prepass_ms,
+                                "ms_per_picture_pageable": prepass_ms, "ms_per_picture_with_block_matching_r8": prepass_me_ms,
                                 "h2d_bytes_per_picture": int(2 * 1920 * 1080 * 2 + CTUS_PER_FRAME * (16 + 32)),
                                 "serial_hook_calls_ms": ctu_us * CTUS_PER_FRAME * 1e-3,
                                 "note": "section 8f rank 2: mlt_begin_picture + mlt_predict_picture on one 1920x1080 picture, host planes page-locked once "

@@ -66,6 +66,7 @@ EXPORTS = {
     "mlt_pin_host_buffer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
     "mlt_unpin_host_buffer": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mlt_picture_ctu_count": (C.c_int, [C.c_void_p]),
+    "mlt_estimate_picture_mv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "mlt_predict_picture": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "mlt_debug_picture_pred": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "mlt_set_engine": (C.c_int, [C.c_void_p, C.c_int]),
@@ -253,9 +254,25 @@ class MltPredictor:
             self._check(n, "mlt_picture_ctu_count")
         return n
 
-    def predict_picture(self, ref_luma: np.ndarray, slice_qp: int, mv: np.ndarray | None = None, ctu_qp: np.ndarray | None = None) -> np.ndarray:
-        """All eligible CTUs of the picture begun, in raster order, from integer-MV prediction out of `ref_luma`."""
-        if ref_luma.dtype != np.int16 or ref_luma.ndim != 2 or ref_luma.strides[1] != 2:
+    def estimate_picture_mv(self, ref_luma: np.ndarray | None, search_range: int):
+        """Integer full-search block matching per eligible CTU on the device -> (mv [n, 2] int16 (x, y), cost [n] uint32).
+        ref_luma = None reuses the reference plane already uploaded for this picture."""
+        if ref_luma is not None and (ref_luma.dtype != np.int16 or ref_luma.ndim != 2 or ref_luma.strides[1] != 2):
+            raise ValueError("ref_luma must be an int16 2-D view")
+        n = self.picture_ctu_count()
+        mv, cost = np.zeros((n, 2), np.int16), np.zeros(n, np.uint32)
+        rc = self._lib.mlt_estimate_picture_mv(
+            self._h, ref_luma.ctypes.data if ref_luma is not None else None, ref_luma.strides[0] // 2 if ref_luma is not None else 0,
+            int(search_range), mv.ctypes.data, cost.ctypes.data,
+        )
+        if rc < 0:
+            self._check(rc, "mlt_estimate_picture_mv")
+        return mv[:rc], cost[:rc]
+
+    def predict_picture(self, ref_luma: np.ndarray | None, slice_qp: int, mv: np.ndarray | None = None, ctu_qp: np.ndarray | None = None) -> np.ndarray:
+        """All eligible CTUs of the picture begun, in raster order, from integer-MV prediction out of `ref_luma` (None: the
+        reference plane already on the device, e.g. after estimate_picture_mv)."""
+        if ref_luma is not None and (ref_luma.dtype != np.int16 or ref_luma.ndim != 2 or ref_luma.strides[1] != 2):
             raise ValueError("ref_luma must be an int16 2-D view")
         n = self.picture_ctu_count()
         if mv is not None:
@@ -268,7 +285,8 @@ class MltPredictor:
                 raise ValueError(f"ctu_qp must be [{n}]")
         out = np.zeros(n, RESULT_DTYPE)
         rc = self._lib.mlt_predict_picture(
-            self._h, ref_luma.ctypes.data, ref_luma.strides[0] // 2, mv.ctypes.data if mv is not None else None,
+            self._h, ref_luma.ctypes.data if ref_luma is not None else None, ref_luma.strides[0] // 2 if ref_luma is not None else 0,
+            mv.ctypes.data if mv is not None else None,
             ctu_qp.ctypes.data if ctu_qp is not None else None, int(slice_qp), out.ctypes.data, n,
         )
         if rc < 0:

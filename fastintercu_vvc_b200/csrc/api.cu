@@ -101,6 +101,9 @@ struct mlt_ctx {
     int16_t *d_ref = nullptr; // reference-picture luma of the frame-level pre-pass (mlt_predict_picture), same pitch as d_pic
     size_t ref_capacity = 0;
     PicCtu *d_pic_ctus = nullptr, *h_pic_ctus = nullptr; // eligible CTUs of the picture: position + integer MV
+    bool ref_valid = false;   // d_ref holds a reference plane uploaded for the picture begun
+    unsigned *d_me_cost = nullptr, *d_me_best = nullptr, *h_me_best = nullptr; // block matching: [n][(2R+1)^2] scratch, [n] winners
+    int16_t *d_me_mv = nullptr, *h_me_mv = nullptr;
     int last_n = 0;
     uint64_t launches = 0;
     bool profiling = false;
@@ -502,6 +505,7 @@ void mlt_destroy(mlt_ctx *c)
     for (auto &H : c->slot) if (H.done) cudaEventDestroy(H.done);
     cudaFree(c->scratch_f); cudaFree(c->d_blob); cudaFree(c->d_in); cudaFree(c->d_ctus); cudaFree(c->d_out);
     cudaFree(c->d_dbg); cudaFree(c->d_pic); cudaFree(c->d_ref); cudaFree(c->d_pic_ctus);
+    cudaFree(c->d_me_cost); cudaFree(c->d_me_best); cudaFree(c->d_me_mv); cudaFreeHost(c->h_me_best); cudaFreeHost(c->h_me_mv);
     cudaFreeHost(c->h_pic_ctus); cudaFreeHost(c->h_in); cudaFreeHost(c->h_ctus); cudaFreeHost(c->h_out);
     for (cudaEvent_t e : c->prof_ev) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : c->ev_in) if (e) cudaEventDestroy(e);
@@ -757,6 +761,7 @@ int mlt_begin_picture(mlt_ctx *c, const int16_t *org_luma, int stride, int width
                          (size_t)width * sizeof(int16_t), height, cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream)); // the caller may reuse / modify its buffer after return
     c->pic_pitch = pitch; c->pic_w = width; c->pic_h = height; c->pic_poc = poc; c->pic_valid = true;
+    c->ref_valid = false; // a reference plane belongs to the picture it was uploaded for
     return MLT_OK;
 }
 
@@ -811,18 +816,9 @@ int mlt_picture_ctu_count(const mlt_ctx *c)
     return (c->pic_w / CTU) * (c->pic_h / CTU); // CTUs lying fully inside the picture (EncCu.cpp:755)
 }
 
-int mlt_predict_picture(mlt_ctx *c, const int16_t *ref_luma, int ref_stride, const int16_t *mv, const int32_t *ctu_qp, int slice_qp,
-                        mlt_result *out, int capacity)
+// upload the reference plane of the picture begun (same pitch as the org plane) and make sure the CTU list buffers exist
+static int upload_reference(mlt_ctx *c, const int16_t *ref_luma, int ref_stride)
 {
-    int rc = check_ctx(c);
-    if (rc) return rc;
-    if (!c->pic_valid) return fail(c, MLT_E_STATE, "mlt_begin_picture has not been called");
-    if (!ref_luma || !out || ref_stride < c->pic_w) return fail(c, MLT_E_INVAL, "bad reference picture");
-    const int cols = c->pic_w / CTU, n = cols * (c->pic_h / CTU);
-    if (n > c->max_batch) return fail(c, MLT_E_BATCH, "picture has %d eligible CTUs > max_batch=%d", n, c->max_batch);
-    if (capacity < n) return fail(c, MLT_E_INVAL, "out holds %d results, the picture has %d eligible CTUs", capacity, n);
-    if (c->submitted != c->collected) return fail(c, MLT_E_STATE, "submitted batches must be collected first");
-    cudaStream_t s = c->stream;
     const size_t need = (size_t)c->pic_pitch * c->pic_h;
     if (need > c->ref_capacity) {
         if (c->d_ref) cudaFree(c->d_ref);
@@ -831,12 +827,70 @@ int mlt_predict_picture(mlt_ctx *c, const int16_t *ref_luma, int ref_stride, con
         CU(cudaMalloc(&c->d_ref, need * sizeof(int16_t)));
         c->ref_capacity = need;
     }
+    c->ref_valid = false;
+    CU(cudaMemcpy2DAsync(c->d_ref, (size_t)c->pic_pitch * sizeof(int16_t), ref_luma, (size_t)ref_stride * sizeof(int16_t),
+                         (size_t)c->pic_w * sizeof(int16_t), c->pic_h, cudaMemcpyHostToDevice, c->stream));
+    c->ref_valid = true;
+    return MLT_OK;
+}
+
+static int ensure_pic_ctus(mlt_ctx *c)
+{
     if (!c->d_pic_ctus) {
         CU(cudaMalloc(&c->d_pic_ctus, (size_t)c->max_batch * sizeof(PicCtu)));
         CU(cudaMallocHost(&c->h_pic_ctus, (size_t)c->max_batch * sizeof(PicCtu)));
     }
-    CU(cudaMemcpy2DAsync(c->d_ref, (size_t)c->pic_pitch * sizeof(int16_t), ref_luma, (size_t)ref_stride * sizeof(int16_t),
-                         (size_t)c->pic_w * sizeof(int16_t), c->pic_h, cudaMemcpyHostToDevice, s));
+    return MLT_OK;
+}
+
+int mlt_estimate_picture_mv(mlt_ctx *c, const int16_t *ref_luma, int ref_stride, int range, int16_t *mv_out, uint32_t *cost_out)
+{
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (!c->pic_valid) return fail(c, MLT_E_STATE, "mlt_begin_picture has not been called");
+    if (!mv_out || range < 0 || range > MLT_ME_MAX_RANGE) return fail(c, MLT_E_INVAL, "bad argument (range 0..%d)", MLT_ME_MAX_RANGE);
+    if (ref_luma ? ref_stride < c->pic_w : !c->ref_valid) return fail(c, ref_luma ? MLT_E_INVAL : MLT_E_STATE, "no reference picture");
+    const int cols = c->pic_w / CTU, n = cols * (c->pic_h / CTU);
+    if (n > c->max_batch) return fail(c, MLT_E_BATCH, "picture has %d eligible CTUs > max_batch=%d", n, c->max_batch);
+    if (c->submitted != c->collected) return fail(c, MLT_E_STATE, "submitted batches must be collected first");
+    cudaStream_t s = c->stream;
+    if (ref_luma && (rc = upload_reference(c, ref_luma, ref_stride)) != MLT_OK) return rc;
+    if ((rc = ensure_pic_ctus(c)) != MLT_OK) return rc;
+    if (!c->d_me_cost) {
+        constexpr int DMAX = 2 * MLT_ME_MAX_RANGE + 1;
+        CU(cudaMalloc(&c->d_me_cost, (size_t)c->max_batch * DMAX * DMAX * sizeof(unsigned)));
+        CU(cudaMalloc(&c->d_me_best, (size_t)c->max_batch * sizeof(unsigned)));
+        CU(cudaMalloc(&c->d_me_mv, (size_t)c->max_batch * 2 * sizeof(int16_t)));
+        CU(cudaMallocHost(&c->h_me_best, (size_t)c->max_batch * sizeof(unsigned)));
+        CU(cudaMallocHost(&c->h_me_mv, (size_t)c->max_batch * 2 * sizeof(int16_t)));
+    }
+    for (int i = 0; i < n; i++) c->h_pic_ctus[i] = PicCtu{(i % cols) * CTU, (i / cols) * CTU, 0, 0};
+    CU(cudaMemcpyAsync(c->d_pic_ctus, c->h_pic_ctus, (size_t)n * sizeof(PicCtu), cudaMemcpyHostToDevice, s));
+    CU(launch_picture_me(c->d_pic, c->d_ref, c->pic_pitch, c->pic_w, c->pic_h, c->d_pic_ctus, n, range, c->d_me_cost, c->d_me_mv, c->d_me_best, s));
+    c->launches += 2;
+    CU(cudaMemcpyAsync(c->h_me_mv, c->d_me_mv, (size_t)n * 2 * sizeof(int16_t), cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(c->h_me_best, c->d_me_best, (size_t)n * sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    memcpy(mv_out, c->h_me_mv, (size_t)n * 2 * sizeof(int16_t));
+    if (cost_out) memcpy(cost_out, c->h_me_best, (size_t)n * sizeof(uint32_t));
+    return n;
+}
+
+int mlt_predict_picture(mlt_ctx *c, const int16_t *ref_luma, int ref_stride, const int16_t *mv, const int32_t *ctu_qp, int slice_qp,
+                        mlt_result *out, int capacity)
+{
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (!c->pic_valid) return fail(c, MLT_E_STATE, "mlt_begin_picture has not been called");
+    if (!out || (ref_luma && ref_stride < c->pic_w)) return fail(c, MLT_E_INVAL, "bad reference picture");
+    if (!ref_luma && !c->ref_valid) return fail(c, MLT_E_STATE, "no reference picture uploaded for this picture");
+    const int cols = c->pic_w / CTU, n = cols * (c->pic_h / CTU);
+    if (n > c->max_batch) return fail(c, MLT_E_BATCH, "picture has %d eligible CTUs > max_batch=%d", n, c->max_batch);
+    if (capacity < n) return fail(c, MLT_E_INVAL, "out holds %d results, the picture has %d eligible CTUs", capacity, n);
+    if (c->submitted != c->collected) return fail(c, MLT_E_STATE, "submitted batches must be collected first");
+    cudaStream_t s = c->stream;
+    if (ref_luma && (rc = upload_reference(c, ref_luma, ref_stride)) != MLT_OK) return rc;
+    if ((rc = ensure_pic_ctus(c)) != MLT_OK) return rc;
     for (int i = 0; i < n; i++) {
         const int x = (i % cols) * CTU, y = (i / cols) * CTU;
         c->h_pic_ctus[i] = PicCtu{x, y, mv ? mv[2 * i] : 0, mv ? mv[2 * i + 1] : 0};

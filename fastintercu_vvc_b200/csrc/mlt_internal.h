@@ -174,6 +174,13 @@ cudaError_t launch_picture_pred(const int16_t *ref, int pitch, int w, int h, con
 cudaError_t launch_picture_cu_gather(const int16_t *org, const int16_t *ref, int pitch, int w, int h, int size, int n, const int16_t *mv, int poc,
                                      int qp, int16_t *out, int32_t *pocqp, cudaStream_t s);
 
+// ---- picture_me.cu : integer full-search block matching per eligible CTU (pre-pass MVs); R <= MLT_ME_MAX_RANGE
+constexpr int MLT_ME_MAX_RANGE = 16;
+constexpr size_t picture_me_smem_bytes(int R) { return (size_t)(16 * MLT_CTU_SIZE + (16 + 2 * R) * (MLT_CTU_SIZE + 2 * R + 2)) * sizeof(int16_t); }
+// cost: scratch [n][(2R+1)^2] u32; mv: [n][2] int16 (x, y); best_cost: [n] u32 or nullptr.  2 kernels + 1 memset.
+cudaError_t launch_picture_me(const int16_t *org, const int16_t *ref, int pitch, int w, int h, const PicCtu *ctus, int n, int R, unsigned *cost,
+                              int16_t *mv, unsigned *best_cost, cudaStream_t s);
+
 // ---- misc
 cudaError_t launch_unpack_act(const __half *in, float *out, int nimg, const ActLayout &L, cudaStream_t s);
 

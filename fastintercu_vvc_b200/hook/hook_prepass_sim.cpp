@@ -3,7 +3,8 @@
 // prepassPicture(ref, mv, sliceQp) once, then the CTU raster reads pictureSplit(x, y) under the unchanged useCNN gate.
 // Used by tests/test_gpu_parity.py to check the C++ path against the per-CTU drop-in call on the GPU.
 //   file: int32 {width, height, stride, poc, slice_qp, has_mv}, int16 org[height][stride], int16 ref[height][stride],
-//         then if has_mv: int16 mv[n][2] for the n eligible CTUs (raster order)
+//         then if has_mv == 1: int16 mv[n][2] for the n eligible CTUs (raster order); has_mv < 0: MVs from the library's
+//         block matching with search range -has_mv
 //   out : one line per CTU of the raster (partial ones included): "x y eligible split"
 #include <cstdio>
 #include <cstdlib>
@@ -24,13 +25,13 @@ int main(int argc, char **argv)
     if (std::fread(ref.data(), sizeof(int16_t), ref.size(), f) != ref.size()) return 2;
     const int n = (w / 128) * (h / 128);
     std::vector<int16_t> mv((size_t)2 * n);
-    if (hasMv && std::fread(mv.data(), sizeof(int16_t), mv.size(), f) != mv.size()) return 2;
+    if (hasMv == 1 && std::fread(mv.data(), sizeof(int16_t), mv.size(), f) != mv.size()) return 2;
     std::fclose(f);
     mlt_hook::SplitPredictor &p = mlt_hook::SplitPredictor::instance();
     if (!p.enabled()) { std::fprintf(stderr, "predictor disabled\n"); return 3; }
     if (p.pictureSplit(0, 0) != -1) return 5; // nothing before the first pre-pass
     if (!p.beginPicture(org.data(), stride, w, h, poc)) return 3;
-    if (!p.prepassPicture(ref.data(), stride, hasMv ? mv.data() : nullptr, qp)) return 3;
+    if (!p.prepassPicture(ref.data(), stride, hasMv == 1 ? mv.data() : nullptr, qp, hasMv < 0 ? -hasMv : 0)) return 3;
     for (int y = 0; y < h; y += 128)
         for (int x = 0; x < w; x += 128) {
             const bool use = mlt_hook::useCNN(0, false, 128, 128, x, y, w, h);

@@ -165,7 +165,14 @@ bool SplitPredictor::prepassFromEnv()
     return s && std::strcmp(s, "0") != 0;
 }
 
-bool SplitPredictor::prepassPicture(const int16_t *refLuma, int refStride, const int16_t *mv, int sliceQp)
+int SplitPredictor::prepassRangeFromEnv()
+{
+    const char *s = std::getenv("MLT_PREPASS_RANGE");
+    const int r = s ? std::atoi(s) : 0;
+    return r < 0 ? 0 : (r > 16 ? 16 : r);
+}
+
+bool SplitPredictor::prepassPicture(const int16_t *refLuma, int refStride, const int16_t *mv, int sliceQp, int searchRange)
 {
     m_picSplit.clear();
     m_picCols = m_picRows = 0;
@@ -173,6 +180,16 @@ bool SplitPredictor::prepassPicture(const int16_t *refLuma, int refStride, const
     const int n = mlt_picture_ctu_count(m_ctx);
     if (n <= 0) return false;
     std::vector<mlt_result> res((size_t)n);
+    std::vector<int16_t> est;
+    if (!mv && searchRange > 0) { // motion from the library's block matching; the plane it uploaded is reused below
+        est.resize((size_t)2 * n);
+        if (mlt_estimate_picture_mv(m_ctx, refLuma, refStride, searchRange, est.data(), nullptr) != n) {
+            std::fprintf(stderr, "error\n");
+            return false;
+        }
+        mv = est.data();
+        refLuma = nullptr;
+    }
     const int got = mlt_predict_picture(m_ctx, refLuma, refStride, mv, nullptr, sliceQp, res.data(), n);
     if (got != n) {
         std::fprintf(stderr, "error\n"); // EncCu.cpp:925; every CTU of this picture then runs full RDO

@@ -49,7 +49,10 @@ public:
     // prediction -- integer-MV motion compensation out of `refLuma` (border-replicated, Picture.cpp:1117); `mv` = [n][2]
     // (x, y) per eligible CTU in raster order or nullptr for zero MV.  xCompressCU then reads pictureSplit(cux, cuy)
     // instead of calling predict(): -1 when the CTU is not eligible / no pre-pass ran for this picture / it failed.
-    bool prepassPicture(const int16_t *refLuma, int refStride, const int16_t *mv, int sliceQp);
+    // searchRange > 0 with mv == nullptr: the MVs come from the library's integer full search (mlt_estimate_picture_mv,
+    // +-searchRange samples, <= 16; env MLT_PREPASS_RANGE), the reference plane is uploaded once for both steps.
+    bool prepassPicture(const int16_t *refLuma, int refStride, const int16_t *mv, int sliceQp, int searchRange = 0);
+    static int prepassRangeFromEnv(); // env MLT_PREPASS_RANGE (0 = zero MV)
     int pictureSplit(int cux, int cuy) const;
     static bool prepassFromEnv(); // env MLT_PREPASS=1
 

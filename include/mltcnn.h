@@ -136,6 +136,14 @@ MLT_API int mlt_predict_ctu_in_picture(mlt_ctx *ctx, int x, int y, const int16_t
  * decisions relative to the reference hook (different pred) and needs its own BD-rate study; the per-CTU calls above
  * remain the exact drop-in. */
 MLT_API int mlt_picture_ctu_count(const mlt_ctx *ctx);
+/* Optional motion for the pre-pass: integer full-search block matching on the device, one MV per eligible CTU --
+ * cost(dx, dy) = sum over the 128x128 block of |org - ref(clamp(x + dx), clamp(y + dy))| for dx, dy in [-range, range]
+ * (range <= 16), reference borders replicated; the smallest (cost, preference) wins, preference 0 = the zero MV, then
+ * raster order of (dy, dx).  mv_out: [n][2] (x, y), cost_out: [n] winning costs or NULL.  The reference plane stays
+ * on the device: a following mlt_predict_picture may pass ref_luma = NULL to reuse it (and ref_luma = NULL here reuses
+ * the plane of a previous call for the same picture).  Returns n or a negative code. */
+MLT_API int mlt_estimate_picture_mv(mlt_ctx *ctx, const int16_t *ref_luma, int ref_stride, int range, int16_t *mv_out,
+                            uint32_t *cost_out);
 MLT_API int mlt_predict_picture(mlt_ctx *ctx, const int16_t *ref_luma, int ref_stride, const int16_t *mv, const int32_t *ctu_qp,
                         int slice_qp, mlt_result *out, int capacity);
 

@@ -432,3 +432,29 @@ void mlto_picture_pred(const int16_t *ref, int ref_stride, int w, int h, int x, 
 {
     mlto_picture_block_pred(ref, ref_stride, w, h, MLTO_CTU, x, y, mvx, mvy, pred);
 }
+
+/* Integer full-search block matching of the CTU at (x, y) (the library's mlt_estimate_picture_mv): candidates dx, dy in
+ * [-range, range], cost = sum |org - ref(clamped)|; smallest (cost, preference) wins, preference 0 = zero MV, then raster
+ * order of (dy, dx).  Returns the winning cost. */
+uint32_t mlto_picture_me(const int16_t *org, int org_stride, const int16_t *ref, int ref_stride, int w, int h, int x, int y, int range,
+                         int16_t mv[2])
+{
+    const int D = 2 * range + 1, centre = range * D + range;
+    uint64_t best = ~(uint64_t)0;
+    for (int k = 0; k < D * D; k++) {
+        const int dy = k / D - range, dx = k % D - range;
+        uint32_t cost = 0;
+        for (int r = 0; r < MLTO_CTU; r++) {
+            const int16_t *o = org + (size_t)(y + r) * org_stride + x;
+            const int16_t *q = ref + (size_t)clampi(y + r + dy, 0, h - 1) * ref_stride;
+            for (int c = 0; c < MLTO_CTU; c++) {
+                const int d = (int)o[c] - (int)q[clampi(x + c + dx, 0, w - 1)];
+                cost += (uint32_t)(d < 0 ? -d : d);
+            }
+        }
+        const uint32_t pref = k == centre ? 0u : (k < centre ? (uint32_t)k + 1u : (uint32_t)k);
+        const uint64_t key = ((uint64_t)cost << 16) | pref;
+        if (key < best) { best = key; mv[0] = (int16_t)dx; mv[1] = (int16_t)dy; }
+    }
+    return (uint32_t)(best >> 16);
+}

@@ -82,6 +82,10 @@ void mlto_picture_pred(const int16_t *ref, int ref_stride, int w, int h, int x, 
 void mlto_picture_block_pred(const int16_t *ref, int ref_stride, int w, int h, int size, int x, int y, int mvx, int mvy,
                              int16_t *pred);
 
+/* integer full-search block matching of the CTU at (x, y), see mltcnn_oracle.c; mv = (x, y); returns the winning cost */
+uint32_t mlto_picture_me(const int16_t *org, int org_stride, const int16_t *ref, int ref_stride, int w, int h, int x, int y,
+                         int range, int16_t mv[2]);
+
 #ifdef __cplusplus
 }
 #endif

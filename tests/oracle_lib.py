@@ -33,6 +33,8 @@ def lib():
         L.mlto_picture_ctus.restype = C.c_int
         L.mlto_picture_ctus.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int]
         L.mlto_picture_pred.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.mlto_picture_me.restype = C.c_uint32
+        L.mlto_picture_me.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.mlto_picture_block_pred.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         _LIB = L
     return _LIB
@@ -145,3 +147,13 @@ class OracleCuModel:
         lg = np.empty((n, 15), np.float32)
         lib().mlto_cu_predict_batch(self.h, self.size, n, orgpred.ctypes.data, pocqp.ctypes.data, lg.ctypes.data, nthreads or (os.cpu_count() or 1))
         return lg
+
+
+def picture_me(org: np.ndarray, ref: np.ndarray, x: int, y: int, search_range: int):
+    """Integer full-search block matching of the CTU at (x, y): ((mvx, mvy), cost) -- the library's mlt_estimate_picture_mv."""
+    assert org.dtype == ref.dtype == np.int16 and org.shape == ref.shape and org.strides[1] == ref.strides[1] == 2
+    h, w = org.shape
+    mv = np.zeros(2, np.int16)
+    cost = lib().mlto_picture_me(org.ctypes.data, org.strides[0] // 2, ref.ctypes.data, ref.strides[0] // 2, w, h, int(x), int(y),
+                                 int(search_range), mv.ctypes.data)
+    return (int(mv[0]), int(mv[1])), int(cost)

@@ -401,6 +401,42 @@ def test_picture_prepass_equals_per_ctu_calls(blob):
         assert e.value.rc == -7  # MLT_E_BATCH: 120 eligible CTUs > max_batch
 
 
+@pytest.mark.parametrize("w,h,rng_", [(416, 240, 8), (416, 240, 16), (1920, 1080, 3), (416, 240, 0)])
+def test_picture_block_matching_is_bit_exact(blob, w, h, rng_):
+    """mlt_estimate_picture_mv (integer full search on the device) == the oracle's restatement: same MV and same cost for
+    every eligible CTU (ties included: flat blocks are planted), and the MVs feed mlt_predict_picture with the
+    reference plane reused on the device."""
+    from fastintercu_vvc_b200 import MltError, MltPredictor
+    from tests.oracle_lib import picture_me
+
+    org, ref, xy, _ = _prepass_picture(w, h, 31)
+    n = len(xy)
+    ref[:] = np.clip(np.roll(org, (3, -2), (0, 1)).astype(np.int32) + np.random.RandomState(2).randint(-3, 4, org.shape), 0, 1023).astype(np.int16)
+    org[0:128, 0:128] = 300  # a flat CTU against a flat reference area: every candidate inside it ties
+    ref[0:140, 0:140] = 300
+    with MltPredictor(blob, device=0, max_batch=max(n, 8)) as p:
+        p.begin_picture(org, poc=5)
+        with pytest.raises(MltError):
+            p.estimate_picture_mv(None, rng_)  # no reference plane uploaded for this picture yet
+        with pytest.raises(MltError):
+            p.estimate_picture_mv(ref, 17)
+        mv, cost = p.estimate_picture_mv(ref, rng_)
+        assert mv.shape == (n, 2)
+        for i, (x, y) in enumerate(xy):
+            want_mv, want_cost = picture_me(org, ref, x, y, rng_)
+            assert (int(mv[i, 0]), int(mv[i, 1])) == want_mv and int(cost[i]) == want_cost, (i, x, y)
+        if rng_ >= 3:
+            assert sum(1 for v in mv if tuple(v) == (-2, 3)) >= n // 2  # the planted motion is found
+        mv2, cost2 = p.estimate_picture_mv(None, rng_)  # plane reused, run-to-run identical
+        assert np.array_equal(mv, mv2) and np.array_equal(cost, cost2)
+        a = p.predict_picture(None, 33, mv=mv)
+        b = p.predict_picture(ref, 33, mv=mv)
+        assert a.tobytes() == b.tobytes()
+        p.begin_picture(org, poc=6)
+        with pytest.raises(MltError):
+            p.predict_picture(None, 33)  # the reference plane belonged to the previous picture
+
+
 def test_cpp_hook_prepass_drives_the_library(pred, blob):
     """The C++ hook's prepassPicture / pictureSplit pair over a 416x240 picture: decisions of
     the eligible CTUs equal the per-CTU drop-in call on the same prediction, partial CTUs carry none."""
@@ -417,12 +453,14 @@ def test_cpp_hook_prepass_drives_the_library(pred, blob):
     full_r = np.zeros((h, stride), np.int16)
     full_o[:, :w] = org
     full_r[:, :w] = ref
-    for has_mv in (0, 1):
+    pred.begin_picture(org, poc)
+    est_mv, _ = pred.estimate_picture_mv(ref, 6)
+    for has_mv in (0, 1, -6):
         with tempfile.NamedTemporaryFile(suffix=".bin", delete=False) as f:
             f.write(np.array([w, h, stride, poc, qp, has_mv], np.int32).tobytes())
             f.write(full_o.tobytes())
             f.write(full_r.tobytes())
-            if has_mv:
+            if has_mv == 1:
                 f.write(mv.tobytes())
             path = f.name
         try:
@@ -437,7 +475,7 @@ def test_cpp_hook_prepass_drives_the_library(pred, blob):
         assert [(x, y) for x, y, _, _ in elig] == [tuple(v) for v in xy]
         assert all(s == -1 for _, _, e, s in rows if not e)
         for i, (x, y, _, s) in enumerate(elig):
-            m = mv[i] if has_mv else (0, 0)
+            m = mv[i] if has_mv == 1 else (est_mv[i] if has_mv < 0 else (0, 0))
             want = pred.predict_ctu(org[y : y + 128, x : x + 128], picture_pred(ref, x, y, *m), poc, qp)["split_l3"]
             assert s == want
 

@@ -152,3 +152,23 @@ def test_picture_pred_equals_padded_reference_window():
         got = picture_pred(ref, x, y, mvx, mvy, size=size)
         want = padded[m + y + mvy : m + y + mvy + size, m + x + mvx : m + x + mvx + size]
         assert np.array_equal(got, want), (size, x, y, mvx, mvy)
+
+
+def test_picture_me_finds_planted_motion_and_prefers_zero_mv():
+    """Block matching restatement: a reference that is the original shifted by (dx, dy) gives MV (dx, dy) at cost 0 for
+    interior CTUs; a flat picture (every candidate ties) gives the zero MV; cost == numpy's SAD at the winner."""
+    from tests.oracle_lib import picture_me, picture_pred
+
+    rng = np.random.RandomState(9)
+    w, h = 416, 240
+    org = rng.randint(0, 1024, (h, w)).astype(np.int16)
+    for (dx, dy) in ((3, -2), (-5, 4), (0, 0), (6, 6)):
+        # ref(x + dx, y + dy) == org(x, y) wherever the shifted position is inside the picture
+        ref = np.roll(org, (dy, dx), (0, 1))
+        mv, cost = picture_me(org, ref, 128, 0, 6)
+        if 0 + dy >= 0:  # the CTU at (128, 0) only sees un-wrapped rows when dy >= 0
+            assert mv == (dx, dy) and cost == 0, (dx, dy, mv, cost)
+        blk = org[0:128, 128:256].astype(np.int64)
+        assert cost == np.abs(blk - picture_pred(ref, 128, 0, *mv).astype(np.int64)).sum()
+    flat = np.full((h, w), 512, np.int16)
+    assert picture_me(flat, flat, 256, 0, 4) == ((0, 0), 0)
