@@ -40,7 +40,7 @@ FLOP_PER_CTU = 1_134_562_340  # SURVEY.md section 8a (2*MAC, all 21 convs + 3 FC
 FLOP_CONV1 = 18_874_368
 FLOP_FC = 3_108
 FLOP_UMMA_PER_CTU = FLOP_PER_CTU - FLOP_CONV1 - FLOP_FC  # the 16 tcgen05 conv launches
-NCU_DRAM_BYTES_PER_CTU = 4_884_600  # measured: 18.757 GB per 3840-CTU step (profiles/r01/ncu_full_v11_summary.csv)
+NCU_DRAM_BYTES_PER_CTU = 4_838_900  # measured: 18.581 GB per 3840-CTU step (profiles/r01/ncu_full_v17_summary.csv; v11: 18.757 GB)
 METRIC = "mlt_cnn_split_ctus_per_s"
 
 
@@ -603,7 +603,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": ach, "peak": sustained, "unit": "TFLOP/s", "frac": ach / sustained,
-                         "traffic": NCU_DRAM_BYTES_PER_CTU * n, "traffic_note": "ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the launches of one 3840-CTU step (profiles/r01/ncu_full_v11_summary.csv), scaled to this step; algorithmic minimum is 65,536 B/CTU -- the rest is inter-layer fp16 activations",
+                         "traffic": NCU_DRAM_BYTES_PER_CTU * n, "traffic_note": "ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the launches of one 3840-CTU step (profiles/r01/ncu_full_v17_summary.csv), scaled to this step; algorithmic minimum is 65,536 B/CTU -- the rest is inter-layer fp16 activations",
                          "kernel": "stem_umma_kernel + conv_umma_kernel x15 (every tcgen05 launch of a step: all 21 convs)",
                          "peak_source": f"{how} bf16 sustained", "kernel_ms_per_step": umma_ms, "stem_ms": float(prof[0]),
                          "head_ms": float(prof[17]), "per_layer_ms": [round(float(x), 4) for x in prof[2:17]]},
