@@ -80,6 +80,20 @@ int main()
     setenv("MLT_WEIGHTS_64", "/nonexistent/cu64.mltw", 1);
     assert(p.predictCu(64, blk.data(), 128, blk.data(), 128, 1, 32) == -1); // no weights / no GPU -> -1, full RDO
     assert(p.predictCu(48, blk.data(), 128, blk.data(), 128, 1, 32) == -1);
+    // frame-level pre-pass: without a usable predictor nothing is ever reported as a decision
+    assert(p.pictureSplit(0, 0) == -1 && p.pictureSplitCu(64, 0, 0) == -1 && p.pictureSplitCu(48, 0, 0) == -1);
+    if (!p.enabled()) {
+        assert(!p.beginPicture(blk.data(), 128, 128, 128, 1));
+        assert(!p.prepassPicture(blk.data(), 128, nullptr, 32) && !p.prepassPicture(blk.data(), 128, nullptr, 32, 8));
+        assert(!p.prepassPictureCu(64, blk.data(), 128, blk.data(), 128, 128, 128, 1, nullptr, 32));
+        assert(p.pictureSplit(0, 0) == -1 && p.pictureSplitCu(64, 0, 0) == -1);
+    }
+    setenv("MLT_PREPASS", "1", 1);
+    setenv("MLT_PREPASS_RANGE", "40", 1);
+    assert(SplitPredictor::prepassFromEnv() && SplitPredictor::prepassRangeFromEnv() == 16);
+    setenv("MLT_PREPASS", "0", 1);
+    unsetenv("MLT_PREPASS_RANGE");
+    assert(!SplitPredictor::prepassFromEnv() && SplitPredictor::prepassRangeFromEnv() == 0);
     std::printf("test_hook: OK (predictor %s, predict -> %d)\n", p.enabled() ? "enabled" : "disabled", r);
     return 0;
 }
