@@ -421,7 +421,9 @@ int enqueue_host_batch(mlt_ctx *c, int slot, int n, const int16_t *src, const ml
     }
     int per = 0;
     for (int i = 0; i < nchunks; i++) per = sizes[i] > per ? sizes[i] : per;
-    const bool two = nchunks > 1 && !c->profiling; // chunks alternate between the two activation sets / compute streams
+    // chunks alternate between the two activation sets / compute streams (product engines only: the fp32 cross-check
+    // engine has ONE set of fp32 buffers, its chunks must stay on one stream)
+    const bool two = nchunks > 1 && !c->profiling && c->engine != 1;
     if (two) { CU(cudaEventRecord(c->ev_fork, s)); CU(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0)); } // descriptors uploaded
     for (int i = 0, off = 0; off < n; off += sizes[i], i++) {
         const int m = sizes[i];

@@ -523,6 +523,24 @@ def test_sliced_device_batch_matches_small_batches(blob, ctus):
     assert dev.tobytes() == host.tobytes()
 
 
+def test_fp32_engine_large_host_batch_is_chunk_safe(blob, oracle):
+    """The fp32 cross-check engine has one set of fp32 buffers: a host batch large enough to be chunked (>= 1024 CTUs) must
+    not spread its chunks over the two compute streams (found by tools/precision_large.py: garbage at n = 2048)."""
+    from fastintercu_vvc_b200 import MltPredictor
+
+    ctus, pq = ref_arch.synth_ctus(1100, 77)
+    with MltPredictor(blob, device=0, max_batch=1100) as p:
+        p.set_engine(1)
+        big = p.predict_batch_dense(ctus, pq).copy()
+        small = np.concatenate([p.predict_batch_dense(ctus[i : i + 275], pq[i : i + 275]) for i in range(0, 1100, 275)])
+        assert big.tobytes() == small.tobytes()
+        lg, sp = oracle.predict_batch(ctus[:64], pq[:64])
+        assert np.abs(big["logits"][:64] - lg).max() < 2e-4
+        p.set_engine(0)
+        prod = p.predict_batch_dense(ctus, pq)
+        assert np.abs(prod["probs"] - big["probs"]).max() <= PROB_TOL
+
+
 def test_errors(pred, blob, ctus):
     from fastintercu_vvc_b200 import MltError, MltPredictor
 
