@@ -805,7 +805,9 @@ int mlt_unpin_host_buffer(mlt_ctx *c, const void *ptr)
     int rc = check_ctx(c);
     if (rc) return rc;
     if (!ptr) return fail(c, MLT_E_INVAL, "null buffer");
+    if (c->submitted != c->collected) return fail(c, MLT_E_STATE, "submitted batches may still be reading host buffers: collect them first");
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     const cudaError_t e = cudaHostUnregister(const_cast<void *>(ptr));
     if (e != cudaSuccess) { cudaGetLastError(); return fail(c, MLT_E_INVAL, "cudaHostUnregister: %s", cudaGetErrorString(e)); }
     return MLT_OK;
