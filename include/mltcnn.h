@@ -148,7 +148,7 @@ MLT_API int mlt_predict_picture(mlt_ctx *ctx, const int16_t *ref_luma, int ref_s
                         int slice_qp, mlt_result *out, int capacity);
 
 /* Optional: page-lock a long-lived host buffer (VTM allocates a Picture's PelStorage once and keeps it for the whole
- * encode, Picture.cpp Picture::create) so that mlt_begin_picture / mlt_predict_picture / the batch calls DMA straight
+ * encode, Picture::create, Picture.cpp:202-213) so that mlt_begin_picture / mlt_predict_picture / the batch calls DMA straight
  * out of it instead of going through the driver's pageable staging.  Plain wrappers, so the host side needs no CUDA
  * headers; unpin before the buffer is freed.  Pinning the same range twice is not an error. */
 MLT_API int mlt_pin_host_buffer(mlt_ctx *ctx, const void *ptr, uint64_t bytes);
