@@ -437,6 +437,27 @@ def test_picture_block_matching_is_bit_exact(blob, w, h, rng_):
             p.predict_picture(None, 33)  # the reference plane belonged to the previous picture
 
 
+def test_prepass_matches_committed_golden(blob):
+    """The CUDA pre-pass against tests/golden/prepass_seed10.npz: block-matching MVs / costs for three search ranges and the
+    checksums of the gathered prediction blocks."""
+    import hashlib
+
+    from fastintercu_vvc_b200 import MltPredictor
+    from tools.gen_golden_prepass import prepass_planes
+
+    g = np.load(os.path.join(GOLD, "prepass_seed10.npz"))
+    org, ref = prepass_planes()
+    with MltPredictor(blob, device=0, max_batch=8) as p:
+        p.begin_picture(org, poc=3)
+        assert p.picture_ctu_count() == len(g["xy"])
+        for R in (0, 4, 9):
+            mv, cost = p.estimate_picture_mv(ref, R)
+            assert np.array_equal(mv, g[f"mv_r{R}"]) and np.array_equal(cost, g[f"cost_r{R}"]), R
+        p.predict_picture(None, 30, mv=g["mv_fixed"])
+        for blk, want in zip(p.debug_picture_pred(), g["pred_sha256"]):
+            assert hashlib.sha256(blk.tobytes()).hexdigest() == str(want)
+
+
 def test_cpp_hook_prepass_drives_the_library(pred, blob):
     """The C++ hook's prepassPicture / pictureSplit pair over a 416x240 picture: decisions of
     the eligible CTUs equal the per-CTU drop-in call on the same prediction, partial CTUs carry none."""

@@ -172,3 +172,47 @@ def test_picture_me_finds_planted_motion_and_prefers_zero_mv():
         assert cost == np.abs(blk - picture_pred(ref, 128, 0, *mv).astype(np.int64)).sum()
     flat = np.full((h, w), 512, np.int16)
     assert picture_me(flat, flat, 256, 0, 4) == ((0, 0), 0)
+
+
+def test_prepass_oracle_matches_committed_golden():
+    """tests/golden/prepass_seed10.npz (tools/gen_golden_prepass.py): eligible-CTU raster, block-matching MVs / costs for three
+    search ranges, checksums of the gathered prediction blocks (CTU and 16-px forms)."""
+    import hashlib
+
+    from tests.oracle_lib import picture_ctus, picture_me, picture_pred
+    from tools.gen_golden_prepass import prepass_planes
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "prepass_seed10.npz"))
+    org, ref = prepass_planes()
+    h, w = org.shape
+    xy = picture_ctus(w, h)
+    assert np.array_equal(xy, g["xy"]) and len(xy) == 6
+    for R in (0, 4, 9):
+        res = [picture_me(org, ref, x, y, R) for x, y in xy]
+        assert np.array_equal(np.array([m for m, _ in res], np.int16), g[f"mv_r{R}"])
+        assert np.array_equal(np.array([c for _, c in res], np.uint32), g[f"cost_r{R}"])
+    assert (g["mv_r9"] == (-2, 3)).all(1).sum() >= 4  # the planted (-2, 3) motion
+    for (x, y), mv, want in zip(xy, g["mv_fixed"], g["pred_sha256"]):
+        assert hashlib.sha256(picture_pred(ref, x, y, *mv).tobytes()).hexdigest() == str(want)
+    cu = b"".join(picture_pred(ref, (i % (w // 16)) * 16, (i // (w // 16)) * 16, i % 7 - 3, i % 5 - 2, size=16).tobytes() for i in range((w // 16) * (h // 16)))
+    assert hashlib.sha256(cu).hexdigest() == str(g["cu16_pred_sha256"])
+
+
+def test_picture_pred_property_random_geometry():
+    """Property check over random picture sizes, block positions and MVs (including far outside): the C restatement ==
+    numpy edge padding."""
+    from tests.oracle_lib import picture_pred
+
+    rng = np.random.RandomState(123)
+    for _ in range(40):
+        w, h = int(rng.randint(16, 300)), int(rng.randint(16, 300))
+        size = int(rng.choice([16, 32, 64, 128]))
+        if size > w or size > h:
+            size = 16
+        ref = rng.randint(-2000, 2000, (h, w + 3)).astype(np.int16)[:, 1 : 1 + w]
+        x, y = int(rng.randint(0, w - size + 1)), int(rng.randint(0, h - size + 1))
+        mvx, mvy = (int(v) for v in rng.randint(-400, 401, 2))
+        m = 420
+        padded = np.pad(ref, m, mode="edge")
+        want = padded[m + y + mvy : m + y + mvy + size, m + x + mvx : m + x + mvx + size]
+        assert np.array_equal(picture_pred(ref, x, y, mvx, mvy, size=size), want), (w, h, size, x, y, mvx, mvy)
