@@ -125,15 +125,62 @@ def synth_frames(n_ctus: int, seed: int):
 # ----------------------------------------------------------------------------------------------- CPU baseline
 
 
+REF_RUNNER = os.path.join(ROOT, "oracle", "ref_libtorch.bin")  # C++ libtorch runner of the hook's call sequence (oracle/ref_libtorch.cpp)
+
+
+def _runner_inputs(n_ctus: int):
+    """TorchScript file (traced like model2torchScript.py:37-48, seeded weights) + a CTU file for oracle/ref_libtorch.bin."""
+    import torch
+
+    from oracle import ref_arch
+
+    net = ref_arch.build_model(ref_arch.make_state_dict(10))
+    traced = torch.jit.trace(net, (torch.rand(1, 2, 128, 128), torch.rand(1), torch.rand(1)))
+    d = tempfile.mkdtemp(prefix="mlt_ref_")
+    pt, ctu_file = os.path.join(d, "MLTORPQ_splitMode_128.pt"), os.path.join(d, "ctus.bin")
+    traced.save(pt)
+    orgpred, pocqp = ref_arch.synth_ctus(n_ctus, 10)
+    with open(ctu_file, "wb") as f:
+        f.write(np.int32(n_ctus).tobytes())
+        for i in range(n_ctus):
+            f.write(pocqp[i].astype(np.int32).tobytes())
+            f.write(np.ascontiguousarray(orgpred[i, 0]).tobytes())
+            f.write(np.ascontiguousarray(orgpred[i, 1]).tobytes())
+    return d, pt, ctu_file
+
+
+def _run_runner(pt: str, ctu_file: str, budget_s: float, threads: int, mode: int):
+    """-> (ctus, seconds, threads) measured by the C++ runner itself (steady_clock around its per-CTU loop)."""
+    import subprocess
+
+    env = {k: v for k, v in os.environ.items() if k not in ("OMP_NUM_THREADS", "MKL_NUM_THREADS")}  # torchrun exports OMP_NUM_THREADS=1
+    r = subprocess.run([REF_RUNNER, pt, ctu_file, f"{budget_s:.3f}", str(threads), str(mode)], capture_output=True, text=True,
+                       timeout=budget_s * 4 + 120, env=env, check=True)
+    n, dt, thr = r.stdout.strip().splitlines()[-1].split()
+    return int(n), float(dt), int(thr)
+
+
 def cpu_reference_rate(budget_s: float, threads: int | None = None):
-    """Reference CPU path: traced TorchScript of the architecture on torch CPU fp32 (libtorch), one CTU per
-    forward like the hook (EncCu.cpp:869-921, model loaded once).  Bounded by `budget_s` seconds."""
+    """Reference CPU path, one CTU per call like the hook (EncCu.cpp:806-921), model loaded once.  Preferred: the C++ libtorch
+    runner oracle/ref_libtorch.bin (the hook's own call sequence: staging loops, from_blob / cat / permute, forward, argmax);
+    if it was not built, the same traced TorchScript module driven from Python (same libtorch kernels).
+    Returns (CTU/s, threads, CTUs, seconds, how)."""
+    import shutil
+
+    threads = threads or len(os.sched_getaffinity(0))
+    if os.path.exists(REF_RUNNER):
+        d, pt, ctu_file = _runner_inputs(16)
+        try:
+            n, dt, thr = _run_runner(pt, ctu_file, budget_s, threads, 0)
+        finally:
+            shutil.rmtree(d, ignore_errors=True)
+        return n / dt, thr, n, dt, "C++ libtorch runner of the hook's call sequence (oracle/ref_libtorch.cpp, libtorch CPU fp32)"
     import torch
 
     from oracle import ref_arch
 
     # all host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which would cripple the CPU arm)
-    torch.set_num_threads(threads or len(os.sched_getaffinity(0)))
+    torch.set_num_threads(threads)
     sd = ref_arch.make_state_dict(10)
     net = ref_arch.build_model(sd)
     ex = (torch.rand(1, 2, 128, 128), torch.rand(1), torch.rand(1))
@@ -151,7 +198,7 @@ def cpu_reference_rate(budget_s: float, threads: int | None = None):
             dt = time.perf_counter() - t0
             if (dt >= budget_s and n >= 16) or n >= 100000:
                 break
-    return n / dt, torch.get_num_threads(), n, dt
+    return n / dt, torch.get_num_threads(), n, dt, "traced TorchScript driven from Python (torch CPU fp32 = libtorch)"
 
 
 def cpu_reference_variants(budget_s: float = 3.0):
@@ -171,13 +218,23 @@ def cpu_reference_variants(budget_s: float = 3.0):
     x = torch.from_numpy(ref_arch.stage_numpy(orgpred))
     poc, qp = torch.from_numpy(pocqp[:, 0].copy()), torch.from_numpy(pocqp[:, 1].copy())
     with torch.no_grad():
-        n, t0 = 0, time.perf_counter()
-        while time.perf_counter() - t0 < budget_s or n < 3:
-            m = torch.jit.load(path)
-            m.eval()
-            m(x[n % 120 : n % 120 + 1], poc[n % 120 : n % 120 + 1], qp[n % 120 : n % 120 + 1])
-            n += 1
-        as_written = n / (time.perf_counter() - t0)
+        if os.path.exists(REF_RUNNER):  # the C++ runner in its load-per-call mode: torch::jit::load inside the per-CTU loop
+            import shutil
+
+            d, pt, ctu_file = _runner_inputs(16)
+            try:
+                rn, rdt, _ = _run_runner(pt, ctu_file, budget_s, len(os.sched_getaffinity(0)), 1)
+            finally:
+                shutil.rmtree(d, ignore_errors=True)
+            as_written = rn / rdt
+        else:
+            n, t0 = 0, time.perf_counter()
+            while time.perf_counter() - t0 < budget_s or n < 3:
+                m = torch.jit.load(path)
+                m.eval()
+                m(x[n % 120 : n % 120 + 1], poc[n % 120 : n % 120 + 1], qp[n % 120 : n % 120 + 1])
+                n += 1
+            as_written = n / (time.perf_counter() - t0)
         traced(x, poc, qp)
         k, t0 = 0, time.perf_counter()
         while time.perf_counter() - t0 < budget_s or k < 2:
@@ -194,12 +251,23 @@ def run_reference_arm(args):
         return 0
     steps, warm = max(args.steps, 1), args.warmup
     per_step_budget = min(8.0, 120.0 / (steps + warm))
-    rates, cores, n_tot = [], 0, 0
-    for i in range(warm + steps):
-        r, cores, n, dt = cpu_reference_rate(per_step_budget)
-        if i >= warm:
-            rates.append((n, dt))
-            n_tot += n
+    rates, cores, n_tot, how = [], 0, 0, ""
+    prepared = _runner_inputs(16) if os.path.exists(REF_RUNNER) else None  # TorchScript + CTU files written once
+    try:
+        for i in range(warm + steps):
+            if prepared:
+                n, dt, cores = _run_runner(prepared[1], prepared[2], per_step_budget, len(os.sched_getaffinity(0)), 0)
+                how = "the C++ libtorch runner of the hook's call sequence (oracle/ref_libtorch.cpp, libtorch CPU fp32)"
+            else:
+                _, cores, n, dt, how = cpu_reference_rate(per_step_budget)
+            if i >= warm:
+                rates.append((n, dt))
+                n_tot += n
+    finally:
+        if prepared:
+            import shutil
+
+            shutil.rmtree(prepared[0], ignore_errors=True)
     tot_n = sum(n for n, _ in rates)
     tot_t = sum(t for _, t in rates)
     v = tot_n / tot_t
@@ -209,7 +277,7 @@ def run_reference_arm(args):
         "data": "synthetic",
         "config": {"workload": "1080p frames (120 CTUs/frame), CPU path: one CTU per forward as EncCu.cpp:869-921, model loaded once"},
         "cpu_baseline": {"value": v, "unit": "CTU/s", "cores": cores, "kind": "port",
-                         "sample": f"{tot_n} CTUs at B=1 through traced TorchScript (torch CPU fp32 = libtorch) in {tot_t:.1f}s"},
+                         "sample": f"{tot_n} CTUs at B=1 through {how} in {tot_t:.1f}s"},
         "e2e": {"value": v, "unit": "CTU/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -659,10 +727,10 @@ def main():
             line["cu_models"]["note"] = (f"secondary (SURVEY.md section 8f rank 1): 64 / 32 / 16-px GapBigMltCuORPQ on all same-size CUs of "
                                          f"{args.cu_frames} 1080p frames per step, device-resident and host-buffer (e2e) CUs/s")
         if not args.no_cpu_baseline and world == 1:
-            r, cores, cn, cdt = cpu_reference_rate(args.cpu_budget)
+            r, cores, cn, cdt, how = cpu_reference_rate(args.cpu_budget)
             aw, b120 = cpu_reference_variants(3.0)
             line["cpu_baseline"] = {"value": r, "unit": "CTU/s", "cores": cores, "kind": "port",
-                                    "sample": f"{cn} CTUs at B=1 through traced TorchScript (torch CPU fp32 = libtorch) in {cdt:.1f}s",
+                                    "sample": f"{cn} CTUs at B=1 through {how} in {cdt:.1f}s",
                                     "as_written_load_per_call": aw, "b120_frame_batch": b120,
                                     "variants_note": "as_written = torch.jit.load on every call like EncCu.cpp:894-900; b120 = one 120-CTU frame per forward (CTU/s)"}
         print(json.dumps(line))

@@ -216,3 +216,36 @@ def test_picture_pred_property_random_geometry():
         padded = np.pad(ref, m, mode="edge")
         want = padded[m + y + mvy : m + y + mvy + size, m + x + mvx : m + x + mvx + size]
         assert np.array_equal(picture_pred(ref, x, y, mvx, mvy, size=size), want), (w, h, size, x, y, mvx, mvy)
+
+
+def test_cpp_libtorch_runner_matches_the_oracle(model, tmp_path):
+    """oracle/ref_libtorch.bin -- the hook's libtorch call sequence (EncCu.cpp:806-921) as a C++ program, the CPU baseline
+    timer of bench.py -- gives the C oracle's split decisions and logits on seeded CTUs, in both load modes."""
+    import subprocess
+
+    import torch
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "oracle", "ref_libtorch.bin")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(root, "oracle")])
+    sd = ref_arch.make_state_dict(10)
+    traced = torch.jit.trace(ref_arch.build_model(sd), (torch.rand(1, 2, 128, 128), torch.rand(1), torch.rand(1)))
+    pt, ctu_file = str(tmp_path / "m.pt"), str(tmp_path / "c.bin")
+    traced.save(pt)
+    ctus, pq = ref_arch.synth_ctus(8, 10)
+    with open(ctu_file, "wb") as f:
+        f.write(np.int32(8).tobytes())
+        for i in range(8):
+            f.write(pq[i].astype(np.int32).tobytes() + np.ascontiguousarray(ctus[i, 0]).tobytes() + np.ascontiguousarray(ctus[i, 1]).tobytes())
+    lg, sp = model.predict_batch(ctus, pq)
+    for mode in ("0", "1"):
+        r = subprocess.run([exe, pt, ctu_file, "0.2", "2", mode], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        rows = [l.split() for l in r.stdout.splitlines() if l.startswith("split")]
+        assert len(rows) == 8
+        for i, row in enumerate(rows):
+            assert int(row[2]) == int(sp[i])
+            assert np.abs(np.array(row[3:7], np.float64) - lg[i, 5:9]).max() < 2e-5
+        n, dt, thr = r.stdout.strip().splitlines()[-1].split()
+        assert int(n) >= 8 and float(dt) > 0 and int(thr) == 2
