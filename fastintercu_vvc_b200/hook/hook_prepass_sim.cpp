@@ -30,6 +30,7 @@ int main(int argc, char **argv)
     mlt_hook::SplitPredictor &p = mlt_hook::SplitPredictor::instance();
     if (!p.enabled()) { std::fprintf(stderr, "predictor disabled\n"); return 3; }
     if (p.pictureSplit(0, 0) != -1) return 5; // nothing before the first pre-pass
+    if (!p.pinHostBuffer(org.data(), org.size() * sizeof(int16_t)) || !p.pinHostBuffer(ref.data(), ref.size() * sizeof(int16_t))) return 3;
     if (!p.beginPicture(org.data(), stride, w, h, poc)) return 3;
     if (!p.prepassPicture(ref.data(), stride, hasMv == 1 ? mv.data() : nullptr, qp, hasMv < 0 ? -hasMv : 0)) return 3;
     for (int y = 0; y < h; y += 128)
@@ -42,5 +43,6 @@ int main(int argc, char **argv)
     // a new picture forgets the previous picture's decisions until its own pre-pass has run
     if (!p.beginPicture(org.data(), stride, w, h, poc + 1)) return 3;
     if (p.pictureSplit(0, 0) != -1) return 5;
+    if (!p.unpinHostBuffer(org.data()) || !p.unpinHostBuffer(ref.data())) return 3;
     return 0;
 }

@@ -159,6 +159,9 @@ bool SplitPredictor::beginPicture(const int16_t *orgLuma, int stride, int width,
     return m_ctx && mlt_begin_picture(m_ctx, orgLuma, stride, width, height, poc) == MLT_OK;
 }
 
+bool SplitPredictor::pinHostBuffer(const void *ptr, uint64_t bytes) { return m_ctx && mlt_pin_host_buffer(m_ctx, ptr, bytes) == MLT_OK; }
+bool SplitPredictor::unpinHostBuffer(const void *ptr) { return m_ctx && mlt_unpin_host_buffer(m_ctx, ptr) == MLT_OK; }
+
 bool SplitPredictor::prepassFromEnv()
 {
     const char *s = std::getenv("MLT_PREPASS");

@@ -44,6 +44,11 @@ public:
     bool beginPicture(const int16_t *orgLuma, int stride, int width, int height, int poc);
     int predictInPicture(int cux, int cuy, const int16_t *pred, int predStride, int qp);
 
+    // Page-lock a long-lived picture buffer once (VTM keeps a Picture's PelStorage for the whole encode, Picture.cpp:202-213) so
+    // that beginPicture / prepassPicture DMA straight out of it; unpin before the buffer is freed.  false if disabled / failed.
+    bool pinHostBuffer(const void *ptr, uint64_t bytes);
+    bool unpinHostBuffer(const void *ptr);
+
     // Frame-level pre-pass, called once per inter picture from EncSlice::encodeCtus after
     // beginPicture: every eligible CTU (gate of EncCu.cpp:755) is inferred in ONE batch from a neighbour-independent
     // prediction -- integer-MV motion compensation out of `refLuma` (border-replicated, Picture.cpp:1117); `mv` = [n][2]
