@@ -1,4 +1,6 @@
-"""Single-CTU hook latency (mlt_predict_ctu, the in-encoder call): run with / without MLT_NO_GRAPH=1 on the same box."""
+"""Single-CTU hook latency (mlt_predict_ctu, the in-encoder call) + bit-identity of the call against the batch path.
+Used in round 1 to A/B a CUDA-graph replay of the n = 1 call (switch MLT_NO_GRAPH; 159.5 vs 160.1 us, no gain -- the graph
+path was removed again, see profiles/r01/README.md); kept as the latency probe."""
 import os
 import sys
 import tempfile
