@@ -18,7 +18,7 @@ namespace {
 constexpr int CTU = MLT_CTU_SIZE;
 constexpr int BAND = 16; // rows per CTA
 
-__global__ void __launch_bounds__(256) picture_me_cost_kernel(const int16_t *__restrict__ org, const int16_t *__restrict__ ref, int pitch, int w, int h,
+__global__ void __launch_bounds__(1024) picture_me_cost_kernel(const int16_t *__restrict__ org, const int16_t *__restrict__ ref, int pitch, int w, int h,
                                                               const PicCtu *__restrict__ ctus, int R, unsigned *__restrict__ cost /*[n][D*D]*/)
 {
     extern __shared__ int16_t sm[];
@@ -85,7 +85,9 @@ cudaError_t launch_picture_me(const int16_t *org, const int16_t *ref, int pitch,
     const int D = 2 * R + 1;
     cudaError_t e = cudaMemsetAsync(cost, 0, (size_t)n * D * D * sizeof(unsigned), s);
     if (e != cudaSuccess) return e;
-    picture_me_cost_kernel<<<dim3(CTU / BAND, n), 256, picture_me_smem_bytes(R), s>>>(org, ref, pitch, w, h, ctus, R, cost);
+    // one thread per candidate when they fit one block (R = 8: 289 candidates -> 320 threads), else strided over 1024
+    const int threads = (D * D + 31) / 32 * 32 < 1024 ? (D * D + 31) / 32 * 32 : 1024;
+    picture_me_cost_kernel<<<dim3(CTU / BAND, n), threads < 128 ? 128 : threads, picture_me_smem_bytes(R), s>>>(org, ref, pitch, w, h, ctus, R, cost);
     picture_me_argmin_kernel<<<(n + 7) / 8, 256, 0, s>>>(cost, n, R, mv, best_cost);
     return cudaGetLastError();
 }
