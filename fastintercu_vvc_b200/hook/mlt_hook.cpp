@@ -1,6 +1,7 @@
 // mlt_hook.cpp -- see mlt_hook.h.  Links against libmltcnn.so only.
 #include "mlt_hook.h"
 
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -44,6 +45,10 @@ SplitPredictor &SplitPredictor::instance()
 
 SplitPredictor::SplitPredictor()
 {
+    m_tracePath = std::getenv("MLT_TRACE");
+    m_dumpPath = std::getenv("MLT_DUMP_INPUTS");
+    const char *st = std::getenv("MLT_STATS");
+    m_stats = st && std::strcmp(st, "0") != 0;
     const char *dis = std::getenv("MLT_DISABLE");
     if (dis && std::strcmp(dis, "0") != 0) { m_disabled = true; return; } // anchor run: hook off, stock RDO
     const char *weights = std::getenv("MLT_WEIGHTS");
@@ -63,6 +68,7 @@ SplitPredictor::SplitPredictor()
 
 SplitPredictor::~SplitPredictor()
 {
+    if (m_stats) std::fprintf(stderr, "mlt_hook: %llu predictor calls, %.3f ms total\n", (unsigned long long)m_calls, m_seconds * 1e3);
     if (m_ctx) mlt_destroy(m_ctx);
     for (mlt_cu_ctx *c : m_cu)
         if (c) mlt_cu_destroy(c);
@@ -149,6 +155,44 @@ int SplitPredictor::predict(const int16_t *org, int orgStride, const int16_t *pr
     return r.split_l3;
 }
 
+bool SplitPredictor::pictureStagingFromEnv()
+{
+    const char *s = std::getenv("MLT_PICTURE_STAGING");
+    return s && std::strcmp(s, "0") != 0;
+}
+
+int SplitPredictor::predictAt(int cuw, int cux, int cuy, const int16_t *org, int orgStride, const int16_t *pred, int predStride, int poc, int qp)
+{
+    const auto t0 = std::chrono::steady_clock::now();
+    int split;
+    if (cuw != MLT_CTU_SIZE)
+        split = m_cuSplit[cuw == 64 ? 0 : (cuw == 32 ? 1 : 2)].empty() ? predictCu(cuw, org, orgStride, pred, predStride, poc, qp) : pictureSplitCu(cuw, cux, cuy);
+    else if (!m_picSplit.empty() && poc == m_picPoc)
+        split = pictureSplit(cux, cuy);
+    else if (m_picStaged && poc == m_picPoc)
+        split = predictInPicture(cux, cuy, pred, predStride, qp);
+    else
+        split = predict(org, orgStride, pred, predStride, poc, qp);
+    m_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    m_calls++;
+    if (m_tracePath) {
+        if (FILE *f = std::fopen(m_tracePath, "a")) {
+            std::fprintf(f, "%d %d %d %d %d\n", poc, cux, cuy, qp, split);
+            std::fclose(f);
+        }
+    }
+    if (m_dumpPath && cuw == MLT_CTU_SIZE) {
+        if (FILE *f = std::fopen(m_dumpPath, "ab")) {
+            const int32_t hdr[2] = {poc, qp};
+            std::fwrite(hdr, 4, 2, f);
+            for (int y = 0; y < cuw; y++) std::fwrite(org + (size_t)y * orgStride, 2, (size_t)cuw, f);
+            for (int y = 0; y < cuw; y++) std::fwrite(pred + (size_t)y * predStride, 2, (size_t)cuw, f);
+            std::fclose(f);
+        }
+    }
+    return split;
+}
+
 bool SplitPredictor::beginPicture(const int16_t *orgLuma, int stride, int width, int height, int poc)
 {
     m_picSplit.clear(); // decisions of the previous picture must never leak into this one
@@ -156,7 +200,9 @@ bool SplitPredictor::beginPicture(const int16_t *orgLuma, int stride, int width,
     for (int i = 0; i < 3; i++) { m_cuSplit[i].clear(); m_cuCols[i] = m_cuRows[i] = 0; }
     m_picW = width;
     m_picH = height;
-    return m_ctx && mlt_begin_picture(m_ctx, orgLuma, stride, width, height, poc) == MLT_OK;
+    m_picPoc = poc;
+    m_picStaged = m_ctx && mlt_begin_picture(m_ctx, orgLuma, stride, width, height, poc) == MLT_OK;
+    return m_picStaged;
 }
 
 bool SplitPredictor::pinHostBuffer(const void *ptr, uint64_t bytes) { return m_ctx && mlt_pin_host_buffer(m_ctx, ptr, bytes) == MLT_OK; }

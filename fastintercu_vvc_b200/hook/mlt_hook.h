@@ -39,6 +39,14 @@ public:
     // to setNewModeList, which then leaves the mode stack untouched, EncModeCtrl.cpp:147-148).
     int predict(const int16_t *org, int orgStride, const int16_t *pred, int predStride, int poc, int qp);
 
+    // The one call the VTM patch makes per eligible CU (integration/apply_vtm_patch.py): dispatches on what was prepared for the
+    // current picture -- the pre-pass table (pictureSplit), the staged org plane (predictInPicture), or nothing (predict /
+    // predictCu for cuw < 128) -- then appends "poc x y qp split" to $MLT_TRACE, the call's inputs to $MLT_DUMP_INPUTS
+    // (records {int32 poc, int32 qp, int16 org[cuw*cuw], int16 pred[cuw*cuw]}, 128x128 calls only) and adds the call's wall
+    // time to the totals printed at exit when MLT_STATS=1.  Same return convention as predict().
+    int predictAt(int cuw, int cux, int cuy, const int16_t *org, int orgStride, const int16_t *pred, int predStride, int poc, int qp);
+    static bool pictureStagingFromEnv(); // env MLT_PICTURE_STAGING=1: EncSlice uploads the org plane once per picture
+
     // Optional per-picture staging from EncSlice::encodeCtus (EncSlice.cpp:1479-1528): upload the original luma
     // once, then only the 32 KiB prediction block per CTU.
     bool beginPicture(const int16_t *orgLuma, int stride, int width, int height, int poc);
@@ -84,6 +92,12 @@ private:
     bool m_cuTried[3] = {false, false, false};
     int m_cuCap[3] = {0, 0, 0};
     bool m_disabled = false;
+    int m_picPoc = -1;          // poc of the picture staged by beginPicture, -1: none
+    bool m_picStaged = false;
+    const char *m_tracePath = nullptr, *m_dumpPath = nullptr;
+    bool m_stats = false;
+    uint64_t m_calls = 0;
+    double m_seconds = 0;
     std::vector<int> m_picSplit; // pre-pass decisions of the current picture, eligible CTUs in raster order
     int m_picCols = 0, m_picRows = 0, m_picW = 0, m_picH = 0;
     std::vector<int> m_cuSplit[3]; // per size: pre-pass decisions of the current picture, raster order

@@ -1,0 +1,3 @@
+// ORACLE BUILD SHIM: see core.hpp
+#pragma once
+#include "core.hpp"
