@@ -75,6 +75,11 @@ struct mlt_ctx {
     } set[2];
     cudaStream_t stream2 = nullptr;            // second compute stream (slice 1)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // mlt_predict_batch_device runs asynchronously on the CALLER's stream but uses the context's activation sets, d_ctus and
+    // stream2: ev_dev marks the end of the last device call so that the next call -- on any stream, through any entry point --
+    // is ordered after it instead of racing on those buffers
+    cudaEvent_t ev_dev = nullptr;
+    bool dev_issued = false, dev_pending_host = false;
     float *act_f[NACT] = {};
     float *scratch_f = nullptr; // shortcut-conv output of the fp32 engine
     // Host-batch slot: the device / pinned buffers one host batch lives in.  Slot 0 = the buffers below (every synchronous
@@ -140,8 +145,9 @@ int load_blob(mlt_ctx *c, const char *path)
     if (!f) return fail(c, MLT_E_IO, "cannot open weight blob '%s'", path);
     fseek(f, 0, SEEK_END);
     const long sz = ftell(f);
+    if (sz < 0) { fclose(f); return fail(c, MLT_E_IO, "cannot determine the size of '%s'", path); }
     fseek(f, 0, SEEK_SET);
-    std::vector<uint8_t> raw((size_t)(sz > 0 ? sz : 0));
+    std::vector<uint8_t> raw((size_t)sz);
     const size_t got = raw.empty() ? 0 : fread(raw.data(), 1, raw.size(), f);
     fclose(f);
     if (got != raw.size() || raw.size() < 32) return fail(c, MLT_E_IO, "short read on '%s'", path);
@@ -159,7 +165,7 @@ int load_blob(mlt_ctx *c, const char *path)
         uint64_t off, nb;
         const uint8_t *e = raw.data() + 32 + (size_t)i * 24;
         memcpy(&id, e, 4); memcpy(&dt, e + 4, 4); memcpy(&off, e + 8, 8); memcpy(&nb, e + 16, 8);
-        if (id >= 0x1000 || off + nb > raw.size() || (off & 255)) return fail(c, MLT_E_FORMAT, "bad section table in '%s'", path);
+        if (id >= 0x1000 || off > raw.size() || nb > raw.size() - off || (off & 255) || c->sec[id].dev != nullptr) return fail(c, MLT_E_FORMAT, "bad section table in '%s'", path);
         c->sec[id].dev = c->d_blob + off;
         c->sec[id].bytes = nb;
     }
@@ -458,12 +464,17 @@ int run_host_batch_chunked(mlt_ctx *c, int n, const int16_t *src, const mlt_ctu_
     return MLT_OK;
 }
 
-int check_ctx(mlt_ctx *c)
+int check_ctx(mlt_ctx *c, bool device_entry = false)
 {
     if (!c) return MLT_E_INVAL;
     c->err.clear();
     cudaError_t e = cudaSetDevice(c->device);
     if (e != cudaSuccess) return fail(c, MLT_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    if (!device_entry && c->dev_pending_host) {
+        // a device-resident call may still be running on the caller's stream: every stream of the context waits for it
+        for (cudaStream_t st : {c->stream, c->stream2, c->copy_stream}) CU(cudaStreamWaitEvent(st, c->ev_dev, 0));
+        c->dev_pending_host = false;
+    }
     return MLT_OK;
 }
 
@@ -501,6 +512,7 @@ void mlt_destroy(mlt_ctx *c)
     for (auto &S : c->set) { for (int a = 0; a < NACT; a++) cudaFree(S.act_h[a]); cudaFree(S.act0q); for (float *g : S.gap_part) cudaFree(g); }
     for (int a = 0; a < NACT; a++) cudaFree(c->act_f[a]);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_dev) cudaEventDestroy(c->ev_dev);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
     if (c->slot[1].d_in) { cudaFree(c->slot[1].d_in); cudaFree(c->slot[1].d_ctus); cudaFree(c->slot[1].d_out); cudaFreeHost(c->slot[1].h_ctus); cudaFreeHost(c->slot[1].h_out); }
@@ -544,6 +556,7 @@ int mlt_create_ex(mlt_ctx **out, const char *weights_path, int cuda_device, int 
         CU(stem_umma_init());
         CU(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->ev_dev, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
         const ActLayout l0q{64, 32, 0, 0};
         for (int si = 0; si < 2; si++) {
@@ -715,13 +728,20 @@ int mlt_collect(mlt_ctx *c, mlt_result *out, int *n_out)
 int mlt_predict_batch_device(mlt_ctx *c, int n, const int16_t *d_orgpred, const int32_t *d_pocqp, mlt_result *d_out,
                              void *cuda_stream)
 {
-    int rc = check_ctx(c);
+    int rc = check_ctx(c, true);
     if (rc) return rc;
     if (n < 0 || (n > 0 && (!d_orgpred || !d_pocqp || !d_out))) return fail(c, MLT_E_INVAL, "null argument");
     if (n > c->max_batch) return fail(c, MLT_E_BATCH, "n=%d > max_batch=%d", n, c->max_batch);
     if (((uintptr_t)d_orgpred & 15) != 0) return fail(c, MLT_E_INVAL, "d_orgpred must be 16-byte aligned");
+    if (c->submitted != c->collected) return fail(c, MLT_E_STATE, "submitted batches must be collected first");
     if (n == 0) return MLT_OK;
     cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+    // order this call after the previous device call (possibly on another stream): both use the context's buffers
+    if (c->dev_issued) CU(cudaStreamWaitEvent(s, c->ev_dev, 0));
+    struct Mark { // ... and leave the marker for whoever comes next, on every exit path
+        mlt_ctx *c; cudaStream_t s;
+        ~Mark() { if (cudaEventRecord(c->ev_dev, s) == cudaSuccess) c->dev_issued = c->dev_pending_host = true; }
+    } mark{c, s};
     // descriptors are built on the device: nothing crosses PCIe on this path
     dense_descs_kernel<<<(n + 255) / 256, 256, 0, s>>>(c->d_ctus, d_orgpred, d_pocqp, n);
     CU(cudaGetLastError());

@@ -56,6 +56,9 @@ struct mlt_cu_ctx {
         bool busy = false;
     } slot[2];
     uint64_t submitted = 0, collected = 0;
+    // end of the last mlt_cu_predict_batch_device (runs on the CALLER's stream, uses the context's buffers): see api.cu
+    cudaEvent_t ev_dev = nullptr;
+    bool dev_issued = false, dev_pending_host = false;
     int16_t *d_pic = nullptr, *d_mv = nullptr; // mlt_cu_predict_picture: org + reference luma planes (same pitch), per-CU MVs
     size_t pic_capacity = 0;
     float *d_dbg = nullptr;
@@ -95,8 +98,9 @@ int load_blob(mlt_cu_ctx *c, const char *path)
     if (!f) return fail(c, MLT_E_IO, "cannot open weight blob '%s'", path);
     fseek(f, 0, SEEK_END);
     const long sz = ftell(f);
+    if (sz < 0) { fclose(f); return fail(c, MLT_E_IO, "cannot determine the size of '%s'", path); }
     fseek(f, 0, SEEK_SET);
-    std::vector<uint8_t> raw((size_t)(sz > 0 ? sz : 0));
+    std::vector<uint8_t> raw((size_t)sz);
     const size_t got = raw.empty() ? 0 : fread(raw.data(), 1, raw.size(), f);
     fclose(f);
     if (got != raw.size() || raw.size() < 32) return fail(c, MLT_E_IO, "short read on '%s'", path);
@@ -114,7 +118,7 @@ int load_blob(mlt_cu_ctx *c, const char *path)
         uint64_t off, nb;
         const uint8_t *e = raw.data() + 32 + (size_t)i * 24;
         memcpy(&id, e, 4); memcpy(&dt, e + 4, 4); memcpy(&off, e + 8, 8); memcpy(&nb, e + 16, 8);
-        if (id >= 0x1000 || off + nb > raw.size() || (off & 255)) return fail(c, MLT_E_FORMAT, "bad section table in '%s'", path);
+        if (id >= 0x1000 || off > raw.size() || nb > raw.size() - off || (off & 255) || c->sec[id].dev != nullptr) return fail(c, MLT_E_FORMAT, "bad section table in '%s'", path);
         c->sec[id].dev = c->d_blob + off;
         c->sec[id].bytes = nb;
     }
@@ -190,12 +194,16 @@ int run_network(mlt_cu_ctx *c, int n, const int16_t *d_orgpred, const int32_t *d
     return MLT_OK;
 }
 
-int check_ctx(mlt_cu_ctx *c)
+int check_ctx(mlt_cu_ctx *c, bool device_entry = false)
 {
     if (!c) return MLT_E_INVAL;
     c->err.clear();
     cudaError_t e = cudaSetDevice(c->device);
     if (e != cudaSuccess) return fail(c, MLT_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    if (!device_entry && c->dev_pending_host) { // a device-resident call may still be running on the caller's stream
+        for (cudaStream_t st : {c->stream, c->copy_stream}) CU(cudaStreamWaitEvent(st, c->ev_dev, 0));
+        c->dev_pending_host = false;
+    }
     return MLT_OK;
 }
 
@@ -290,6 +298,7 @@ void mlt_cu_destroy(mlt_cu_ctx *c)
     cudaFree(c->d_pic); cudaFree(c->d_mv);
     cudaFreeHost(c->h_in); cudaFreeHost(c->h_pq); cudaFreeHost(c->h_out);
     for (cudaEvent_t e : c->ev_in) if (e) cudaEventDestroy(e);
+    if (c->ev_dev) cudaEventDestroy(c->ev_dev);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -317,6 +326,7 @@ int mlt_cu_create(mlt_cu_ctx **out, const char *weights_path, int cuda_device, i
         CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
         for (cudaEvent_t &e : c->ev_in) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->ev_dev, cudaEventDisableTiming));
         for (int li = 0; li < CU_NCONV; li++) CU(cu_conv_info(cu_size, li, &c->info[li]));
         int r = load_blob(c, weights_path);
         if (r) return r;
@@ -508,13 +518,18 @@ int mlt_cu_predict_picture(mlt_cu_ctx *c, const int16_t *org_luma, int org_strid
 int mlt_cu_predict_batch_device(mlt_cu_ctx *c, int n, const int16_t *d_orgpred, const int32_t *d_pocqp, mlt_cu_result *d_out,
                                 void *cuda_stream)
 {
-    int rc = check_ctx(c);
+    int rc = check_ctx(c, true);
     if (rc) return rc;
     if (n < 0 || (n > 0 && (!d_orgpred || !d_pocqp || !d_out))) return fail(c, MLT_E_INVAL, "null argument");
     if (n > c->cap) return fail(c, MLT_E_BATCH, "n=%d > max_batch=%d", n, c->cap);
     if (((uintptr_t)d_orgpred & 15) != 0) return fail(c, MLT_E_INVAL, "d_orgpred must be 16-byte aligned");
+    if (c->submitted != c->collected) return fail(c, MLT_E_STATE, "submitted batches must be collected first");
     if (n == 0) return MLT_OK;
-    return run_network(c, n, d_orgpred, d_pocqp, d_out, static_cast<cudaStream_t>(cuda_stream));
+    cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+    if (c->dev_issued) CU(cudaStreamWaitEvent(s, c->ev_dev, 0)); // after the previous device call, whatever its stream
+    rc = run_network(c, n, d_orgpred, d_pocqp, d_out, s);
+    if (cudaEventRecord(c->ev_dev, s) == cudaSuccess) c->dev_issued = c->dev_pending_host = true;
+    return rc;
 }
 
 int64_t mlt_cu_debug_activation(mlt_cu_ctx *c, int layer, float *out, int64_t capacity)

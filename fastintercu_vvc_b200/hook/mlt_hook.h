@@ -88,6 +88,7 @@ public:
 private:
     SplitPredictor();
     mlt_ctx *m_ctx = nullptr;
+    int m_ctxCap = 512; // batch capacity of m_ctx (eligible CTUs of the largest picture seen so far)
     mlt_cu_ctx *m_cu[3] = {nullptr, nullptr, nullptr}; // 64, 32, 16
     bool m_cuTried[3] = {false, false, false};
     int m_cuCap[3] = {0, 0, 0};

@@ -112,7 +112,11 @@ MLT_API int mlt_submit_batch_dense(mlt_ctx *ctx, int n, const int16_t *orgpred, 
 MLT_API int mlt_collect(mlt_ctx *ctx, mlt_result *out, int *n_out);
 
 /* Device-resident batch on the caller's stream (cudaStream_t passed as void*; NULL = default stream).
- * d_orgpred / d_pocqp / d_out are device pointers; asynchronous w.r.t. the host. */
+ * d_orgpred / d_pocqp / d_out are device pointers; asynchronous w.r.t. the host.  The call uses the context's own
+ * activation buffers: the library orders it after the previous device call (whatever its stream) and orders every later
+ * call of any entry point after it, so back-to-back calls need no synchronisation by the caller; the caller only has to
+ * keep d_orgpred / d_pocqp / d_out alive and untouched until its stream reaches the end of the call.  Refused with
+ * MLT_E_STATE while submitted batches are uncollected. */
 MLT_API int mlt_predict_batch_device(mlt_ctx *ctx, int n, const int16_t *d_orgpred, const int32_t *d_pocqp,
                              mlt_result *d_out, void *cuda_stream);
 

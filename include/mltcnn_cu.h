@@ -66,7 +66,9 @@ MLT_API int mlt_cu_collect(mlt_cu_ctx *ctx, mlt_cu_result *out, int *n_out);
 MLT_API int mlt_cu_picture_cu_count(int cu_size, int width, int height);
 MLT_API int mlt_cu_predict_picture(mlt_cu_ctx *ctx, const int16_t *org_luma, int org_stride, const int16_t *ref_luma, int ref_stride,
                                    int width, int height, int poc, const int16_t *mv, int qp, mlt_cu_result *out, int capacity);
-/* Device-resident batch on the caller's stream (cudaStream_t as void*); asynchronous w.r.t. the host. */
+/* Device-resident batch on the caller's stream (cudaStream_t as void*); asynchronous w.r.t. the host.  Ordered by the
+ * library after the previous device call and before every later call of any entry point (see mlt_predict_batch_device);
+ * MLT_E_STATE while submitted batches are uncollected. */
 MLT_API int mlt_cu_predict_batch_device(mlt_cu_ctx *ctx, int n, const int16_t *d_orgpred, const int32_t *d_pocqp,
                                         mlt_cu_result *d_out, void *cuda_stream);
 

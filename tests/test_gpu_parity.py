@@ -9,6 +9,7 @@ Bars (BASELINE.json north_star): integer staging bit-exact; probabilities max |d
 """
 import os
 import subprocess
+import sys
 import tempfile
 
 import numpy as np
@@ -544,6 +545,44 @@ def test_sliced_device_batch_matches_small_batches(blob, ctus):
     assert dev.tobytes() == host.tobytes()
 
 
+def test_device_calls_on_different_streams_and_host_calls_do_not_race(blob, ctus):
+    """mlt_predict_batch_device is asynchronous on the caller's stream but uses the context's activation buffers: two device calls
+    on DIFFERENT streams and a host-path call issued right behind them, with no synchronisation by the caller, must all give the
+    small-batch results (the library orders them with an event); uncollected submitted batches refuse the device entry."""
+    import torch
+
+    from fastintercu_vvc_b200 import MltPredictor
+    from fastintercu_vvc_b200.capi import RESULT_DTYPE, MltError
+
+    orgpred, pocqp = ctus
+    n = 601
+    rs = np.random.RandomState(11)
+    ia, ib = rs.randint(0, len(orgpred), n), rs.randint(0, len(orgpred), n)
+    with MltPredictor(blob, device=0, max_batch=640) as p:
+        base = p.predict_batch_dense(orgpred, pocqp)
+        sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+        bufs = []
+        for idx in (ia, ib):
+            bufs.append((torch.from_numpy(np.ascontiguousarray(orgpred[idx])).cuda(), torch.from_numpy(np.ascontiguousarray(pocqp[idx])).cuda(),
+                         torch.zeros(n * RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")))
+        torch.cuda.synchronize()
+        for rep in range(3):
+            for (d_in, d_pq, d_out), st in zip(bufs, (sa, sb)):
+                p.predict_batch_device(n, d_in.data_ptr(), d_pq.data_ptr(), d_out.data_ptr(), st.cuda_stream)
+            host = p.predict_batch_dense(orgpred, pocqp)  # host path right behind the two device calls, no sync in between
+            one = p.predict_ctu(orgpred[3, 0], orgpred[3, 1], int(pocqp[3, 0]), int(pocqp[3, 1]))
+            torch.cuda.synchronize()
+            assert host.tobytes() == base.tobytes() and one.tobytes() == base[3].tobytes()
+            for (_, _, d_out), idx in zip(bufs, (ia, ib)):
+                dev = np.frombuffer(d_out.cpu().numpy().tobytes(), RESULT_DTYPE)
+                assert np.array_equal(dev["logits"].view(np.uint32), base["logits"][idx].view(np.uint32)), rep
+        p.submit_batch_dense(orgpred, pocqp)
+        d_in, d_pq, d_out = bufs[0]
+        with pytest.raises(MltError):
+            p.predict_batch_device(n, d_in.data_ptr(), d_pq.data_ptr(), d_out.data_ptr(), sa.cuda_stream)
+        assert p.collect().tobytes() == base.tobytes()
+
+
 def test_fp32_engine_large_host_batch_is_chunk_safe(blob, oracle):
     """The fp32 cross-check engine has one set of fp32 buffers: a host batch large enough to be chunked (>= 1024 CTUs) must
     not spread its chunks over the two compute streams (found by tools/precision_large.py: garbage at n = 2048)."""
@@ -645,3 +684,32 @@ def test_pipelined_submit_collect_matches_the_synchronous_call():
             assert g.tobytes() == w.tobytes()
         assert p.predict_batch_dense(*batches[1]).tobytes() == want[1].tobytes()  # synchronous path usable again
     os.unlink(path)
+
+
+# ------------------------------------------------------------------------------------------- inside the encoder
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "EncoderApp_mlt")), reason="oracle/_ref encoders not built")
+def test_patched_vtm_encoder_matches_the_reference_hook_encoder(tmp_path):
+    """The hot path where the reference runs it: VTM-11.0's EncCu::xCompressCU.  A short RA encode (1 I + 2 B pictures of 416x240,
+    6 predictor calls) with (i) the reference's own hook translation unit on libtorch CPU and (ii) the patched encoder calling
+    libmltcnn.so through hook/mlt_hook.cpp must take the same split decisions, write the same bitstream and reconstruction, and the
+    bitstream must decode to that reconstruction (oracle/vtm/Makefile builds both from /root/reference; tools/vtm_run.py)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import vtm_run
+
+    work = str(tmp_path)
+    model_dir, blob = vtm_run.make_weights(work)
+    clip = {"name": "t416", "w": 416, "h": 240, "bits": 8, "frames": 3, "path": os.path.join(work, "t.yuv")}
+    vtm_run.synth_clip(clip["path"], 416, 240, 3, 8)
+    res = [vtm_run.run_encode(e, clip, 32, work, model_dir, blob, 0, "2.1") for e in ("ref_cpu", "mlt", "staged")]
+    for r in res:
+        assert r["rc"] == 0 and r["decode_matches_recon"], r
+        assert r["error_lines"] == 0 and r["hello_lines"] == 0, r
+    ref, mlt, staged = res
+    assert len(ref["trace"]) == 6 and all(t[4] in (0, 1, 2, 3) for t in ref["trace"])
+    assert mlt["trace"] == ref["trace"] and staged["trace"] == ref["trace"]
+    assert mlt["bitstream_md5"] == ref["bitstream_md5"] == staged["bitstream_md5"]
+    assert mlt["recon_md5"] == ref["recon_md5"]
+    assert mlt["hook_calls"] == 6
