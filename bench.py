@@ -126,6 +126,17 @@ def synth_frames(n_ctus: int, seed: int):
 
 
 REF_RUNNER = os.path.join(ROOT, "oracle", "ref_libtorch.bin")  # C++ libtorch runner of the hook's call sequence (oracle/ref_libtorch.cpp)
+# The reference's OWN statements for the path (EncCu.cpp:803-926 compiled verbatim into a timing harness, oracle/vtm/ref_hook_tu.cpp;
+# built by oracle/vtm/Makefile where /root/reference exists and shipped to the GPU box under oracle/_ref/): preferred over the port
+REF_TU = os.path.join(ROOT, "oracle", "_ref", "ref_hook_tu_cpu")
+REF_TU_CUDA = os.path.join(ROOT, "oracle", "_ref", "ref_hook_tu_cuda")
+HOW_TU = ("the reference's own hook statements EncCu.cpp:803-926 compiled verbatim (oracle/_ref/ref_hook_tu_cpu; edits: at::kCPU, model "
+          "directory, module kept across calls), libtorch CPU fp32")
+HOW_PORT = "C++ libtorch runner of the hook's call sequence (oracle/ref_libtorch.cpp, libtorch CPU fp32)"
+
+
+def ref_kind() -> str:
+    return "reference" if os.path.exists(REF_TU) else "port"
 
 
 def _runner_inputs(n_ctus: int):
@@ -149,13 +160,19 @@ def _runner_inputs(n_ctus: int):
     return d, pt, ctu_file
 
 
-def _run_runner(pt: str, ctu_file: str, budget_s: float, threads: int, mode: int):
+def _run_runner(pt: str, ctu_file: str, budget_s: float, threads: int, mode: int, exe: str | None = None):
     """-> (ctus, seconds, threads) measured by the C++ runner itself (steady_clock around its per-CTU loop)."""
     import subprocess
 
-    env = {k: v for k, v in os.environ.items() if k not in ("OMP_NUM_THREADS", "MKL_NUM_THREADS")}  # torchrun exports OMP_NUM_THREADS=1
-    r = subprocess.run([REF_RUNNER, pt, ctu_file, f"{budget_s:.3f}", str(threads), str(mode)], capture_output=True, text=True,
-                       timeout=budget_s * 4 + 120, env=env, check=True)
+    env = {k: v for k, v in os.environ.items() if k not in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "MLT_REF_LOAD_PER_CALL")}  # torchrun exports OMP_NUM_THREADS=1
+    if os.path.exists(exe or REF_TU):  # mode 1 = torch::jit::load on every call, the hook as written (EncCu.cpp:894-900)
+        env["MLT_REF_MODEL_DIR"] = os.path.dirname(pt)
+        if mode == 1:
+            env["MLT_REF_LOAD_PER_CALL"] = "1"
+        cmd = [exe or REF_TU, ctu_file, f"{budget_s:.3f}", str(threads)]
+    else:
+        cmd = [REF_RUNNER, pt, ctu_file, f"{budget_s:.3f}", str(threads), str(mode)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=budget_s * 4 + 180, env=env, check=True)
     n, dt, thr = r.stdout.strip().splitlines()[-1].split()
     return int(n), float(dt), int(thr)
 
@@ -168,13 +185,13 @@ def cpu_reference_rate(budget_s: float, threads: int | None = None):
     import shutil
 
     threads = threads or len(os.sched_getaffinity(0))
-    if os.path.exists(REF_RUNNER):
+    if os.path.exists(REF_TU) or os.path.exists(REF_RUNNER):
         d, pt, ctu_file = _runner_inputs(16)
         try:
             n, dt, thr = _run_runner(pt, ctu_file, budget_s, threads, 0)
         finally:
             shutil.rmtree(d, ignore_errors=True)
-        return n / dt, thr, n, dt, "C++ libtorch runner of the hook's call sequence (oracle/ref_libtorch.cpp, libtorch CPU fp32)"
+        return n / dt, thr, n, dt, HOW_TU if os.path.exists(REF_TU) else HOW_PORT
     import torch
 
     from oracle import ref_arch
@@ -218,7 +235,7 @@ def cpu_reference_variants(budget_s: float = 3.0):
     x = torch.from_numpy(ref_arch.stage_numpy(orgpred))
     poc, qp = torch.from_numpy(pocqp[:, 0].copy()), torch.from_numpy(pocqp[:, 1].copy())
     with torch.no_grad():
-        if os.path.exists(REF_RUNNER):  # the C++ runner in its load-per-call mode: torch::jit::load inside the per-CTU loop
+        if os.path.exists(REF_TU) or os.path.exists(REF_RUNNER):  # load-per-call mode: torch::jit::load inside the per-CTU loop
             import shutil
 
             d, pt, ctu_file = _runner_inputs(16)
@@ -252,12 +269,12 @@ def run_reference_arm(args):
     steps, warm = max(args.steps, 1), args.warmup
     per_step_budget = min(8.0, 120.0 / (steps + warm))
     rates, cores, n_tot, how = [], 0, 0, ""
-    prepared = _runner_inputs(16) if os.path.exists(REF_RUNNER) else None  # TorchScript + CTU files written once
+    prepared = _runner_inputs(16) if (os.path.exists(REF_TU) or os.path.exists(REF_RUNNER)) else None  # TorchScript + CTU files written once
     try:
         for i in range(warm + steps):
             if prepared:
                 n, dt, cores = _run_runner(prepared[1], prepared[2], per_step_budget, len(os.sched_getaffinity(0)), 0)
-                how = "the C++ libtorch runner of the hook's call sequence (oracle/ref_libtorch.cpp, libtorch CPU fp32)"
+                how = HOW_TU if os.path.exists(REF_TU) else HOW_PORT
             else:
                 _, cores, n, dt, how = cpu_reference_rate(per_step_budget)
             if i >= warm:
@@ -276,7 +293,7 @@ def run_reference_arm(args):
         "ms_per_step": 1e3 * tot_t / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": "1080p frames (120 CTUs/frame), CPU path: one CTU per forward as EncCu.cpp:869-921, model loaded once"},
-        "cpu_baseline": {"value": v, "unit": "CTU/s", "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": v, "unit": "CTU/s", "cores": cores, "kind": ref_kind(),
                          "sample": f"{tot_n} CTUs at B=1 through {how} in {tot_t:.1f}s"},
         "e2e": {"value": v, "unit": "CTU/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -463,6 +480,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU baseline work (rank 0, N=1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sustain-s", type=float, default=2.5, help="seconds of the sustained device-resident run (clocks sampled inside it)")
     ap.add_argument("--cu-frames", type=int, default=8, help="1080p frames whose 64 / 32 / 16-px CUs form one step of the CU-model lines (0 = skip)")
     ap.add_argument("--cu-only", action="store_true", help="only the smaller-CU models (tuning runs)")
     ap.add_argument("--cu-sizes", default="64,32,16", help="CU sizes of the CU-model lines (profiling runs pick one)")
@@ -551,6 +569,30 @@ def main():
     clocks = sampler.stop()
     clocks["note"] = clocks_note
 
+    # ---- sustained measurement: the identical device-resident loop for >= 2 s with nvidia-smi sampled INSIDE the window
+    # (the K-step region above lasts only K x ~5.5 ms; the part is power-capped, so the long run is the honest clock)
+    sus_sampler = ClockSampler(local)
+    sus_sampler.start()
+    for _ in range(3):
+        device_step()
+    barrier()
+    sus_sampler.mark_begin()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    step_ms = torch.tensor([dev_ms / steps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(step_ms, op=dist.ReduceOp.MAX)
+    sus_steps = max(steps, int(np.ceil(args.sustain_s * 1e3 / float(step_ms))))  # the same count on every rank
+    s0.record(stream)
+    for i in range(sus_steps):
+        device_step()
+        if i % 64 == 63:
+            torch.cuda.current_stream().synchronize()  # keep the launch queue bounded
+    s1.record(stream)
+    barrier()
+    sus_sampler.mark_end()
+    sus_ms = s0.elapsed_time(s1)
+    sus_clocks = sus_sampler.stop()
+
     # ---- per-kernel device times (roofline), measured live with CUDA events around each launch
     pred.set_profiling(True)
     prof = np.zeros(18, np.float64)
@@ -594,12 +636,13 @@ def main():
     d_probe = torch.empty_like(d_in)
     h_probe = h_in
     d_probe.copy_(h_probe, non_blocking=True)
-    torch.cuda.synchronize()
+    barrier()  # every rank copies at the same time: the probe sees the host's aggregate H2D contention
     t0 = time.perf_counter()
-    for _ in range(3):
+    for _ in range(6):
         d_probe.copy_(h_probe, non_blocking=True)
     torch.cuda.synchronize()
-    h2d_gbps = 3 * orgpred_pinned.nbytes / (time.perf_counter() - t0) / 1e9
+    h2d_gbps = 6 * orgpred_pinned.nbytes / (time.perf_counter() - t0) / 1e9
+    barrier()
     del d_probe
 
     # ---- single-frame latency (the 120 CTUs of one 1080p frame), host buffers, for the record
@@ -671,9 +714,9 @@ def main():
     ctu_us = (time.perf_counter() - t0) / 200 * 1e6
 
     if world > 1:
-        t = torch.tensor([dev_ms, e2e_s, e2e_sync_s], dtype=torch.float64, device="cuda")
+        t = torch.tensor([dev_ms, e2e_s, e2e_sync_s, sus_ms, -h2d_gbps], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_s, e2e_sync_s = float(t[0]), float(t[1]), float(t[2])
+        dev_ms, e2e_s, e2e_sync_s, sus_ms, h2d_gbps = float(t[0]), float(t[1]), float(t[2]), float(t[3]), -float(t[4])  # slowest rank's link
     total_ctus = n * world * steps
     value = total_ctus / (dev_ms * 1e-3)
     e2e = total_ctus / e2e_s
@@ -692,17 +735,21 @@ def main():
                        "frames_per_step": args.frames, "ctus_per_step_per_gpu": n,
                        "l2": f"inputs {n * 65536 / 2**20:.0f} MiB + activations > 126 MB L2, no flush needed",
                        "parallelism": f"replicas x{world} (frames sharded, no collectives)", "host_binding": numa},
-            # both host-buffer entry points are timed; `value` is the faster one on this box (the pipelined pair wins on 1-2
-            # GPUs; from 4 ranks on the host's aggregate H2D rate is the bound and the blocking call's burstier copies do better)
-            "e2e": {"value": max(e2e, e2e_sync), "unit": "CTU/s", "h2d_bytes_per_step": int(n * (65536 + 8)), "d2h_bytes_per_step": int(n * RESULT_DTYPE.itemsize),
-                    "api": ("mlt_submit_batch_dense + mlt_collect (pinned host int16 in, mlt_result out, two batches in flight)" if e2e >= e2e_sync
-                            else "mlt_predict_batch_dense (pinned host int16 in, mlt_result out, one blocking call per step)"),
-                    "pipelined_value": e2e, "pipelined_api": "mlt_submit_batch_dense + mlt_collect (two batches in flight)",
+            # ONE public API is the e2e value at every N: the pipelined pair; the blocking call is reported next to it
+            "e2e": {"value": e2e, "unit": "CTU/s", "h2d_bytes_per_step": int(n * (65536 + 8)), "d2h_bytes_per_step": int(n * RESULT_DTYPE.itemsize),
+                    "api": "mlt_submit_batch_dense + mlt_collect (pinned host int16 in, mlt_result out, two batches in flight)",
                     "sync_call_value": e2e_sync, "sync_call_api": "mlt_predict_batch_dense (one blocking call per step)",
                     "h2d_link_gbps": h2d_gbps, "h2d_bound_ctus_per_s": h2d_gbps * 1e9 / (65536 + 8) * world},
             "gpu_launches": int(launches),
             "clocks": clocks,
+            "sustained": {"seconds": sus_ms * 1e-3, "steps": sus_steps, "value": n * world * sus_steps / (sus_ms * 1e-3), "unit": "CTU/s",
+                          "ms_per_step": sus_ms / sus_steps, "clocks": sus_clocks,
+                          "tflops_whole_net": n * sus_steps / (sus_ms * 1e-3) * FLOP_PER_CTU / 1e12,
+                          "frac_of_sustained_peak": n * sus_steps / (sus_ms * 1e-3) * FLOP_PER_CTU / 1e12 / sustained,
+                          "frac_of_burst_peak": n * sus_steps / (sus_ms * 1e-3) * FLOP_PER_CTU / 1e12 / burst,
+                          "note": "the same device-resident step repeated back to back for >= --sustain-s seconds; nvidia-smi sampled inside the window"},
             "roofline": {"bound": "tensor", "achieved": ach, "peak": sustained, "unit": "TFLOP/s", "frac": ach / sustained,
+                         "peak_burst": burst, "frac_vs_burst": ach / burst,
                          "traffic": NCU_DRAM_BYTES_PER_CTU * n, "traffic_note": "ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the launches of one 3840-CTU step (profiles/r01/ncu_full_v17_summary.csv), scaled to this step; algorithmic minimum is 65,536 B/CTU -- the rest is inter-layer fp16 activations",
                          "kernel": "stem_umma_kernel + conv_umma_kernel x15 (every tcgen05 launch of a step: all 21 convs)",
                          "peak_source": f"{how} bf16 sustained", "kernel_ms_per_step": umma_ms, "stem_ms": float(prof[0]),
@@ -726,10 +773,26 @@ def main():
                                                 0.0 if args.no_cpu_baseline else min(3.0, args.cpu_budget / 4))
             line["cu_models"]["note"] = (f"secondary (SURVEY.md section 8f rank 1): 64 / 32 / 16-px GapBigMltCuORPQ on all same-size CUs of "
                                          f"{args.cu_frames} 1080p frames per step, device-resident and host-buffer (e2e) CUs/s")
+        if not args.no_cpu_baseline and world == 1 and os.path.exists(REF_TU_CUDA):
+            # the reference AS SHIPPED runs its hook on libtorch-CUDA (at::kCUDA, EncCu.cpp:804): the same statements on this GPU
+            import shutil
+
+            d, pt, ctu_file = _runner_inputs(16)
+            try:
+                gn, gdt, _ = _run_runner(pt, ctu_file, 3.0, len(os.sched_getaffinity(0)), 0, exe=REF_TU_CUDA)
+                wn, wdt, _ = _run_runner(pt, ctu_file, 3.0, len(os.sched_getaffinity(0)), 1, exe=REF_TU_CUDA)
+                line["reference_as_shipped_cuda"] = {
+                    "load_once_ctus_per_s": gn / gdt, "as_written_load_per_call_ctus_per_s": wn / wdt, "unit": "CTU/s",
+                    "note": "oracle/_ref/ref_hook_tu_cuda: the reference's own hook statements (EncCu.cpp:803-926, at::kCUDA as shipped) through "
+                            "libtorch 2.11 CUDA on this B200, B = 1 like the hook; as_written reloads the TorchScript file on every call (:894-900)"}
+            except Exception as e:  # noqa: BLE001 -- diagnostic only
+                line["reference_as_shipped_cuda"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+            finally:
+                shutil.rmtree(d, ignore_errors=True)
         if not args.no_cpu_baseline and world == 1:
             r, cores, cn, cdt, how = cpu_reference_rate(args.cpu_budget)
             aw, b120 = cpu_reference_variants(3.0)
-            line["cpu_baseline"] = {"value": r, "unit": "CTU/s", "cores": cores, "kind": "port",
+            line["cpu_baseline"] = {"value": r, "unit": "CTU/s", "cores": cores, "kind": ref_kind(),
                                     "sample": f"{cn} CTUs at B=1 through {how} in {cdt:.1f}s",
                                     "as_written_load_per_call": aw, "b120_frame_batch": b120,
                                     "variants_note": "as_written = torch.jit.load on every call like EncCu.cpp:894-900; b120 = one 120-CTU frame per forward (CTU/s)"}

@@ -61,6 +61,9 @@ EXPORTS = {
     "mlt_predict_batch_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mlt_submit_batch_dense": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "mlt_collect": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
+    "mlt_pack10": (C.c_uint64, [C.c_void_p, C.c_uint64, C.c_void_p]),
+    "mlt_predict_batch_packed10": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mlt_submit_batch_packed10": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "mlt_begin_picture": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
     "mlt_predict_ctu_in_picture": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "mlt_pin_host_buffer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
@@ -101,6 +104,21 @@ EXPORTS.update({
 })
 
 _LIB = None
+PACKED10_BYTES = 40960  # MLT_CTU_PACKED10_BYTES
+
+
+def pack10(orgpred: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+    """Host-side packer of the 10-bit transport (mlt_pack10): int16 [n,2,128,128] -> uint8 [n,40960].  Raises if a sample lies
+    outside [0, 1023] (such blocks must use the int16 entry points)."""
+    if orgpred.dtype != np.int16 or orgpred.shape[1:] != (2, CTU, CTU) or not orgpred.flags.c_contiguous:
+        raise ValueError("orgpred must be C-contiguous int16 [n,2,128,128]")
+    n = len(orgpred)
+    if out is None:
+        out = np.empty((n, PACKED10_BYTES), np.uint8)
+    bad = load_library().mlt_pack10(orgpred.ctypes.data, orgpred.size, out.ctypes.data)
+    if bad:
+        raise ValueError(f"{bad} samples outside [0, 1023]: not packable, use the int16 entry points")
+    return out
 
 
 def lib_path() -> str:
@@ -207,6 +225,27 @@ class MltPredictor:
             raise ValueError("orgpred must be C-contiguous int16 [n,2,128,128]")
         pocqp = np.ascontiguousarray(pocqp, np.int32)
         self._check(self._lib.mlt_submit_batch_dense(self._h, n, orgpred.ctypes.data, pocqp.ctypes.data), "mlt_submit_batch_dense")
+
+    # -- 10-bit packed transport (40 KiB per CTU instead of 64 KiB; samples must be in [0, 1023])
+    @staticmethod
+    def _packed_view(packed: np.ndarray) -> int:
+        if packed.dtype != np.uint8 or packed.ndim != 2 or packed.shape[1] != PACKED10_BYTES or not packed.flags.c_contiguous:
+            raise ValueError(f"packed must be C-contiguous uint8 [n,{PACKED10_BYTES}] (pack10())")
+        return len(packed)
+
+    def predict_batch_packed10(self, packed: np.ndarray, pocqp: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        n = self._packed_view(packed)
+        pocqp = np.ascontiguousarray(pocqp, np.int32)
+        if out is None:
+            out = np.zeros(n, RESULT_DTYPE)
+        self._check(self._lib.mlt_predict_batch_packed10(self._h, n, packed.ctypes.data, pocqp.ctypes.data, out.ctypes.data), "mlt_predict_batch_packed10")
+        return out
+
+    def submit_batch_packed10(self, packed: np.ndarray, pocqp: np.ndarray):
+        """Pipelined like submit_batch_dense; `packed` must stay alive and unchanged until the matching collect()."""
+        n = self._packed_view(packed)
+        pocqp = np.ascontiguousarray(pocqp, np.int32)
+        self._check(self._lib.mlt_submit_batch_packed10(self._h, n, packed.ctypes.data, pocqp.ctypes.data), "mlt_submit_batch_packed10")
 
     def collect(self, out: np.ndarray | None = None) -> np.ndarray:
         """Blocks for the oldest submitted batch; returns its results (a view of `out` when given)."""

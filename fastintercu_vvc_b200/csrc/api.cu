@@ -23,6 +23,8 @@ enum : uint32_t {
 
 constexpr int NCONV = 16, NACT = 17, CTU = MLT_CTU_SIZE;
 constexpr size_t CTU_IN_ELEMS = (size_t)2 * CTU * CTU; // org + pred planes
+constexpr size_t CTU_PACKED_BYTES = MLT_CTU_PACKED10_BYTES; // the same as a 10-bit packed stream (pack10.cu)
+static_assert(CTU_PACKED_BYTES == CTU_IN_ELEMS * 10 / 8, "packed CTU size");
 
 // forward order of the 16 3x3 convs after conv1 (arch.py:247-254 with BasicBlock [2,2,2,2])
 const LayerDesc kLayers[NCONV] = {
@@ -87,6 +89,7 @@ struct mlt_ctx {
     // batch k + 1 runs while batch k computes).
     struct HostSlot {
         int16_t *d_in = nullptr;
+        uint8_t *d_packed = nullptr; // 10-bit packed transport (mlt_*_packed10): H2D lands here, unpack10_kernel fills d_in; on first use
         CtuDev *d_ctus = nullptr, *h_ctus = nullptr;
         mlt_result *d_out = nullptr, *h_out = nullptr;
         cudaEvent_t done = nullptr;
@@ -385,7 +388,8 @@ int run_host_batch(mlt_ctx *c, int n, mlt_result *out, bool upload_in)
 // otherwise `descs` are gathered chunk by chunk into the pinned staging buffer first.
 // Enqueues everything (descriptor upload, chunked H2D, kernels, D2H of the results into the slot's pinned buffer, `done`
 // event) without waiting for it.
-int enqueue_host_batch(mlt_ctx *c, int slot, int n, const int16_t *src, const mlt_ctu_desc *descs, const int32_t *pocqp)
+int enqueue_host_batch(mlt_ctx *c, int slot, int n, const int16_t *src, const mlt_ctu_desc *descs, const int32_t *pocqp,
+                       const uint8_t *packed = nullptr)
 {
     cudaStream_t s = c->stream;
     mlt_ctx::HostSlot &H = c->slot[slot];
@@ -434,15 +438,24 @@ int enqueue_host_batch(mlt_ctx *c, int slot, int n, const int16_t *src, const ml
     for (int i = 0, off = 0; off < n; off += sizes[i], i++) {
         const int m = sizes[i];
         const int16_t *from = src ? src + (size_t)off * CTU_IN_ELEMS : c->h_in + (size_t)off * CTU_IN_ELEMS;
-        if (!src)
-            for (int k = off; k < off + m; k++)
-                gather_ctu(c->h_in + (size_t)k * CTU_IN_ELEMS, descs[k].org, descs[k].org_stride, descs[k].pred, descs[k].pred_stride);
-        CU(cudaMemcpyAsync(H.d_in + (size_t)off * CTU_IN_ELEMS, from, (size_t)m * CTU_IN_ELEMS * sizeof(int16_t),
-                           cudaMemcpyHostToDevice, c->copy_stream));
+        if (packed) {
+            CU(cudaMemcpyAsync(H.d_packed + (size_t)off * CTU_PACKED_BYTES, packed + (size_t)off * CTU_PACKED_BYTES, (size_t)m * CTU_PACKED_BYTES,
+                               cudaMemcpyHostToDevice, c->copy_stream));
+        } else {
+            if (!src)
+                for (int k = off; k < off + m; k++)
+                    gather_ctu(c->h_in + (size_t)k * CTU_IN_ELEMS, descs[k].org, descs[k].org_stride, descs[k].pred, descs[k].pred_stride);
+            CU(cudaMemcpyAsync(H.d_in + (size_t)off * CTU_IN_ELEMS, from, (size_t)m * CTU_IN_ELEMS * sizeof(int16_t),
+                               cudaMemcpyHostToDevice, c->copy_stream));
+        }
         CU(cudaEventRecord(c->ev_in[i], c->copy_stream));
         const int si = two ? (i & 1) : 0;
         cudaStream_t cs = si ? c->stream2 : s;
         CU(cudaStreamWaitEvent(cs, c->ev_in[i], 0));
+        if (packed) { // 40 KiB -> 64 KiB per CTU on the chunk's compute stream, right in front of its stem kernel
+            CU(launch_unpack10(H.d_packed + (size_t)off * CTU_PACKED_BYTES, H.d_in + (size_t)off * CTU_IN_ELEMS, (size_t)m * CTU_IN_ELEMS, cs));
+            c->launches++;
+        }
         const int rc = run_network(c, H.d_ctus + off, m, H.d_out + off, cs, si);
         if (rc) { cudaStreamSynchronize(c->copy_stream); cudaStreamSynchronize(c->stream2); return rc; }
     }
@@ -454,10 +467,17 @@ int enqueue_host_batch(mlt_ctx *c, int slot, int n, const int16_t *src, const ml
     return MLT_OK;
 }
 
-int run_host_batch_chunked(mlt_ctx *c, int n, const int16_t *src, const mlt_ctu_desc *descs, const int32_t *pocqp, mlt_result *out)
+int ensure_packed(mlt_ctx *c, mlt_ctx::HostSlot &H)
+{
+    if (!H.d_packed) CU(cudaMalloc(&H.d_packed, (size_t)c->max_batch * CTU_PACKED_BYTES));
+    return MLT_OK;
+}
+
+int run_host_batch_chunked(mlt_ctx *c, int n, const int16_t *src, const mlt_ctu_desc *descs, const int32_t *pocqp, mlt_result *out,
+                           const uint8_t *packed = nullptr)
 {
     if (c->submitted != c->collected) return fail(c, MLT_E_STATE, "%llu submitted batch(es) not collected yet", (unsigned long long)(c->submitted - c->collected));
-    const int rc = enqueue_host_batch(c, 0, n, src, descs, pocqp);
+    const int rc = enqueue_host_batch(c, 0, n, src, descs, pocqp, packed);
     if (rc) return rc;
     CU(cudaEventSynchronize(c->slot[0].done));
     memcpy(out, c->slot[0].h_out, (size_t)n * sizeof(mlt_result));
@@ -515,6 +535,7 @@ void mlt_destroy(mlt_ctx *c)
     if (c->ev_dev) cudaEventDestroy(c->ev_dev);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
+    for (auto &H : c->slot) cudaFree(H.d_packed);
     if (c->slot[1].d_in) { cudaFree(c->slot[1].d_in); cudaFree(c->slot[1].d_ctus); cudaFree(c->slot[1].d_out); cudaFreeHost(c->slot[1].h_ctus); cudaFreeHost(c->slot[1].h_out); }
     for (auto &H : c->slot) if (H.done) cudaEventDestroy(H.done);
     cudaFree(c->scratch_f); cudaFree(c->d_blob); cudaFree(c->d_in); cudaFree(c->d_ctus); cudaFree(c->d_out);
@@ -687,11 +708,11 @@ int mlt_predict_batch_dense(mlt_ctx *c, int n, const int16_t *orgpred, const int
     return run_host_batch_chunked(c, n, orgpred, nullptr, pocqp, out);
 }
 
-int mlt_submit_batch_dense(mlt_ctx *c, int n, const int16_t *orgpred, const int32_t *pocqp)
+static int submit_host_batch(mlt_ctx *c, int n, const int16_t *orgpred, const uint8_t *packed, const int32_t *pocqp)
 {
     int rc = check_ctx(c);
     if (rc) return rc;
-    if (n < 1 || !orgpred || !pocqp) return fail(c, MLT_E_INVAL, "null argument / empty batch");
+    if (n < 1 || (!orgpred && !packed) || !pocqp) return fail(c, MLT_E_INVAL, "null argument / empty batch");
     if (n > c->max_batch) return fail(c, MLT_E_BATCH, "n=%d > max_batch=%d", n, c->max_batch);
     if (c->submitted - c->collected >= 2) return fail(c, MLT_E_STATE, "two batches already in flight: call mlt_collect first");
     const int si = (int)(c->submitted & 1);
@@ -703,11 +724,27 @@ int mlt_submit_batch_dense(mlt_ctx *c, int n, const int16_t *orgpred, const int3
         CU(cudaHostAlloc(&H.h_ctus, (size_t)c->max_batch * sizeof(CtuDev), cudaHostAllocDefault));
         CU(cudaHostAlloc(&H.h_out, (size_t)c->max_batch * sizeof(mlt_result), cudaHostAllocDefault));
     }
-    rc = enqueue_host_batch(c, si, n, orgpred, nullptr, pocqp);
+    if (packed && (rc = ensure_packed(c, H)) != MLT_OK) return rc;
+    rc = enqueue_host_batch(c, si, n, orgpred, nullptr, pocqp, packed);
     if (rc) return rc;
     H.busy = true;
     c->submitted++;
     return MLT_OK;
+}
+
+int mlt_submit_batch_dense(mlt_ctx *c, int n, const int16_t *orgpred, const int32_t *pocqp) { return submit_host_batch(c, n, orgpred, nullptr, pocqp); }
+
+int mlt_submit_batch_packed10(mlt_ctx *c, int n, const uint8_t *packed, const int32_t *pocqp) { return submit_host_batch(c, n, nullptr, packed, pocqp); }
+
+int mlt_predict_batch_packed10(mlt_ctx *c, int n, const uint8_t *packed, const int32_t *pocqp, mlt_result *out)
+{
+    int rc = check_ctx(c);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!packed || !pocqp || !out))) return fail(c, MLT_E_INVAL, "null argument");
+    if (n > c->max_batch) return fail(c, MLT_E_BATCH, "n=%d > max_batch=%d", n, c->max_batch);
+    if (n == 0) return MLT_OK;
+    if ((rc = ensure_packed(c, c->slot[0])) != MLT_OK) return rc;
+    return run_host_batch_chunked(c, n, nullptr, nullptr, pocqp, out, packed);
 }
 
 int mlt_collect(mlt_ctx *c, mlt_result *out, int *n_out)

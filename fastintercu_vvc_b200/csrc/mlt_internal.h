@@ -181,6 +181,9 @@ constexpr size_t picture_me_smem_bytes(int R) { return (size_t)(16 * MLT_CTU_SIZ
 cudaError_t launch_picture_me(const int16_t *org, const int16_t *ref, int pitch, int w, int h, const PicCtu *ctus, int n, int R, unsigned *cost,
                               int16_t *mv, unsigned *best_cost, cudaStream_t s);
 
+// ---- pack10.cu : 10-bit packed Pel transport (4 samples per 5 bytes); device side of mlt_*_packed10
+cudaError_t launch_unpack10(const uint8_t *packed, int16_t *out, size_t samples, cudaStream_t s);
+
 // ---- misc
 cudaError_t launch_unpack_act(const __half *in, float *out, int nimg, const ActLayout &L, cudaStream_t s);
 

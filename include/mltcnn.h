@@ -111,6 +111,19 @@ MLT_API int mlt_predict_batch_dense(mlt_ctx *ctx, int n, const int16_t *orgpred,
 MLT_API int mlt_submit_batch_dense(mlt_ctx *ctx, int n, const int16_t *orgpred, const int32_t *pocqp);
 MLT_API int mlt_collect(mlt_ctx *ctx, mlt_result *out, int *n_out);
 
+/* 10-bit packed transport of the same dense batch (no counterpart in the reference, which moves 128 KiB of fp32 per CTU,
+ * EncCu.cpp:875): with InternalBitDepth 10 every Pel is in [0, 1023], so a CTU's 2 x 16384 int16 samples travel as a
+ * little-endian bit stream of 10-bit fields, MLT_CTU_PACKED10_BYTES = 40960 bytes instead of 65536, and are unpacked on the
+ * device in front of the stem kernel.  On multi-GPU hosts the aggregate H2D rate bounds the batch API; this is -37.5 % bytes.
+ * mlt_pack10 is the host-side packer (plain C, any thread; count % 4 == 0): it returns the number of samples OUTSIDE
+ * [0, 1023] -- such a block cannot be packed (the (uint16_t)-cast semantics of EncCu.cpp:816,827 need all 16 bits) and must
+ * go through the int16 entry points.  Results are byte-identical to mlt_predict_batch_dense on the unpacked samples.
+ * mlt_submit_batch_packed10 pairs with mlt_collect exactly like mlt_submit_batch_dense. */
+#define MLT_CTU_PACKED10_BYTES 40960
+MLT_API uint64_t mlt_pack10(const int16_t *src, uint64_t count, uint8_t *dst);
+MLT_API int mlt_predict_batch_packed10(mlt_ctx *ctx, int n, const uint8_t *packed, const int32_t *pocqp, mlt_result *out);
+MLT_API int mlt_submit_batch_packed10(mlt_ctx *ctx, int n, const uint8_t *packed, const int32_t *pocqp);
+
 /* Device-resident batch on the caller's stream (cudaStream_t passed as void*; NULL = default stream).
  * d_orgpred / d_pocqp / d_out are device pointers; asynchronous w.r.t. the host.  The call uses the context's own
  * activation buffers: the library orders it after the previous device call (whatever its stream) and orders every later

@@ -583,6 +583,33 @@ def test_device_calls_on_different_streams_and_host_calls_do_not_race(blob, ctus
         assert p.collect().tobytes() == base.tobytes()
 
 
+def test_packed10_transport_is_byte_identical_to_the_int16_path(blob, ctus):
+    """10-bit packed transport (mlt_pack10 on the host, unpack10_kernel on the device): the blocking and the pipelined packed entry
+    points must return exactly what mlt_predict_batch_dense returns on the same samples -- small batch, a chunked batch (>= 1024
+    CTUs: growing chunk schedule, both activation sets) and two batches in flight."""
+    from fastintercu_vvc_b200 import MltPredictor
+    from fastintercu_vvc_b200.capi import pack10
+
+    orgpred, pocqp = ctus
+    n = 1100
+    idx = np.random.RandomState(5).randint(0, len(orgpred), n)
+    big, big_pq = np.ascontiguousarray(orgpred[idx]), np.ascontiguousarray(pocqp[idx])
+    with MltPredictor(blob, device=0, max_batch=n) as p:
+        base = p.predict_batch_dense(orgpred, pocqp)
+        l0 = p.launch_count
+        got = p.predict_batch_packed10(pack10(orgpred), pocqp)
+        assert p.launch_count - l0 == 18  # unpack + stem + 15 convs + head
+        assert got.tobytes() == base.tobytes()
+        want = p.predict_batch_dense(big, big_pq)
+        packed = pack10(big)
+        assert p.predict_batch_packed10(packed, big_pq).tobytes() == want.tobytes()
+        p.submit_batch_packed10(packed, big_pq)
+        p.submit_batch_packed10(pack10(orgpred), pocqp)
+        assert p.collect().tobytes() == want.tobytes()
+        assert p.collect().tobytes() == base.tobytes()
+        assert np.array_equal(want["logits"].view(np.uint32), base["logits"][idx].view(np.uint32))
+
+
 def test_fp32_engine_large_host_batch_is_chunk_safe(blob, oracle):
     """The fp32 cross-check engine has one set of fp32 buffers: a host batch large enough to be chunked (>= 1024 CTUs) must
     not spread its chunks over the two compute streams (found by tools/precision_large.py: garbage at n = 2048)."""

@@ -102,14 +102,14 @@ def test_library_exports_every_declared_symbol():
     from fastintercu_vvc_b200 import capi
 
     hdr = open(os.path.join(ROOT, "include", "mltcnn.h")).read() + open(os.path.join(ROOT, "include", "mltcnn_cu.h")).read()
-    declared = set(re.findall(r"MLT_API[^;(]*?\b(mlt_[a-z_]+)\s*\(", hdr))
+    declared = set(re.findall(r"MLT_API[^;(]*?\b(mlt_[a-z0-9_]+)\s*\(", hdr))
     assert len(declared) >= 18 + 11, declared
     lib = capi.load_library()
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/*.h but not exported"
     assert declared == set(capi.EXPORTS), declared ^ set(capi.EXPORTS)
     out = subprocess.run(["nm", "-D", "--defined-only", capi.lib_path()], capture_output=True, text=True).stdout
-    exported = set(re.findall(r" T (mlt_[a-z_]+)", out))
+    exported = set(re.findall(r" T (mlt_[a-z0-9_]+)", out))
     assert exported == declared, exported ^ declared  # nothing else leaks out of the library
     assert lib.mlt_abi_version() == 1
     assert b"batch" in lib.mlt_strerror(-7)
@@ -291,3 +291,27 @@ def test_packer_reads_the_reference_containers(tmp_path):
         pw.export_state_dict(sd, rt)
         assert all(np.array_equal(pw.load_checkpoint(rt)[k], sd[k]) for k in sd)
     assert pw.main(["only-one-arg"]) == 2
+
+
+def test_pack10_host_packer_roundtrip_and_range_check():
+    """mlt_pack10 (host side of the 10-bit packed transport): little-endian bit stream of 10-bit fields, 4 samples per 5 bytes;
+    samples outside [0, 1023] are counted, not silently saturated."""
+    from fastintercu_vvc_b200 import capi
+
+    rs = np.random.RandomState(3)
+    x = rs.randint(0, 1024, (3, 2, 128, 128)).astype(np.int16)
+    x[0, 0, 0, :4] = (0, 1023, 512, 1)
+    p = capi.pack10(x)
+    assert p.shape == (3, capi.PACKED10_BYTES) and capi.PACKED10_BYTES == 2 * 128 * 128 * 10 // 8
+    bits = np.unpackbits(p.reshape(-1), bitorder="little").reshape(-1, 10)
+    back = (bits.astype(np.int32) << np.arange(10)).sum(1).astype(np.int16).reshape(x.shape)
+    assert np.array_equal(back, x)
+    assert p[0, :5].tolist() == [0x00, 0xFC, 0x0F, 0x60, 0x00]  # 0 | 1023<<10 | 512<<20 | 1<<30, known answer
+    L = capi.load_library()
+    out = np.empty(capi.PACKED10_BYTES, np.uint8)
+    for bad_val, count in ((-1, 1), (1024, 1), (-32768, 1)):
+        y = x[1].copy()
+        y[1, 5, 7] = bad_val
+        assert L.mlt_pack10(y.ctypes.data, y.size, out.ctypes.data) == count
+        with pytest.raises(ValueError):
+            capi.pack10(y[None])

@@ -17,7 +17,7 @@ for what in "$@"; do
       echo "config1seq rc=$?"; head -40 gpurun_out/${tag}_config1seq.log ;;
     cut3)  # affordable cut of config 3: 1920x1080 10-bit, few frames, 4 QPs, all encodes side by side
       timeout ${CUT3_TIMEOUT:-2400} python tools/vtm_run.py --size ${CUT3_SIZE:-1920x1080} --bits 10 --frames ${CUT3_FRAMES:-5} --qps 22,27,32,37 \
-          --encoders ${CUT3_ENCODERS:-ref_cpu,mlt,anchor,prepass0,prepass8} --jobs ${CUT3_JOBS:-12} \
+          --encoders ${CUT3_ENCODERS:-ref_cpu,mlt,anchor,prepass0,prepass8} --jobs ${CUT3_JOBS:-12} --ref-threads ${CUT3_REF_THREADS:-2} \
           --out gpurun_out/${tag}_cut3.json > gpurun_out/${tag}_cut3.log 2>&1
       echo "cut3 rc=$?"; head -120 gpurun_out/${tag}_cut3.log ;;
   esac

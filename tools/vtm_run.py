@@ -226,6 +226,7 @@ def main() -> None:
     ap.add_argument("--encoders", default="ref_cpu,mlt,anchor")
     ap.add_argument("--jobs", type=int, default=1, help="encodes run side by side (timings are only comparable at equal load)")
     ap.add_argument("--gpus", type=int, default=1, help="GPUs to spread GPU encoders over (CUDA_VISIBLE_DEVICES per process)")
+    ap.add_argument("--ref-threads", type=int, default=0, help="OMP_NUM_THREADS for the reference-hook encoders (0 = libtorch default = all cores)")
     ap.add_argument("--work", default=None)
     ap.add_argument("--out", default=None)
     ap.add_argument("--keep-traces", action="store_true")
@@ -246,7 +247,7 @@ def main() -> None:
     qps = [int(q) for q in a.qps.split(",")]
     encs = a.encoders.split(",")
     level = {416: "2.1", 832: "3.1", 1280: "4", 1920: "4.1", 3840: "5.1"}
-    jobs = [(e, c, q) for c in clips for q in qps for e in encs]
+    jobs = [(e, c, q) for c in clips for q in sorted(qps) for e in encs]  # low QPs (the long encodes) start first
     t0 = time.time()
     gpu_rr = [0]
 
@@ -256,11 +257,12 @@ def main() -> None:
         if e not in ("ref_cpu", "anchor"):
             dev = gpu_rr[0] % a.gpus
             gpu_rr[0] += 1
-        return run_encode(e, c, q, work, model_dir, blob, dev, level.get(c["w"], "5.1"))
+        extra = {"OMP_NUM_THREADS": str(a.ref_threads)} if (a.ref_threads and e.startswith("ref_")) else None
+        return run_encode(e, c, q, work, model_dir, blob, dev, level.get(c["w"], "5.1"), extra)
 
     with ThreadPoolExecutor(max_workers=a.jobs) as ex:
         results = list(ex.map(one, jobs))
-    doc = {"host_cores": os.cpu_count(), "jobs_side_by_side": a.jobs, "gpus": a.gpus, "wall_s": round(time.time() - t0, 1),
+    doc = {"host_cores": os.cpu_count(), "jobs_side_by_side": a.jobs, "ref_threads": a.ref_threads or "all", "gpus": a.gpus, "wall_s": round(time.time() - t0, 1),
            "clips": [{k: v for k, v in c.items() if k != "path"} for c in clips], "qps": qps, "encoders": encs,
            "weights": "oracle.ref_arch.make_state_dict(10): seeded random (the trained .pt is not in the reference, .MISSING_LARGE_BLOBS)",
            "comparison": compare(results)}
