@@ -16,7 +16,7 @@ namespace {
 
 constexpr uint32_t MLTW_MAGIC = 0x57544C4Du;
 enum : uint32_t {
-    SEC_CONV1_F32 = 0x001, SEC_CONV1_UMMA = 0x002, SEC_STEM_CONV1 = 0x003, SEC_W_F16 = 0x100, SEC_BIAS_FUSED = 0x200, SEC_W_F32 = 0x300, SEC_BIAS = 0x400,
+    SEC_CONV1_F32 = 0x001, SEC_CONV1_UMMA = 0x002, SEC_STEM_CONV1 = 0x003, SEC_STEM5_W = 0x004, SEC_STEM5_CORR = 0x005, SEC_W_F16 = 0x100, SEC_BIAS_FUSED = 0x200, SEC_W_F32 = 0x300, SEC_BIAS = 0x400,
     SEC_SC_W_F16 = 0x500, SEC_SC_W_F32 = 0x600, SEC_SC_BIAS = 0x700, SEC_FC_W = 0x800, SEC_FC_B = 0x900, SEC_BIAS_MMA = 0xA00, SEC_X_W_F16 = 0xB00,
     SEC_W_SPLIT = 0xC00, SEC_X_SPLIT = 0xD00 // layer3 weights packed for the channel-split kernels
 };
@@ -174,7 +174,8 @@ int load_blob(mlt_ctx *c, const char *path)
     }
     // every section this architecture needs must be present with the exact size
     auto need = [&](uint32_t id, size_t bytes) { return c->sec[id].dev != nullptr && c->sec[id].bytes == bytes; };
-    bool ok = need(SEC_CONV1_F32, 9 * 2 * 32 * 4) && need(SEC_CONV1_UMMA, 2 * 4 * 32 * 16) && need(SEC_STEM_CONV1, 4 * 1024);
+    bool ok = need(SEC_CONV1_F32, 9 * 2 * 32 * 4) && need(SEC_CONV1_UMMA, 2 * 4 * 32 * 16) && need(SEC_STEM_CONV1, 4 * 1024) &&
+              need(SEC_STEM5_W, 7 * 1024) && need(SEC_STEM5_CORR, (2 * 5 * 2 * 32 + 2 * 32 + 32) * 4);
     for (int li = 0; li < NCONV && ok; li++) {
         const LayerDesc &L = kLayers[li];
         ok = need(SEC_W_F16 + li, (size_t)9 * L.cin * L.cout * 2) && need(SEC_W_F32 + li, (size_t)9 * L.cin * L.cout * 4) &&
@@ -266,8 +267,13 @@ int run_network(mlt_ctx *c, const CtuDev *ctus, int n, mlt_result *out, cudaStre
         int first = 0;
         if (c->engine == 0) {
             // fused stem: staging + conv1 + layer0.0.conv1; conv1's 1 MiB / CTU output never reaches HBM
-            CU(launch_stem_umma(ctus, n, secp<__half>(c, SEC_STEM_CONV1), secp<__half>(c, SEC_W_F16 + 0), secp<float>(c, SEC_BIAS_FUSED + 0),
-                                S.act0q, S.act_h[1], c->num_sms, s));
+            static const bool old_stem = getenv("MLT_STEM_OLD") != nullptr; // A/B switch: the round-1 stem (conv1 and layer0.0.conv1 as two MMA stages)
+            if (old_stem)
+                CU(launch_stem_umma(ctus, n, secp<__half>(c, SEC_STEM_CONV1), secp<__half>(c, SEC_W_F16 + 0), secp<float>(c, SEC_BIAS_FUSED + 0),
+                                    S.act0q, S.act_h[1], c->num_sms, s));
+            else
+                CU(launch_stem5_umma(ctus, n, secp<__half>(c, SEC_STEM5_W), secp<float>(c, SEC_STEM5_CORR), secp<float>(c, SEC_STEM5_CORR) + 704,
+                                     S.act0q, S.act_h[1], c->num_sms, s)); // bias: the section's last 32 floats (corrected for W5's fp16 rounding)
             c->launches++;
             if (prof) { CU(cudaEventRecord(c->prof_ev[ev++], s)); CU(cudaEventRecord(c->prof_ev[ev++], s)); }
             first = 1;
@@ -575,6 +581,7 @@ int mlt_create_ex(mlt_ctx **out, const char *weights_path, int cuda_device, int 
         if (r) return r;
         CU(conv_umma_init());
         CU(stem_umma_init());
+        CU(stem5_umma_init());
         CU(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&c->ev_dev, cudaEventDisableTiming));

@@ -61,6 +61,14 @@ cudaError_t stem_umma_init();
 cudaError_t launch_stem_umma(const CtuDev *ctus, int n, const __half *w1 /*SEC_STEM_CONV1*/, const __half *w0, const float *bias /*fp32*/,
                              __half *act0q /*conv1 at even rows/cols [n][4][64][64][8]*/, __half *act1, int num_sms, cudaStream_t s);
 
+// ---- stem5_umma.cu : the stem with conv1 and layer0.0.conv1 COMPOSED into one 5x5 stride-2 conv (no activation lies between them,
+// arch.py:277-279) + conv1 at the even positions for layer0.0's shortcut; product path since round 2 (MLT_STEM_OLD=1: the kernel above)
+cudaError_t stem5_umma_init();
+cudaError_t launch_stem5_umma(const CtuDev *ctus, int n, const __half *w /*SEC_STEM5_W*/, const float *corrw /*SEC_STEM5_CORR*/, const float *bias,
+                              __half *act0q, __half *act1, int num_sms, cudaStream_t s);
+cudaError_t launch_cu_stem5_umma(int size, const CtuDev *cus, int n, const __half *w, const float *corrw, const float *bias, __half *act0q,
+                                 __half *act1, int cap, int num_sms, cudaStream_t s);
+
 // the same fused stem for the 64- / 32-px CU networks (strip-layout outputs; a 16-px CU is smaller than one work unit)
 cudaError_t launch_cu_stem_umma(int size, const CtuDev *cus, int n, const __half *w1, const __half *w0, const float *bias, __half *act0q,
                                 __half *act1, int cap, int num_sms, cudaStream_t s);

@@ -23,8 +23,13 @@ The smaller-CU models (64 / 32 / 16-px `GapBigMltCuORPQ`, mlt_cu_or_pq_arch.py:5
 model2torchScript.py:14-22) use the same container with the header's arch field = CU size: the operand layouts follow
 the per-size tile shapes of csrc/cu_net.cuh, so a blob is packed for ONE size (`cu_conv_table(size)`).
 
+  * corrects every tcgen05 conv's bias for the SYSTEMATIC part of its fp16 weight-rounding error, E[(w_q - w) * x], with per-tap
+    input means from one exact fp32 forward over calibration blocks (bias_correction; seeded synthetic blocks by default,
+    `--calib blocks.npy` for real ones); the fp32 cross-check sections are left exact.
+
 CLI:  python -m fastintercu_vvc_b200.pack_weights model.pth out.mltw            (128x128 CTU model)
       python -m fastintercu_vvc_b200.pack_weights --cu 64 model.pth out.mltw    (64 / 32 / 16-px CU model)
+      python -m fastintercu_vvc_b200.pack_weights --calib blocks.npy model.pth out.mltw
 """
 from __future__ import annotations
 
@@ -42,6 +47,8 @@ PLANES = (32, 64, 128, 256)
 SEC_CONV1_F32 = 0x001
 SEC_CONV1_UMMA = 0x002
 SEC_STEM_CONV1 = 0x003
+SEC_STEM5_W = 0x004     # composite stem operands for csrc/stem5_umma.cu (stem5_operands)
+SEC_STEM5_CORR = 0x005  # fp32 border-correction weights of the same kernel
 SEC_W_F16 = 0x100
 SEC_BIAS_FUSED = 0x200
 SEC_W_F32 = 0x300
@@ -135,6 +142,88 @@ def quantize_fp16_diffused(w: np.ndarray) -> np.ndarray:
     return out.reshape(w.shape)
 
 
+# --------------------------------------------------------------------------- calibrated bias correction
+
+
+def stage_input(orgpred: np.ndarray) -> np.ndarray:
+    """int16 [n][2][S][S] (org, pred) -> float32 [n][2][S][S] (org, |org - pred|) * (float)(1/1023), clamped: EncCu.cpp:810-867."""
+    o = orgpred[:, 0].astype(np.uint16).astype(np.int32)
+    q = orgpred[:, 1].astype(np.uint16).astype(np.int32)
+    x = np.stack([o, np.abs(o - q)], 1).astype(np.float32) * ALPHA
+    return np.clip(x, 0.0, 1.0)
+
+
+def tap_means(x, k: int, stride: int, pad: int) -> np.ndarray:
+    """Mean, over images and output positions, of the zero-padded input sample each kernel tap sees: [C][k][k] (torch [n][C][H][W])."""
+    import torch.nn.functional as F
+
+    n, c, h, w = x.shape
+    xp = F.pad(x, (pad, pad, pad, pad))
+    ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+    out = np.zeros((c, k, k))
+    for a in range(k):
+        for b in range(k):
+            out[:, a, b] = xp[:, :, a : a + stride * (ho - 1) + 1 : stride, b : b + stride * (wo - 1) + 1 : stride].double().mean((0, 2, 3)).numpy()
+    return out
+
+
+def calibrate_tap_means(sd: dict, orgpred: np.ndarray) -> dict:
+    """One exact fp32 forward of the network (torch CPU, folded BN) over calibration blocks; returns, per 3x3 conv prefix, the mean
+    input sample under each kernel tap [cin][3][3] (zero padding included), plus 'stem5': the same for the composite 5x5 stride-2
+    stem conv over the two input planes [2][5][5].  Works for the CTU network (4 stages) and the CU networks (5 stages)."""
+    import torch
+    import torch.nn.functional as F
+
+    sd = normalise_state_dict(sd)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a, np.float32))
+    means = {}
+    with torch.no_grad():
+        x = T(stage_input(orgpred))
+        means["stem5"] = tap_means(x, 5, 2, 2)
+        y = F.conv2d(x, T(sd["conv1.weight"]), padding=1)
+        L = 0
+        while f"layer{L}.0.conv1.weight" in sd:
+            for b in range(2):
+                p = f"layer{L}.{b}"
+                w1, b1 = fold_bn(sd[f"{p}.conv1.weight"], sd, f"{p}.bn1")
+                w2, b2 = fold_bn(sd[f"{p}.conv2.weight"], sd, f"{p}.bn2")
+                stride = 2 if b == 0 else 1
+                means[f"{p}.conv1"] = tap_means(y, 3, stride, 1)
+                t = F.relu(F.conv2d(y, T(w1), T(b1), stride=stride, padding=1))
+                means[f"{p}.conv2"] = tap_means(t, 3, 1, 1)
+                o = F.conv2d(t, T(w2), T(b2), padding=1)
+                if b == 0:
+                    ws, bs = fold_bn(sd[f"{p}.shortcut.0.weight"], sd, f"{p}.shortcut.1")
+                    o = o + F.conv2d(y, T(ws), T(bs), stride=stride)
+                else:
+                    o = o + y
+                y = F.relu(o)
+            L += 1
+    # fp16-rounded means: the correction must not depend on the last bits of this machine's fp32 conv kernels
+    return {k: v.astype(np.float16).astype(np.float64) for k, v in means.items()}
+
+
+def bias_correction(exact: np.ndarray, quantized: np.ndarray, tapmean: np.ndarray) -> np.ndarray:
+    """E[sum_k (w_q - w) x_k] per output channel for weights [cout][cin][k][k] and tap means [cin][k][k]: the systematic part of
+    the fp16 weight-rounding error.  It is the same at every pixel of every block, so it survives the global average pools and is
+    the largest single error of the fp16-operand path (tools/emulate_ctu_precision.py: per-logit offsets up to 6e-4 against a
+    sample-to-sample spread of 1e-4); subtracting it from the layer's bias costs nothing at run time."""
+    dw = quantized.astype(np.float64) - exact.astype(np.float64)
+    return np.einsum("ncab,cab->n", dw, tapmean)
+
+
+CALIB_SEED, CALIB_CTUS, CALIB_CUS = 77001, 16, 96
+
+
+def default_calibration(arch: int) -> np.ndarray:
+    """Calibration blocks when the caller has none (e.g. dumped from a real encode, hook/dataset_dump): seeded synthetic ones."""
+    from . import synth
+
+    if arch == ARCH_CTU128:
+        return synth.synth_ctus(CALIB_CTUS, CALIB_SEED)[0]
+    return synth.synth_cus(CALIB_CUS, arch, CALIB_SEED)[0]
+
+
 def pack_umma_b(w: np.ndarray, group: int) -> np.ndarray:
     """Folded OIHW fp32 -> fp16 [cin/group][kh*kw][group/8][cout][8] (error-diffused rounding, quantize_fp16_diffused)."""
     cout, cin, kh, kw = w.shape
@@ -205,6 +294,63 @@ def stem_conv1_operand(w: np.ndarray) -> np.ndarray:
     return out
 
 
+def stem5_composite(w1: np.ndarray, w0f: np.ndarray):
+    """conv1 (arch.py:278: 2 -> 32, 3x3, pad 1, NO BatchNorm, NO activation) feeds layer0.0.conv1 (32 -> 32, 3x3, stride 2, pad 1,
+    folded BN) and layer0.0's shortcut directly, so conv1 o layer0.0.conv1 is ONE linear map of the input: a 5x5 stride-2 conv
+    2 -> 32 -- except where layer0.0.conv1's zero padding replaces conv1 outputs at row / column -1 (output row 0 / column 0).
+    Returns float64
+      W5   [32][2][5][5]  W5[co][ci][a+kh][b+kw] += w0f[co][cm][a][b] * w1[cm][ci][kh][kw]; z = W5 * in(2oy-2.., 2ox-2..) (zero-padded in)
+      Wtop [32][2][5]     the part of W5[dy = 2] that came through conv1 row -1 (a = 0, kh = 2): subtract Wtop * in(0, 2ox-2+e) at oy = 0
+      Wleft[32][2][5]     the same through conv1 column -1 (b = 0, kw = 2): subtract Wleft * in(2oy-2+e, 0) at ox = 0
+      Wc   [32][2]        conv1(-1,-1)'s share (a = b = 0, kh = kw = 2), contained in both: add back Wc * in(0, 0) at (0, 0)."""
+    w1 = w1.astype(np.float64)
+    w0f = w0f.astype(np.float64)
+    W5 = np.zeros((32, 2, 5, 5))
+    Wtop = np.zeros((32, 2, 5))
+    Wleft = np.zeros((32, 2, 5))
+    for a in range(3):
+        for b in range(3):
+            for kh in range(3):
+                for kw in range(3):
+                    t = w0f[:, :, a, b] @ w1[:, :, kh, kw]  # [co][ci]
+                    W5[:, :, a + kh, b + kw] += t
+                    if a == 0 and kh == 2:
+                        Wtop[:, :, b + kw] += t
+                    if b == 0 and kw == 2:
+                        Wleft[:, :, a + kh] += t
+    Wc = w0f[:, :, 0, 0] @ w1[:, :, 2, 2]
+    return W5, Wtop, Wleft, Wc
+
+
+def stem5_operands(w1: np.ndarray, w0f: np.ndarray):
+    """Operands of csrc/stem5_umma.cu.  The A operand rows are output pixels; a 16-byte K chunk is {org, res} of four horizontally
+    adjacent input samples (sample * 2^-10, exact in fp16), so all weights carry (float)(1/1023) * 2^10 (the staging multiply of
+    EncCu.cpp:835-838 folded in, like conv1_operand).
+      fp16 [7][2 chunks][32 cout][8]:
+        m = 0..4  composite 5x5 stride-2 conv, kernel row dy = m: chunk 0 element dx*2 + ch = W5[co][ch][dy][dx] (dx < 4),
+                  chunk 1 elements 0, 1 = W5[co][ch][dy][4], rest 0
+        m = 5     conv1 at even positions (the shortcut's input): chunks = kernel rows kh = 0 and kh = 2, element dx*2 + ch
+        m = 6     chunk 0 = kernel row kh = 1, chunk 1 = 0
+      fp32 [2][5][2][32] + [2][32]: Wtop / Wleft as [e][ch][co] and Wc as [ch][co], scaled the same way (CUDA-core border fix)."""
+    scale = float(ALPHA) * 1024.0
+    W5, Wtop, Wleft, Wc = stem5_composite(w1, w0f)
+    op = np.zeros((7, 2, 32, 8), np.float64)
+    for dy in range(5):
+        for dx in range(4):
+            for ch in range(2):
+                op[dy, 0, :, dx * 2 + ch] = W5[:, ch, dy, dx] * scale
+        for ch in range(2):
+            op[dy, 1, :, ch] = W5[:, ch, dy, 4] * scale
+    w1d = w1.astype(np.float64) * scale
+    for m, c, kh in ((5, 0, 0), (5, 1, 2), (6, 0, 1)):
+        for dx in range(3):
+            for ch in range(2):
+                op[m, c, :, dx * 2 + ch] = w1d[:, ch, kh, dx]
+    corr = np.concatenate([(Wtop * scale).transpose(2, 1, 0).reshape(-1), (Wleft * scale).transpose(2, 1, 0).reshape(-1),
+                           (Wc * scale).transpose(1, 0).reshape(-1)]).astype(np.float32)
+    return op.astype(np.float16), corr
+
+
 def extra_operand_hilo(ws: np.ndarray, gx: int) -> np.ndarray:
     """[cout][xc] fp32 folded 1x1 shortcut weights -> fp16 [xc/gx][hi, lo][gx/8][cout][8]: hi = fp16(w), lo = fp16(w - hi).
     The conv kernel runs the extra-operand stage twice (ConvCfg::XLO), so the shortcut is applied at ~2^-22 precision."""
@@ -225,9 +371,11 @@ def extra_operand(ws: np.ndarray, gx: int) -> np.ndarray:
     return np.ascontiguousarray(t)
 
 
-def build_sections(sd: dict) -> list:
+def build_sections(sd: dict, calib: np.ndarray | None = None, correct_bias: bool = True) -> list:
+    """calib: int16 [n][2][128][128] calibration CTUs for the bias correction (default: seeded synthetic ones)."""
     sd = normalise_state_dict(sd)
     secs = []
+    tm = calibrate_tap_means(sd, default_calibration(ARCH_CTU128) if calib is None else calib) if correct_bias else None
 
     def add(sid, arr, dtype):
         secs.append((sid, np.ascontiguousarray(arr, dtype)))
@@ -236,12 +384,28 @@ def build_sections(sd: dict) -> list:
     add(SEC_CONV1_F32, w.transpose(2, 3, 1, 0).reshape(9, 2, 32), np.float32)
     add(SEC_CONV1_UMMA, conv1_operand(w), np.float16)
     add(SEC_STEM_CONV1, stem_conv1_operand(w), np.float16)
+    w0f, b0f = fold_bn(sd["layer0.0.conv1.weight"], sd, "layer0.0.bn1")
+    s5w, s5c = stem5_operands(w, w0f)
+    b5 = b0f.astype(np.float64)
+    if tm is not None:  # the composite weights as the kernel sees them (fp16, without the staging scale) against the exact ones
+        W5 = stem5_composite(w, w0f)[0]
+        W5q = np.zeros_like(W5)
+        sc = float(ALPHA) * 1024.0
+        for dy in range(5):
+            for ch in range(2):
+                for dx in range(4):
+                    W5q[:, ch, dy, dx] = s5w[dy, 0, :, dx * 2 + ch].astype(np.float64) / sc
+                W5q[:, ch, dy, 4] = s5w[dy, 1, :, ch].astype(np.float64) / sc
+        b5 = b5 - bias_correction(W5, W5q, tm["stem5"])
+    add(SEC_STEM5_W, s5w, np.float16)
+    add(SEC_STEM5_CORR, np.concatenate([s5c, b5.astype(np.float32)]), np.float32)  # ... + the stem kernel's own (corrected) bias [32]
     for li, (prefix, cin, cout, stride, hout, group, sc) in enumerate(conv_table()):
         bn = prefix.replace("conv", "bn")
         wf, bf = fold_bn(sd[f"{prefix}.weight"], sd, bn)
         assert wf.shape == (cout, cin, 3, 3), (prefix, wf.shape)
         packed = pack_umma_b(wf, group)
         add(SEC_W_F16 + li, packed, np.float16)
+        corr = bias_correction(wf, quantize_fp16_diffused(wf), tm[prefix]) if tm is not None else 0.0
         if li in SPLIT_LAYERS:
             add(SEC_W_SPLIT + li, split_cout(packed, SPLIT_WAYS), np.float16)
         add(SEC_W_F32 + li, wf.transpose(2, 3, 1, 0).reshape(9, cin, cout), np.float32)
@@ -264,6 +428,7 @@ def build_sections(sd: dict) -> list:
             add(SEC_X_W_F16 + li, xop, np.float16)
             if li in SPLIT_LAYERS:
                 add(SEC_X_SPLIT + li, split_cout(xop, SPLIT_WAYS), np.float16)
+        fused = (fused.astype(np.float64) - corr).astype(np.float32)  # tcgen05 path only: SEC_BIAS (fp32 engine, exact weights) stays exact
         add(SEC_BIAS_FUSED + li, fused, np.float32)
         add(SEC_BIAS_MMA + li, bias_operand(fused), np.float16)
     for i in range(3):
@@ -299,9 +464,10 @@ def cu_conv_table(size: int):
     return rows
 
 
-def build_cu_sections(sd: dict, size: int) -> list:
+def build_cu_sections(sd: dict, size: int, calib: np.ndarray | None = None, correct_bias: bool = True) -> list:
     sd = normalise_state_dict(sd)
     secs = []
+    tm = calibrate_tap_means(sd, default_calibration(size) if calib is None else calib) if correct_bias else None
 
     def add(sid, arr, dtype):
         secs.append((sid, np.ascontiguousarray(arr, dtype)))
@@ -316,6 +482,8 @@ def build_cu_sections(sd: dict, size: int) -> list:
         add(SEC_W_F16 + li, pack_umma_b(wf, group), np.float16)
         add(SEC_W_F32 + li, wf.transpose(2, 3, 1, 0).reshape(9, cin, cout), np.float32)
         add(SEC_BIAS + li, bf, np.float32)
+        # (tap means include the zero padding, so the centre-tap-only layers of 1x1 maps are covered: their other taps have mean 0)
+        corr = bias_correction(wf, quantize_fp16_diffused(wf), tm[prefix]) if tm is not None else 0.0
         fused = bf
         if kind == 1:  # 1x1 stride-2 shortcut conv + BN of the stage's first block, as hi + lo fp16 K-slabs
             sp = prefix.rsplit(".", 1)[0] + ".shortcut"
@@ -327,6 +495,7 @@ def build_cu_sections(sd: dict, size: int) -> list:
             fused = (bf.astype(np.float32) + bs.astype(np.float32)).astype(np.float32)
         elif kind == 3:  # identity residual of the second block
             add(SEC_X_W_F16 + li, extra_operand(np.eye(cout, dtype=np.float32), gx), np.float16)
+        fused = (fused.astype(np.float64) - corr).astype(np.float32)
         add(SEC_BIAS_FUSED + li, fused, np.float32)
         add(SEC_BIAS_MMA + li, bias_operand(fused), np.float16)
     for i in range(4):
@@ -335,8 +504,8 @@ def build_cu_sections(sd: dict, size: int) -> list:
     return secs
 
 
-def pack(sd: dict, arch: int = ARCH_CTU128) -> bytes:
-    secs = build_sections(sd) if arch == ARCH_CTU128 else build_cu_sections(sd, arch)
+def pack(sd: dict, arch: int = ARCH_CTU128, calib: np.ndarray | None = None) -> bytes:
+    secs = build_sections(sd, calib) if arch == ARCH_CTU128 else build_cu_sections(sd, arch, calib)
     table_bytes = 24 * len(secs)
     off = (32 + table_bytes + 255) // 256 * 256
     table, blobs = [], []
@@ -354,16 +523,16 @@ def pack(sd: dict, arch: int = ARCH_CTU128) -> bytes:
     return out
 
 
-def write_blob(sd: dict, path: str) -> int:
-    data = pack(sd)
+def write_blob(sd: dict, path: str, calib: np.ndarray | None = None) -> int:
+    data = pack(sd, calib=calib)
     with open(path, "wb") as f:
         f.write(data)
     return len(data)
 
 
-def write_cu_blob(sd: dict, size: int, path: str) -> int:
+def write_cu_blob(sd: dict, size: int, path: str, calib: np.ndarray | None = None) -> int:
     assert size in (64, 32, 16)
-    data = pack(sd, size)
+    data = pack(sd, size, calib)
     with open(path, "wb") as f:
         f.write(data)
     return len(data)
@@ -412,14 +581,18 @@ def export_state_dict(sd: dict, path: str) -> None:
 
 def main(argv=None):
     argv = list(sys.argv[1:] if argv is None else argv)
-    size = 0
-    if len(argv) >= 2 and argv[0] == "--cu":
-        size, argv = int(argv[1]), argv[2:]
+    size, calib = 0, None
+    while len(argv) >= 2 and argv[0] in ("--cu", "--calib"):
+        if argv[0] == "--cu":
+            size = int(argv[1])
+        else:  # int16 [n][2][S][S] .npy of (org, pred) blocks, e.g. collected with hook/dataset_dump from a real encode
+            calib = np.load(argv[1])
+        argv = argv[2:]
     if len(argv) != 2 or size not in (0, 64, 32, 16):
         print(__doc__)
         return 2
     sd = load_checkpoint(argv[0])
-    n = write_cu_blob(sd, size, argv[1]) if size else write_blob(sd, argv[1])
+    n = write_cu_blob(sd, size, argv[1], calib) if size else write_blob(sd, argv[1], calib)
     print(f"wrote {argv[1]}: {n} bytes")
     return 0
 

@@ -169,7 +169,33 @@ def test_cu_staging_edge_cases(ctx):
     want = ref_arch.cu_activations(ref_arch.build_cu_model(sd), ref_arch.stage_numpy(orgpred))[0]
     assert np.abs(got0 - want).max() <= 2e-3 * max(1.0, float(np.abs(want).max()))
     lg = ref_arch.forward_cu_logits(ref_arch.build_cu_model(sd), ref_arch.stage_numpy(orgpred), pocqp)
-    assert np.abs(res["probs"] - softmax_levels(lg)).max() <= 2 * PROB_TOL  # saturated inputs: large activations
+    assert np.abs(res["probs"] - softmax_levels(lg)).max() <= PROB_TOL
+
+
+def test_cu_agreement_at_scale(ctx):
+    """20,480 fresh CUs per size against the fp32 torch oracle (all host cores): max |dprob| <= 1e-3 at every level, and >= 99.9 %
+    agreement of the level-1 decision -- the one the hook takes for cuw < 128 (`elements()[0]`, EncCu.cpp:916-919).  The deeper levels
+    (3 / 4 / 6 classes on 4x4 .. 1x1 maps) are reported; their disagreements must all be fp32 ties."""
+    import torch
+
+    size, sd, p = ctx
+    torch.set_num_threads(len(os.sched_getaffinity(0)))
+    n = 20480
+    cus, pq = ref_arch.synth_cus(n, size, 31337)
+    res = np.concatenate([p.predict_batch_dense(cus[i : i + p.max_batch], pq[i : i + p.max_batch]) for i in range(0, n, p.max_batch)])
+    lg = ref_arch.forward_cu_logits(ref_arch.build_cu_model(sd), ref_arch.stage_numpy(cus), pq)
+    dp = float(np.abs(res["probs"] - softmax_levels(lg)).max())
+    flips, worst = [], 0.0
+    for l, (a, b) in enumerate(LEVELS):
+        bad = np.nonzero(res["split"][:, l] != lg[:, a:b].argmax(1))[0]
+        flips.append(len(bad))
+        if len(bad):
+            srt = np.sort(lg[bad, a:b], 1)
+            worst = max(worst, float((srt[:, -1] - srt[:, -2]).max()))
+    print(f"size {size}: n={n} max|dprob|={dp:.3e} flips per level {flips} (level 1 agreement {1 - flips[0] / n:.5f}), largest fp32 margin among flips {worst:.2e}")
+    assert dp <= PROB_TOL
+    assert 1 - flips[0] / n >= 0.999
+    assert worst < 8e-3, "a disagreement away from a numerical tie"
 
 
 def test_cu_error_paths(ctx):

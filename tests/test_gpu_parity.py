@@ -222,7 +222,7 @@ def test_agreement_on_larger_sample(pred, oracle):
     assert dp <= PROB_TOL
     bad = res["split_l3"] != sp
     assert np.all(margin[bad] < 2e-3), "a disagreement away from a numerical tie"
-    assert agree >= 0.99
+    assert agree >= 0.999
     assert set(sp.tolist()) == {0, 1, 2, 3}
 
 
@@ -245,6 +245,77 @@ def test_agreement_2048_ctus_vs_fp32_oracle(blob, oracle):
     assert dp <= PROB_TOL
     assert agree[2] >= 0.999 and min(agree) >= 0.998
     assert np.all(margin[bad] < 2e-3), "a disagreement away from a numerical tie"
+
+
+def test_agreement_at_scale_20480_ctus(blob, oracle):
+    """The north_star bars where they are tight: 20,480 fresh synthetic CTUs through the product path (tcgen05, fp16 operands) and
+    through the fp32 CUDA-core cross-check engine, itself anchored to the fp32 C oracle on the first 256: max |dprob| <= 1e-3 and
+    >= 99.9 % split-decision agreement at EVERY level; every disagreement is an fp32 tie (top-2 logit margin < 2e-3).  Deterministic:
+    seeded inputs, bit-reproducible kernels -- the same counts on every run of a given build."""
+    from fastintercu_vvc_b200 import MltPredictor
+
+    N, B = 20480, 2048
+    levels = (("split_l1", 0, 2), ("split_l2", 2, 5), ("split_l3", 5, 9))
+    flips = {k: 0 for k, _, _ in levels}
+    max_dp, worst_margin = 0.0, 0.0
+    with MltPredictor(blob, device=0, max_batch=B) as p:
+        for done in range(0, N, B):
+            ctus_, pq = ref_arch.synth_ctus(B, 700000 + done)
+            p.set_engine(0)
+            a = p.predict_batch_dense(ctus_, pq).copy()
+            p.set_engine(1)
+            r = p.predict_batch_dense(ctus_, pq).copy()
+            if done == 0:
+                lg, _ = oracle.predict_batch(ctus_[:256], pq[:256])
+                assert np.abs(r["logits"][:256] - lg).max() < 3e-4  # the comparison engine is the oracle's arithmetic
+            max_dp = max(max_dp, float(np.abs(a["probs"] - r["probs"]).max()))
+            for k, lo, hi in levels:
+                bad = np.nonzero(a[k] != r[k])[0]
+                flips[k] += len(bad)
+                for i in bad:
+                    top2 = np.sort(r["logits"][i, lo:hi])[-2:]
+                    worst_margin = max(worst_margin, float(top2[1] - top2[0]))
+    agree = {k: 1.0 - v / N for k, v in flips.items()}
+    print(f"n={N}: max|dprob|={max_dp:.3e}, flips L1/L2/L3={flips['split_l1']}/{flips['split_l2']}/{flips['split_l3']}, "
+          f"agreement {agree['split_l1']:.5f}/{agree['split_l2']:.5f}/{agree['split_l3']:.5f}, largest fp32 margin among the flips {worst_margin:.2e}")
+    assert max_dp <= PROB_TOL
+    assert min(agree.values()) >= 0.999
+    assert worst_margin < 2e-3, "a disagreement away from a numerical tie"
+
+
+def test_product_stem_follows_the_uint16_cast_semantics(pred, oracle):
+    """Pel values outside 0..1023 through the PRODUCT stem (stem5_umma.cu stagers, not the staging probe): negative samples become
+    large uint16 values and clamp to 1.0, |org - pred| is taken on the casts (EncCu.cpp:816,827,833,848-867).  Logits and
+    probabilities must follow the oracle, and the stem's two outputs the fp32 engine's, as for in-range CTUs."""
+    rng = np.random.RandomState(17)
+    n = 12
+    orgpred = rng.randint(-300, 1400, (n, 2, 128, 128)).astype(np.int16)
+    orgpred[0] = -1          # every sample casts to 65535
+    orgpred[1, 0] = 1023
+    orgpred[1, 1] = -32768   # |1023 - 32768| clamps
+    orgpred[2, 0] = 1024     # just past the clamp
+    orgpred[2, 1] = 0
+    orgpred[3, 0, :, :64] = 0  # a hard vertical edge through the block at the work-unit boundary
+    pocqp = np.stack([rng.randint(0, 33, n), rng.randint(20, 50, n)], 1).astype(np.int32)
+    res = pred.predict_batch_dense(orgpred, pocqp)
+    act1 = pred.debug_activation(1, n)
+    act2 = pred.debug_activation(2, n)  # consumes the stem's conv1 quarter through layer0.0's shortcut
+    lg, sp = oracle.predict_batch(orgpred, pocqp)
+    dp = np.abs(res["probs"] - softmax_levels(lg)).max()
+    pred.set_engine(1)
+    try:
+        pred.predict_batch_dense(orgpred, pocqp)
+        ref1, ref2 = pred.debug_activation(1, n), pred.debug_activation(2, n)
+    finally:
+        pred.set_engine(0)
+    e1 = np.abs(act1 - ref1).max() / np.abs(ref1).max()
+    e2 = np.abs(act2 - ref2).max() / np.abs(ref2).max()
+    print(f"out-of-range Pel through the product stem: act1 {e1:.2e}, act2 {e2:.2e}, max|dprob| {dp:.2e}")
+    assert e1 < 2e-3 and e2 < 2e-3
+    assert dp <= PROB_TOL
+    srt = np.sort(lg[:, 5:9], 1)
+    bad = res["split_l3"] != sp
+    assert np.all((srt[:, -1] - srt[:, -2])[bad] < 2e-3)
 
 
 def test_batch_shapes_and_entry_points_agree(pred, ctus):
