@@ -16,7 +16,7 @@ using namespace mlt;
 namespace {
 
 constexpr uint32_t MLTW_MAGIC = 0x57544C4Du;
-enum : uint32_t { SEC_CONV1_UMMA = 0x002, SEC_STEM_CONV1 = 0x003, SEC_W_F16 = 0x100, SEC_BIAS_FUSED = 0x200, SEC_FC_W = 0x800, SEC_FC_B = 0x900, SEC_BIAS_MMA = 0xA00, SEC_X_W_F16 = 0xB00 };
+enum : uint32_t { SEC_CONV1_UMMA = 0x002, SEC_STEM_CONV1 = 0x003, SEC_STEM5_W = 0x004, SEC_STEM5_CORR = 0x005, SEC_W_F16 = 0x100, SEC_BIAS_FUSED = 0x200, SEC_FC_W = 0x800, SEC_FC_B = 0x900, SEC_BIAS_MMA = 0xA00, SEC_X_W_F16 = 0xB00 };
 constexpr int FC_IN[CU_NHEAD] = {66, 98, 130, 258}, FC_OUT[CU_NHEAD] = {2, 3, 4, 6};
 
 struct Section { const uint8_t *dev = nullptr; size_t bytes = 0; };
@@ -123,7 +123,8 @@ int load_blob(mlt_cu_ctx *c, const char *path)
         c->sec[id].bytes = nb;
     }
     auto need = [&](uint32_t id, size_t bytes) { return c->sec[id].dev != nullptr && c->sec[id].bytes == bytes; };
-    bool ok = need(SEC_CONV1_UMMA, 2 * 4 * 32 * 16) && need(SEC_STEM_CONV1, 4 * 1024);
+    bool ok = need(SEC_CONV1_UMMA, 2 * 4 * 32 * 16) && need(SEC_STEM_CONV1, 4 * 1024) && need(SEC_STEM5_W, 7 * 1024) &&
+              need(SEC_STEM5_CORR, (2 * 5 * 2 * 32 + 2 * 32 + 32) * 4);
     for (int li = 0; li < CU_NCONV && ok; li++) {
         const CuLayerInfo &L = c->info[li];
         ok = need(SEC_W_F16 + li, (size_t)9 * L.cin * L.cout * 2) && need(SEC_BIAS_FUSED + li, (size_t)L.cout * 4) &&
@@ -153,9 +154,13 @@ int run_network(mlt_cu_ctx *c, int n, const int16_t *d_orgpred, const int32_t *d
 {
     cu_dense_descs_kernel<<<(n + 255) / 256, 256, 0, s>>>(c->d_cus, d_orgpred, d_pocqp, n, c->size);
     CU(cudaGetLastError());
-    if (c->fused)
+    static const bool old_stem = getenv("MLT_STEM_OLD") != nullptr; // A/B switch: the round-1 stem (conv1 and layer0.0.conv1 as two MMA stages)
+    if (c->fused && old_stem)
         CU(launch_cu_stem_umma(c->size, c->d_cus, n, secp<__half>(c, SEC_STEM_CONV1), secp<__half>(c, SEC_W_F16 + 0),
                                secp<float>(c, SEC_BIAS_FUSED + 0), c->act0q, c->act[1], c->cap, c->num_sms, s));
+    else if (c->fused) // conv1 o layer0.0.conv1 composed into one 5x5 stride-2 conv (stem5_umma.cu)
+        CU(launch_cu_stem5_umma(c->size, c->d_cus, n, secp<__half>(c, SEC_STEM5_W), secp<float>(c, SEC_STEM5_CORR), secp<float>(c, SEC_STEM5_CORR) + 704,
+                                c->act0q, c->act[1], c->cap, c->num_sms, s));
     else
         CU(launch_cu_conv1(c->size, c->d_cus, n, secp<__half>(c, SEC_CONV1_UMMA), c->act[0], c->cap, s));
     c->launches += 2;
@@ -333,6 +338,7 @@ int mlt_cu_create(mlt_cu_ctx **out, const char *weights_path, int cuda_device, i
         CU(conv_umma_init()); // resolves cuTensorMapEncodeTiled
         CU(cu_conv_init(cu_size));
         CU(stem_umma_init());
+        CU(stem5_umma_init());
         c->fused = cu_size >= 32 && getenv("MLT_CU_UNFUSED") == nullptr; // a 16-px CU is smaller than one stem work unit
         // every activation is ONE strip over the whole batch: [plane][C/8][row][cap images][x][8] fp16
         c->lay[0] = ActLayout{cu_size, 32, 1, 0, c->cap};

@@ -351,6 +351,24 @@ def stem5_operands(w1: np.ndarray, w0f: np.ndarray):
     return op.astype(np.float16), corr
 
 
+def stem5_sections(w1: np.ndarray, w0f: np.ndarray, b0f: np.ndarray, tapmean5: np.ndarray | None):
+    """(SEC_STEM5_W array, SEC_STEM5_CORR array): the operands of stem5_operands + the stem kernel's own bias [32] at the end of
+    the fp32 section, corrected for the fp16 rounding of the composite weights when tap means are given."""
+    s5w, s5c = stem5_operands(w1, w0f)
+    b5 = b0f.astype(np.float64)
+    if tapmean5 is not None:  # the composite weights as the kernel sees them (fp16, without the staging scale) against the exact ones
+        W5 = stem5_composite(w1, w0f)[0]
+        W5q = np.zeros_like(W5)
+        sc = float(ALPHA) * 1024.0
+        for dy in range(5):
+            for ch in range(2):
+                for dx in range(4):
+                    W5q[:, ch, dy, dx] = s5w[dy, 0, :, dx * 2 + ch].astype(np.float64) / sc
+                W5q[:, ch, dy, 4] = s5w[dy, 1, :, ch].astype(np.float64) / sc
+        b5 = b5 - bias_correction(W5, W5q, tapmean5)
+    return s5w, np.concatenate([s5c, b5.astype(np.float32)])
+
+
 def extra_operand_hilo(ws: np.ndarray, gx: int) -> np.ndarray:
     """[cout][xc] fp32 folded 1x1 shortcut weights -> fp16 [xc/gx][hi, lo][gx/8][cout][8]: hi = fp16(w), lo = fp16(w - hi).
     The conv kernel runs the extra-operand stage twice (ConvCfg::XLO), so the shortcut is applied at ~2^-22 precision."""
@@ -385,20 +403,9 @@ def build_sections(sd: dict, calib: np.ndarray | None = None, correct_bias: bool
     add(SEC_CONV1_UMMA, conv1_operand(w), np.float16)
     add(SEC_STEM_CONV1, stem_conv1_operand(w), np.float16)
     w0f, b0f = fold_bn(sd["layer0.0.conv1.weight"], sd, "layer0.0.bn1")
-    s5w, s5c = stem5_operands(w, w0f)
-    b5 = b0f.astype(np.float64)
-    if tm is not None:  # the composite weights as the kernel sees them (fp16, without the staging scale) against the exact ones
-        W5 = stem5_composite(w, w0f)[0]
-        W5q = np.zeros_like(W5)
-        sc = float(ALPHA) * 1024.0
-        for dy in range(5):
-            for ch in range(2):
-                for dx in range(4):
-                    W5q[:, ch, dy, dx] = s5w[dy, 0, :, dx * 2 + ch].astype(np.float64) / sc
-                W5q[:, ch, dy, 4] = s5w[dy, 1, :, ch].astype(np.float64) / sc
-        b5 = b5 - bias_correction(W5, W5q, tm["stem5"])
+    s5w, s5c = stem5_sections(w, w0f, b0f, tm["stem5"] if tm is not None else None)
     add(SEC_STEM5_W, s5w, np.float16)
-    add(SEC_STEM5_CORR, np.concatenate([s5c, b5.astype(np.float32)]), np.float32)  # ... + the stem kernel's own (corrected) bias [32]
+    add(SEC_STEM5_CORR, s5c, np.float32)  # border-term weights + the stem kernel's own (corrected) bias [32]
     for li, (prefix, cin, cout, stride, hout, group, sc) in enumerate(conv_table()):
         bn = prefix.replace("conv", "bn")
         wf, bf = fold_bn(sd[f"{prefix}.weight"], sd, bn)
@@ -475,7 +482,11 @@ def build_cu_sections(sd: dict, size: int, calib: np.ndarray | None = None, corr
     w = sd["conv1.weight"].astype(np.float32)  # [32][2][3][3], no BN / bias (mlt_cu_or_pq_arch.py:105)
     add(SEC_CONV1_F32, w.transpose(2, 3, 1, 0).reshape(9, 2, 32), np.float32)
     add(SEC_CONV1_UMMA, conv1_operand(w), np.float16)
-    add(SEC_STEM_CONV1, stem_conv1_operand(w), np.float16)  # the 64- / 32-px networks run the fused stem (csrc/stem_umma.cu)
+    add(SEC_STEM_CONV1, stem_conv1_operand(w), np.float16)  # round-1 fused stem (csrc/stem_umma.cu; MLT_STEM_OLD=1)
+    w0f, b0f = fold_bn(sd["layer0.0.conv1.weight"], sd, "layer0.0.bn1")
+    s5w, s5c = stem5_sections(w, w0f, b0f, tm["stem5"] if tm is not None else None)  # the 64- / 32-px networks run csrc/stem5_umma.cu
+    add(SEC_STEM5_W, s5w, np.float16)
+    add(SEC_STEM5_CORR, s5c, np.float32)
     for li, (prefix, cin, cout, stride, hout, group, xc, gx, kind) in enumerate(cu_conv_table(size)):
         wf, bf = fold_bn(sd[f"{prefix}.weight"], sd, prefix.replace("conv", "bn"))
         assert wf.shape == (cout, cin, 3, 3), (prefix, wf.shape)
