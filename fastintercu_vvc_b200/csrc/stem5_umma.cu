@@ -29,7 +29,7 @@ namespace mlt {
 namespace stem5 {
 constexpr int NEPI = 8;
 constexpr int W_EPI = 0, W_MMA = NEPI, W_STG = NEPI + 1;
-constexpr int NTHREADS = (NEPI + 1 + 4) * 32;              // 416
+__host__ __device__ constexpr int nthreads(int nstg) { return (NEPI + 1 + nstg) * 32; } // 416 with 4 stager warps
 constexpr int PE = 18, EP_ROWS = 18;
 constexpr int EP_ARR = EP_ROWS * PE * 16;                  // one (col parity, row parity) array: 324 entries
 constexpr int EP_BYTES = 4 * EP_ARR;                       // 20,736
@@ -53,6 +53,8 @@ static_assert(OFF_W % 128 == 0 && OFF_CORRW % 16 == 0 && OFF_CORR % 16 == 0 && O
 static_assert(2 * SMEM_BYTES <= 227 * 1024, "two CTAs per SM");
 } // namespace stem5
 
+constexpr int STEM5_DEFAULT_STAGERS = 4;
+
 struct Stem5Params {
     const CtuDev *ctus;
     const __half *w;     // SEC_STEM5_W  [7][2][32][8]
@@ -62,14 +64,16 @@ struct Stem5Params {
     __half *act1;        // layer0.0.conv1 output
     int n;
     int cap;             // strip layouts (S < 128): images per strip
+    int dbg;             // MLT_STEM5_DBG (timing experiments only, results invalid): 1 no global stores, 2 no global loads, 4 no EP gather
 };
 
 __device__ __forceinline__ uint32_t s5_absdiff16(uint32_t o, uint32_t p) { return o > p ? o - p : p - o; } // cv::absdiff, CV_16U
 
-template <int S>
-__global__ void __launch_bounds__(stem5::NTHREADS, 2) stem5_umma_kernel(const Stem5Params p)
+template <int S, int NSTG>
+__global__ void __launch_bounds__(stem5::nthreads(NSTG), 2) stem5_umma_kernel(const Stem5Params p)
 {
     using namespace stem5;
+    constexpr int NTHREADS = nthreads(NSTG), STG_THREADS = NSTG * 32;
     constexpr int OH = S / 2, UW = S / 32, UPI = UW * UW; // output map size; work units per row / per block
     auto out_off = [&](int b, int oy, int ox) -> size_t {
         return S == 128 ? (size_t)b * (4 * OH * OH * 8) + (size_t)(oy * OH + ox) * 8 : ((size_t)(oy * p.cap + b) * OH + ox) * 8;
@@ -85,9 +89,9 @@ __global__ void __launch_bounds__(stem5::NTHREADS, 2) stem5_umma_kernel(const St
 
     if (tid == 0) {
         for (int i = 0; i < 2; i++) {
-            mbar_init(&ep_full[i], 4); mbar_init(&ep_empty[i], 1);
+            mbar_init(&ep_full[i], NSTG); mbar_init(&ep_empty[i], 1);
             mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], NEPI);
-            mbar_init(&corr_full[i], 4);
+            mbar_init(&corr_full[i], NSTG);
         }
         mbar_fence_init();
     }
@@ -108,15 +112,16 @@ __global__ void __launch_bounds__(stem5::NTHREADS, 2) stem5_umma_kernel(const St
 
     if (warp >= W_STG) {
         // ======================= stagers: int16 window -> fp16 {org, res} plane H -> expanded, parity-split operand EP (+ border terms)
-        const int st = tid - W_STG * 32; // 0..127
+        const int st = tid - W_STG * 32; // 0 .. STG_THREADS - 1
         uint32_t *H = reinterpret_cast<uint32_t *>(smem + OFF_RAW);
         constexpr int NV = RAW_ROWS * 6;          // 210 (row, 8-sample vector) pairs of the window
         constexpr int NE = 4 * EP_ROWS * PE;      // 1296 entry slots
-        constexpr int EPT = (NE + 127) / 128;     // entry slots per thread
+        constexpr int EPT = (NE + STG_THREADS - 1) / STG_THREADS; // entry slots per thread
+        constexpr int VPT = (NV + STG_THREADS - 1) / STG_THREADS; // window vectors per thread
         int src[EPT];                             // H index of the entry's first sample, or -1 (never read with non-zero weights)
 #pragma unroll
         for (int k = 0; k < EPT; k++) {
-            const int e = st + k * 128;
+            const int e = st + k * STG_THREADS;
             src[k] = -1;
             if (e < NE) {
                 const int arr = e / (EP_ROWS * PE), rem = e % (EP_ROWS * PE), ri = rem / PE, xj = rem % PE;
@@ -126,32 +131,32 @@ __global__ void __launch_bounds__(stem5::NTHREADS, 2) stem5_umma_kernel(const St
                 if (used && t < RAW_ROWS) src[k] = t * RAW_COLS + sc + 6; // first sample X = 2*ox0 - 2 + sc  <->  H column sc + 6
             }
         }
-        auto load_window = [&](int u, uint4 (&vo)[2], uint4 (&vp)[2]) {
+        auto load_window = [&](int u, uint4 (&vo)[VPT], uint4 (&vp)[VPT]) {
             // rows Y = 2*oy0 - 2 + t (t < 35), columns X = 2*ox0 - 8 + c (c < 48); outside the block = zero padding
             const int ctu = u / UPI, oy0 = ((u % UPI) / UW) * 16, ox0 = ((u % UPI) % UW) * 16;
             const CtuDev d = p.ctus[ctu];
 #pragma unroll
-            for (int k = 0; k < 2; k++) {
-                const int i = st + k * 128, t = i / 6, vx = i % 6;
+            for (int k = 0; k < VPT; k++) {
+                const int i = st + k * STG_THREADS, t = i / 6, vx = i % 6;
                 const int Y = 2 * oy0 - 2 + t, X = 2 * ox0 - 8 + vx * 8;
                 vo[k] = vp[k] = make_uint4(0, 0, 0, 0);
-                if (i < NV && Y >= 0 && Y < S && X >= 0 && X < S) {
+                if (i < NV && Y >= 0 && Y < S && X >= 0 && X < S && !(p.dbg & 2)) {
                     vo[k] = __ldg(reinterpret_cast<const uint4 *>(d.org + (size_t)Y * d.org_stride + X));
                     vp[k] = __ldg(reinterpret_cast<const uint4 *>(d.pred + (size_t)Y * d.pred_stride + X));
                 }
             }
         };
-        uint4 vo[2], vp[2];
+        uint4 vo[VPT], vp[VPT];
         if ((int)blockIdx.x < total_units) load_window(blockIdx.x, vo, vp);
         const float *cw = reinterpret_cast<const float *>(smem + OFF_CORRW);
         uint32_t ul = 0;
         for (int u = blockIdx.x; u < total_units; u += gridDim.x, ul++) {
             const int oy0 = ((u % UPI) / UW) * 16, ox0 = ((u % UPI) % UW) * 16;
-            asm volatile("bar.sync 1, 128;" ::: "memory"); // every stager is done reading the previous unit's H
+            asm volatile("bar.sync 1, %0;" ::"n"(STG_THREADS) : "memory"); // every stager is done reading the previous unit's H
 #pragma unroll
-            for (int k = 0; k < 2; k++) {
-                const int i = st + k * 128;
-                if (i < NV) {
+            for (int k = 0; k < VPT; k++) {
+                const int i = st + k * STG_THREADS;
+                if (i < NV && !(p.dbg & 32)) {
                     const uint32_t ow[4] = {vo[k].x, vo[k].y, vo[k].z, vo[k].w}, pw[4] = {vp[k].x, vp[k].y, vp[k].z, vp[k].w};
                     uint32_t hv[8];
 #pragma unroll
@@ -168,22 +173,22 @@ __global__ void __launch_bounds__(stem5::NTHREADS, 2) stem5_umma_kernel(const St
                     dst[1] = make_uint4(hv[4], hv[5], hv[6], hv[7]);
                 }
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(STG_THREADS) : "memory");
             if (u + (int)gridDim.x < total_units) load_window(u + gridDim.x, vo, vp); // prefetch: lands while we gather
             const uint32_t buf = ul & 1;
             mbar_wait(&ep_empty[buf], ((ul >> 1) & 1) ^ 1);
             uint8_t *ep = smem + OFF_EP + buf * EP_BYTES;
 #pragma unroll
             for (int k = 0; k < EPT; k++) {
-                if (src[k] >= 0) {
+                if (src[k] >= 0 && !(p.dbg & 4)) {
                     const uint2 *hp = reinterpret_cast<const uint2 *>(H + (src[k] & ~1));
                     const uint2 w0 = hp[0], w1 = hp[1], w2 = hp[2];
                     const bool odd = src[k] & 1;
-                    *reinterpret_cast<uint4 *>(ep + (size_t)(st + k * 128) * 16) =
+                    *reinterpret_cast<uint4 *>(ep + (size_t)(st + k * STG_THREADS) * 16) =
                         odd ? make_uint4(w0.y, w1.x, w1.y, w2.x) : make_uint4(w0.x, w0.y, w1.x, w1.y);
                 }
             }
-            if (oy0 == 0 || ox0 == 0) {
+            if ((oy0 == 0 || ox0 == 0) && st < 128) {
                 // border terms (see the header): slot ps < 16 = output (0, ox0 + ps), top; ps >= 16 = output (oy0 + ps - 16, 0), left;
                 // the epilogue of the unit that used this buffer two units ago must be done with it
                 mbar_wait(&d_empty[buf], ((ul >> 1) & 1) ^ 1);
@@ -231,7 +236,7 @@ __global__ void __launch_bounds__(stem5::NTHREADS, 2) stem5_umma_kernel(const St
             if (elect_one_sync()) {
                 const uint32_t ep = sEP + buf * EP_BYTES;
 #pragma unroll
-                for (int half = 0; half < 2; half++) { // left / right 8 output columns
+                for (int half = 0; half < ((p.dbg & 8) ? 0 : 2); half++) { // left / right 8 output columns
                     const uint32_t d5 = tmem + buf * 128 + half * 32, dq = d5 + 64;
 #pragma unroll
                     for (int dy = 0; dy < 5; dy++) {
@@ -245,8 +250,11 @@ __global__ void __launch_bounds__(stem5::NTHREADS, 2) stem5_umma_kernel(const St
                     umma_f16(dq, umma_desc_pack(q0, a_hi), umma_desc_pack(umma_desc_lo(sW + 5 * 1024, 512), b_hi), idesc, 0);
                     umma_f16(dq, umma_desc_pack(q1, a_hi), umma_desc_pack(umma_desc_lo(sW + 6 * 1024, 512), b_hi), idesc, 1);
                 }
-                umma_commit(&d_full[buf]);
-                umma_commit(&ep_empty[buf]);
+                if (p.dbg & 64) { mbar_arrive(&d_full[buf]); mbar_arrive(&ep_empty[buf]); } // timing experiment: plain arrives instead of commits
+                else {
+                    umma_commit(&d_full[buf]);
+                    umma_commit(&ep_empty[buf]);
+                }
             }
             __syncwarp();
         }
@@ -263,6 +271,12 @@ __global__ void __launch_bounds__(stem5::NTHREADS, 2) stem5_umma_kernel(const St
             tc_fence_after();
             const uint32_t tbase = tmem + ((uint32_t)(wq * 32) << 16) + buf * 128 + half * 32;
             uint32_t v[32];
+            if (p.dbg & 16) { // timing experiment: no TMEM reads, no math, no stores
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&d_empty[buf]);
+                continue;
+            }
             tmem_ld32(tbase, v);
             tmem_ld_wait();
             const float *ct = reinterpret_cast<const float *>(smem + OFF_CORR + buf * CORR_BYTES) + j * 32;
@@ -288,7 +302,7 @@ __global__ void __launch_bounds__(stem5::NTHREADS, 2) stem5_umma_kernel(const St
                     __half2 *h2 = reinterpret_cast<__half2 *>(&ov);
 #pragma unroll
                     for (int k = 0; k < 4; k++) h2[k] = __hmax2(__floats2half2_rn(x[2 * k], x[2 * k + 1]), zero2);
-                    *reinterpret_cast<uint4 *>(op + (size_t)q * out_chunk) = ov;
+                    if (!(p.dbg & 1)) *reinterpret_cast<uint4 *>(op + (size_t)q * out_chunk) = ov;
                 }
             }
             tmem_ld32(tbase + 64, v);
@@ -301,7 +315,7 @@ __global__ void __launch_bounds__(stem5::NTHREADS, 2) stem5_umma_kernel(const St
                     __half2 *h2 = reinterpret_cast<__half2 *>(&ov);
 #pragma unroll
                     for (int k = 0; k < 4; k++) h2[k] = __floats2half2_rn(__uint_as_float(v[q * 8 + 2 * k]), __uint_as_float(v[q * 8 + 2 * k + 1]));
-                    *reinterpret_cast<uint4 *>(op + (size_t)q * out_chunk) = ov;
+                    if (!(p.dbg & 1)) *reinterpret_cast<uint4 *>(op + (size_t)q * out_chunk) = ov;
                 }
             }
             tc_fence_before();
@@ -318,11 +332,42 @@ __global__ void __launch_bounds__(stem5::NTHREADS, 2) stem5_umma_kernel(const St
     }
 }
 
+static int stem5_dbg()
+{
+    static const int v = getenv("MLT_STEM5_DBG") ? atoi(getenv("MLT_STEM5_DBG")) : 0;
+    return v;
+}
+
+static int stem5_nstg()
+{
+    static const int v = getenv("MLT_STEM5_STAGERS") ? atoi(getenv("MLT_STEM5_STAGERS")) : STEM5_DEFAULT_STAGERS; // measurement override: 4 / 6 / 8
+    return v == 4 || v == 6 || v == 8 ? v : STEM5_DEFAULT_STAGERS;
+}
+
+template <int S>
+static cudaError_t stem5_launch(const Stem5Params &p, int grid, cudaStream_t s)
+{
+    switch (stem5_nstg()) {
+    case 4: return launch_pdl(stem5_umma_kernel<S, 4>, dim3(grid), dim3(stem5::nthreads(4)), stem5::SMEM_BYTES, s, p);
+    case 6: return launch_pdl(stem5_umma_kernel<S, 6>, dim3(grid), dim3(stem5::nthreads(6)), stem5::SMEM_BYTES, s, p);
+    default: return launch_pdl(stem5_umma_kernel<S, 8>, dim3(grid), dim3(stem5::nthreads(8)), stem5::SMEM_BYTES, s, p);
+    }
+}
+
+template <int S>
+static cudaError_t stem5_attr()
+{
+    cudaError_t e = cudaFuncSetAttribute(stem5_umma_kernel<S, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, stem5::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(stem5_umma_kernel<S, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, stem5::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(stem5_umma_kernel<S, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, stem5::SMEM_BYTES);
+    return e;
+}
+
 cudaError_t stem5_umma_init()
 {
-    cudaError_t e = cudaFuncSetAttribute(stem5_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, stem5::SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(stem5_umma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, stem5::SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(stem5_umma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, stem5::SMEM_BYTES);
+    cudaError_t e = stem5_attr<128>();
+    if (e == cudaSuccess) e = stem5_attr<64>();
+    if (e == cudaSuccess) e = stem5_attr<32>();
     return e;
 }
 
@@ -337,8 +382,8 @@ cudaError_t launch_stem5_umma(const CtuDev *ctus, int n, const __half *w, const 
                               int num_sms, cudaStream_t s)
 {
     if (n <= 0) return cudaSuccess;
-    Stem5Params p{ctus, w, corrw, bias, act0q, act1, n, 0};
-    return launch_pdl(stem5_umma_kernel<128>, dim3(stem5_grid(n * 16, num_sms)), dim3(stem5::NTHREADS), stem5::SMEM_BYTES, s, p);
+    Stem5Params p{ctus, w, corrw, bias, act0q, act1, n, 0, stem5_dbg()};
+    return stem5_launch<128>(p, stem5_grid(n * 16, num_sms), s);
 }
 
 // the same stem for a 64- or 32-px CU network: act0q / act1 are strips of `cap` images (S/2 x S/2 x 32, not parity-planar)
@@ -346,10 +391,10 @@ cudaError_t launch_cu_stem5_umma(int size, const CtuDev *cus, int n, const __hal
                                  __half *act1, int cap, int num_sms, cudaStream_t s)
 {
     if (n <= 0) return cudaSuccess;
-    Stem5Params p{cus, w, corrw, bias, act0q, act1, n, cap};
-    const dim3 grid(stem5_grid(n * (size / 32) * (size / 32), num_sms)), block(stem5::NTHREADS);
-    if (size == 64) return launch_pdl(stem5_umma_kernel<64>, grid, block, stem5::SMEM_BYTES, s, p);
-    if (size == 32) return launch_pdl(stem5_umma_kernel<32>, grid, block, stem5::SMEM_BYTES, s, p);
+    Stem5Params p{cus, w, corrw, bias, act0q, act1, n, cap, stem5_dbg()};
+    const int grid = stem5_grid(n * (size / 32) * (size / 32), num_sms);
+    if (size == 64) return stem5_launch<64>(p, grid, s);
+    if (size == 32) return stem5_launch<32>(p, grid, s);
     return cudaErrorInvalidValue;
 }
 
