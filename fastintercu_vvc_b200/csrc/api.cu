@@ -18,7 +18,8 @@ constexpr uint32_t MLTW_MAGIC = 0x57544C4Du;
 enum : uint32_t {
     SEC_CONV1_F32 = 0x001, SEC_CONV1_UMMA = 0x002, SEC_STEM_CONV1 = 0x003, SEC_STEM5_W = 0x004, SEC_STEM5_CORR = 0x005, SEC_W_F16 = 0x100, SEC_BIAS_FUSED = 0x200, SEC_W_F32 = 0x300, SEC_BIAS = 0x400,
     SEC_SC_W_F16 = 0x500, SEC_SC_W_F32 = 0x600, SEC_SC_BIAS = 0x700, SEC_FC_W = 0x800, SEC_FC_B = 0x900, SEC_BIAS_MMA = 0xA00, SEC_X_W_F16 = 0xB00,
-    SEC_W_SPLIT = 0xC00, SEC_X_SPLIT = 0xD00 // layer3 weights packed for the channel-split kernels
+    SEC_W_SPLIT = 0xC00, SEC_X_SPLIT = 0xD00, // layer3 (4 ways) and layer2 (4 ways) weights packed for the channel-split kernels
+    SEC_W_SPLIT8 = 0xE00, SEC_X_SPLIT8 = 0xF00 // layer3 split 8 ways
 };
 
 constexpr int NCONV = 16, NACT = 17, CTU = MLT_CTU_SIZE;
@@ -71,7 +72,8 @@ struct mlt_ctx {
         __half *act_h[NACT] = {}; // [0] (conv1's full output, parity-planar) exists only for the unfused engine / debug reads
         __half *act0q = nullptr;  // conv1's output at even rows / columns (input of layer0.0's shortcut), dense [n][4][64][64][8]
         ConvParams conv_p[NCONV]; // tensor maps + weight pointers of every tcgen05 conv, built once at create
-        ConvParams conv_split[NCONV]; // layer3 again for the channel-split kernels (small batches): split-packed weights
+        ConvParams conv_split[NCONV]; // layer3 (and layer2) again for the channel-split kernels (small batches): split-packed weights, 4 ways
+        ConvParams conv_split8[NCONV]; // layer3 split 8 ways (tiny batches)
         float *gap_part[3] = {};  // pool partial sums written by convs 7 / 11 / 15: [cap][8 | 2 | 1 tiles][4][64 | 128 | 256]
         int cap = 0;              // images
     } set[2];
@@ -181,11 +183,13 @@ int load_blob(mlt_ctx *c, const char *path)
         ok = need(SEC_W_F16 + li, (size_t)9 * L.cin * L.cout * 2) && need(SEC_W_F32 + li, (size_t)9 * L.cin * L.cout * 4) &&
              need(SEC_BIAS + li, (size_t)L.cout * 4) && need(SEC_BIAS_FUSED + li, (size_t)L.cout * 4) &&
              need(SEC_BIAS_MMA + li, (size_t)L.cout * 32);
-        if (ok && li >= CONV_SPLIT_FIRST) ok = need(SEC_W_SPLIT + li, (size_t)9 * L.cin * L.cout * 2);
+        if (ok && li >= CONV_L2SPLIT_FIRST) ok = need(SEC_W_SPLIT + li, (size_t)9 * L.cin * L.cout * 2);
+        if (ok && li >= CONV_SPLIT_FIRST) ok = need(SEC_W_SPLIT8 + li, (size_t)9 * L.cin * L.cout * 2);
         if (ok && (li & 1)) { // second conv of a block: extra operand = shortcut conv (first block) or identity
             const int xc = L.sc >= 0 ? kLayers[li - 1].cin : L.cout;
             ok = need(SEC_X_W_F16 + li, (size_t)xc * L.cout * 2 * (L.sc >= 0 ? 2 : 1)); // shortcut weights: hi + lo
-            if (ok && li >= CONV_SPLIT_FIRST) ok = need(SEC_X_SPLIT + li, (size_t)xc * L.cout * 2 * (L.sc >= 0 ? 2 : 1));
+            if (ok && li >= CONV_L2SPLIT_FIRST) ok = need(SEC_X_SPLIT + li, (size_t)xc * L.cout * 2 * (L.sc >= 0 ? 2 : 1));
+            if (ok && li >= CONV_SPLIT_FIRST) ok = need(SEC_X_SPLIT8 + li, (size_t)xc * L.cout * 2 * (L.sc >= 0 ? 2 : 1));
         }
         if (ok && L.sc >= 0) {
             const int csc = kLayers[li - 1].cin;
@@ -287,6 +291,44 @@ int run_network(mlt_ctx *c, const CtuDev *ctus, int n, mlt_result *out, cudaStre
             CU(cudaMemcpy2DAsync(S.act0q, q, S.act_h[0], 4 * q, q, n, cudaMemcpyDeviceToDevice, s));
             if (prof) CU(cudaEventRecord(c->prof_ev[ev++], s));
         }
+        // MLT_CHAIN=1 (experiment, off by default): for one or two CTUs run convs 1..15 as ONE cluster kernel -- cluster barriers instead
+        // of 15 kernel boundaries.  Per-tile arithmetic is the per-layer kernels' own, so results are bit-identical (GPU test); measured
+        // on B200 it is NOT faster (151 vs 139 us per call): PDL already overlaps each kernel's prologue and weight fetch with its
+        // predecessor, the chain serialises them, and layer3 is bound by the ~27 GB/s one SM's bulk copies reach (profiles/r02/README.md)
+        static const bool use_chain = getenv("MLT_CHAIN") != nullptr && getenv("MLT_NO_CHAIN") == nullptr;
+        if (first == 1 && n <= CHAIN_MAX_IMAGES && !prof && use_chain && !getenv("MLT_TRACE_LAYER")) {
+            ChainParams cp;
+            for (int li = 1; li < NCONV; li++) {
+                cp.p[li - 1] = li >= CONV_SPLIT_FIRST ? S.conv_split8[li] : (li >= CONV_L2SPLIT_FIRST ? S.conv_split[li] : S.conv_p[li]);
+                cp.p[li - 1].nimg = n;
+            }
+            static const bool chain_trace = getenv("MLT_CHAIN_TRACE") != nullptr; // debug: per-layer %globaltimer stamps of CTA 0 -> stderr
+            static unsigned long long *d_ct = nullptr;
+            if (chain_trace && !d_ct) CU(cudaMalloc(&d_ct, 64 * sizeof(unsigned long long)));
+            cp.trace = chain_trace ? d_ct : nullptr;
+            static const int chain_trace_layer = getenv("MLT_CHAIN_TRACE_LAYER") ? atoi(getenv("MLT_CHAIN_TRACE_LAYER")) : -1; // 1..15: stamps inside that conv
+            if (chain_trace && chain_trace_layer >= 1 && chain_trace_layer < NCONV) {
+                CU(cudaMemsetAsync(d_ct + 32, 0, 16 * sizeof(unsigned long long), s));
+                cp.p[chain_trace_layer - 1].trace = reinterpret_cast<long long *>(d_ct + 32);
+            }
+            CU(launch_conv_chain(cp, s));
+            c->launches++;
+            first = NCONV;
+            if (chain_trace) {
+                unsigned long long h[31];
+                CU(cudaStreamSynchronize(s));
+                CU(cudaMemcpy(h, d_ct, sizeof h, cudaMemcpyDeviceToHost));
+                fprintf(stderr, "chain trace (ns; layer / barrier):");
+                for (int k = 1; k < 31; k++) fprintf(stderr, " %llu%s", h[k] - h[k - 1], (k & 1) ? "/" : "");
+                fprintf(stderr, "  total %llu\n", h[30] - h[0]);
+                if (chain_trace_layer >= 1) {
+                    unsigned long long g[8];
+                    CU(cudaMemcpy(g, d_ct + 32, sizeof g, cudaMemcpyDeviceToHost));
+                    fprintf(stderr, "conv %d stamps (ns since layer entry): init %llu | first A box %llu | first B slot %llu | last commit %llu | acc ready %llu | stored %llu\n",
+                            chain_trace_layer, g[1] - g[0], g[2] - g[0], g[3] - g[0], g[4] - g[0], g[5] - g[0], g[6] - g[0]);
+                }
+            }
+        }
         for (int li = first; li < NCONV; li++) {
             ConvParams &p = S.conv_p[li];
             p.nimg = n;
@@ -300,7 +342,18 @@ int run_network(mlt_ctx *c, const CtuDev *ctus, int n, mlt_result *out, cudaStre
             // layer3 on a small batch (fewer tiles than half the SMs): 256 output channels split over 4 CTAs per tile
             static const bool no_split = getenv("MLT_NO_SPLIT") != nullptr; // A/B switch for measurements
             const bool split = li >= CONV_SPLIT_FIRST && !no_split && (n + 1) / 2 * 2 <= c->num_sms && li != trace_layer;
-            if (split) {
+            // tiny batches: layer3 8 ways / layer2 4 ways while the items still fit one wave
+            const bool split8 = split && (n + 1) / 2 * CONV_SPLIT8_WAYS <= c->num_sms;
+            const bool split_l2 = li >= CONV_L2SPLIT_FIRST && li < CONV_SPLIT_FIRST && !no_split && 2 * n * CONV_L2SPLIT_WAYS <= c->num_sms / 2 && li != trace_layer;
+            if (split8) {
+                ConvParams &q = S.conv_split8[li];
+                q.nimg = n;
+                CU(launch_conv_umma(li + CONV_SPLIT8_OFFSET, q, c->num_sms, s));
+            } else if (split_l2) {
+                ConvParams &q = S.conv_split[li];
+                q.nimg = n;
+                CU(launch_conv_umma(li + CONV_L2SPLIT_OFFSET, q, c->num_sms, s));
+            } else if (split) {
                 ConvParams &q = S.conv_split[li];
                 q.nimg = n;
                 CU(launch_conv_umma(li + CONV_SPLIT_OFFSET, q, c->num_sms, s));
@@ -617,10 +670,15 @@ int mlt_create_ex(mlt_ctx **out, const char *weights_path, int cuda_device, int 
                 p.relu = 1;
                 p.dbg = getenv("MLT_DEBUG_FLAGS") ? atoi(getenv("MLT_DEBUG_FLAGS")) : 0;
                 p.reverse = getenv("MLT_NO_REVERSE") ? 0 : (li & 1); // the stem walks the images upwards, conv 1 downwards, conv 2 upwards, ...
-                if (li >= CONV_SPLIT_FIRST) {
+                if (li >= CONV_L2SPLIT_FIRST) {
                     S.conv_split[li] = p;
                     S.conv_split[li].w = secp<__half>(c, SEC_W_SPLIT + li);
                     S.conv_split[li].x_w = conv2 ? secp<__half>(c, SEC_X_SPLIT + li) : nullptr;
+                }
+                if (li >= CONV_SPLIT_FIRST) {
+                    S.conv_split8[li] = p;
+                    S.conv_split8[li].w = secp<__half>(c, SEC_W_SPLIT8 + li);
+                    S.conv_split8[li].x_w = conv2 ? secp<__half>(c, SEC_X_SPLIT8 + li) : nullptr;
                 }
             }
         }

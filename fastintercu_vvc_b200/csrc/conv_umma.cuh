@@ -96,7 +96,7 @@ struct ConvCfg {
     static constexpr int X_SLAB_BYTES = GX * NC * 2;
     static constexpr int W_MAIN_BYTES = NCG * 9 * SLAB_BYTES;
     static constexpr int W_X_BYTES = XC * NC * 2 * XP;
-    static constexpr bool RESIDENT = (W_MAIN_BYTES + W_X_BYTES) <= 84 * 1024 && !FLAT; // (FLAT: several cin groups -> streamed path)
+    static constexpr bool RESIDENT = (W_MAIN_BYTES + W_X_BYTES) <= 84 * 1024 && !FLAT && NSPLIT == 1; // (FLAT / channel split: streamed path)
     // weight-slab ring: deep enough that ring depth x MMA time per slab covers the ~2500-cycle L2 -> smem latency of a
     // bulk copy (one slab feeds G/16 MMAs of max(N/2, 32 + N/4) cycles), leaving room for >= MIN_NAS activation stages
     // streamed weights: the activation ring holds exactly two passes' worth of one step (MIN_NAS = 4: one stage per tile
@@ -104,10 +104,24 @@ struct ConvCfg {
     // slab must cover the L2 -> smem latency of a bulk copy
     static constexpr int TP = RESIDENT ? 1 : 2;     // tiles per pass: streamed weight slabs are shared by a pair of tiles
     static constexpr int MIN_NAS = 4;
-    static constexpr int NBS_MAX = (231000 - MIN_NAS * A_STAGE_BYTES - COUT * 32 - 4096) / SLAB_BYTES;
-    static constexpr int NBS = RESIDENT ? 0 : (NBS_MAX > 12 ? 12 : NBS_MAX);
-    static_assert(RESIDENT || NBS >= 3, "weight ring too shallow");
-    static constexpr int B_BYTES = RESIDENT ? (W_MAIN_BYTES + W_X_BYTES) : NBS * SLAB_BYTES;
+    // taps per ring slot: channel-split layers (tiny batches, one pass per CTA) take all nine taps of a cin group as ONE slot -- one
+    // bulk copy and one wait / commit per 9 * G / 16 MMAs.  With a slot per tap the issue loop itself (wait, fence, elect, 2 MMAs, commit:
+    // ~100 ns per iteration, 80 iterations per layer3 conv) was the whole 13-20 us of a layer3 conv on one CTU, whatever the split.
+    static constexpr int TPS = (NSPLIT > 1 && !CENTER_ONLY) ? NTAPS : 1;
+    static constexpr int RSLOT_BYTES = TPS * SLAB_BYTES;
+    // ... and they reserve activation stages for (up to 8 of) the TMA boxes of a whole pass before the weight ring takes the rest: with
+    // one pass per CTA both streams are bound by round trips to L2 (~1.5 us each), i.e. by how much of the pass is in flight at once
+    static constexpr int A_WANT = (NCG + NXS) * (HILO_IN ? 2 : 1) < 8 ? (NCG + NXS) * (HILO_IN ? 2 : 1) : 8;
+    static constexpr int A_FIT = 96 * 1024 / A_STAGE_BYTES; // ... within 96 KB
+    static constexpr int A_RESERVE = NSPLIT > 1 ? (A_WANT < A_FIT ? A_WANT : (A_FIT > MIN_NAS ? A_FIT : MIN_NAS)) : MIN_NAS;
+    static constexpr int NBS_MAX = (231000 - (A_RESERVE > MIN_NAS ? A_RESERVE : MIN_NAS) * A_STAGE_BYTES - COUT * 32 - 4096) / RSLOT_BYTES;
+    // channel-split layers serve tiny batches (one pass per CTA): a 12-slab ring makes their weight stream latency-bound (measured on
+    // one CTU: 13-18 us per layer3 conv, ~18 GB/s per CTA) -- there the ring takes every slab of a pass, so all copies are in flight at once
+    static constexpr int PASS_SLABS = NCG * (NTAPS / TPS) + NXS * XP; // ring slots one pass consumes
+    static constexpr int NBS = RESIDENT ? 0 : (NSPLIT > 1 ? (NBS_MAX > PASS_SLABS ? PASS_SLABS : NBS_MAX) : (NBS_MAX > 12 ? 12 : NBS_MAX));
+    static_assert(RESIDENT || NBS >= 3 || NBS >= PASS_SLABS, "weight ring too shallow");
+    static constexpr int B_BYTES = RESIDENT ? (W_MAIN_BYTES + W_X_BYTES) : NBS * RSLOT_BYTES;
+    static_assert(X_SLAB_BYTES <= RSLOT_BYTES, "extra-operand slabs share the ring slots");
     static constexpr int BIAS_BYTES = COUT * 32;    // bias as a K=16 B operand
     static constexpr int ONES_BYTES = 2 * 128 * 16; // matching A operand: k=0,1 -> 1.0, rest 0
     static constexpr int A_BUDGET = 231000 - B_BYTES - BIAS_BYTES - ONES_BYTES;
@@ -166,6 +180,16 @@ struct ConvCfg {
     __host__ __device__ static int num_tiles(int nimg) { return ((NB != 1 || FLAT) ? (nimg + NB - 1) / NB : nimg * TILES_PER_IMG) * NSPLIT; } // work items
 };
 
+// MLT_CHAIN_TRACE debug: %globaltimer stamp k of this layer, written by CTA 0 only (chain mode, p.trace != nullptr)
+__device__ __forceinline__ void layer_stamp(const ConvParams &p, int bid, int k)
+{
+    if (p.trace != nullptr && bid == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.trace[k] = (long long)t;
+    }
+}
+
 // offset (in 16-byte units) of tap (kh, kw) inside the A stage
 template <class C>
 __device__ __forceinline__ int tap_offset16(int kh, int kw)
@@ -177,10 +201,13 @@ __device__ __forceinline__ int tap_offset16(int kh, int kw)
     return (py * 2 + px) * (C::PLANE_STRIDE / 16) + ro * C::PITCH + co;
 }
 
-template <class C>
-__global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_constant__ ConvParams p)
+// One layer on the tiles bid, bid + nblk, ... of the grid.  CHAIN = false: the body of conv_umma_kernel (one launch per layer: allocates
+// and frees its TMEM, PDL-orders itself against the previous kernel).  CHAIN = true: one step of conv_chain_kernel, which runs the
+// layers of a small batch back to back inside ONE thread-block cluster: TMEM is allocated once by the caller (chain_tmem), the
+// mbarriers are re-initialised per layer and invalidated at its end, and the caller separates the layers by a cluster barrier.
+template <class C, bool CHAIN>
+__device__ __forceinline__ void conv_layer_body(const ConvParams &p, uint8_t *smem, const uint32_t chain_tmem, const int bid, const int nblk)
 {
-    extern __shared__ __align__(128) uint8_t smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::OFF_BAR);
     uint64_t *fullA = bars, *emptyA = bars + C::NAS;
     uint64_t *fullB = bars + 2 * C::NAS;
@@ -190,6 +217,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ntiles = C::num_tiles(p.nimg);
+    if (CHAIN && tid == 0) layer_stamp(p, bid, 0);
 
     if (tid == 0) {
         for (int i = 0; i < C::NAS; i++) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
@@ -203,16 +231,21 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
     for (int i = tid; i < C::ONES_BYTES / 16; i += C::NTHREADS)
         reinterpret_cast<uint4 *>(smem + C::OFF_ONES)[i] = i < 128 ? make_uint4(0x3C003C00u, 0, 0, 0) : make_uint4(0, 0, 0, 0);
     fence_proxy_async_smem();
-    if (warp == C::W_MMA) { tmem_alloc(tmem_slot, C::TMEM_COLS); tmem_relinquish(); }
+    if constexpr (!CHAIN) {
+        if (warp == C::W_MMA) { tmem_alloc(tmem_slot, C::TMEM_COLS); tmem_relinquish(); }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = CHAIN ? chain_tmem : *tmem_slot;
+    if (CHAIN && tid == 0) layer_stamp(p, bid, 1);
     const uint32_t sA = smem_u32(smem + C::OFF_A), sB = smem_u32(smem + C::OFF_B);
     // PDL: let the next kernel of the stream start its prologue; everything that touches activations waits for the
     // previous kernel here -- the weight loader does not (weights are constants), so its copies overlap that tail
-    griddep_launch_dependents();
-    if (warp != C::W_BLOAD) griddep_wait();
+    if constexpr (!CHAIN) {
+        griddep_launch_dependents();
+        if (warp != C::W_BLOAD) griddep_wait();
+    }
 
     if (warp < 8) {
         // ======================= epilogue: TMEM (bias, conv, shortcut / residual all accumulated) -> regs -> ReLU -> fp16
@@ -229,7 +262,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
 #pragma unroll
             for (int j = 0; j < C::COUT; j++) bias_r[j] = __ldg(p.bias_f32 + j);
         }
-        for (int tile = blockIdx.x + grp * gridDim.x; tile < ((C::RESIDENT && (p.dbg & 8)) ? 0 : ntiles); tile += 2 * gridDim.x, acc_it += 2) {
+        for (int tile = bid + grp * nblk; tile < ((C::RESIDENT && (p.dbg & 8)) ? 0 : ntiles); tile += 2 * nblk, acc_it += 2) {
             // p.reverse: this layer walks the images in the opposite direction to the previous one, so that it starts on
             // the activations the previous kernel wrote last (still in the 126 MB L2) -- consecutive layers zig-zag
             const int pitem = p.reverse ? ntiles - 1 - tile : tile;
@@ -254,6 +287,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
             const uint32_t acc = acc_it % C::NACC;
             mbar_wait(&accFull[acc], (acc_it / C::NACC) & 1);
             tc_fence_after();
+            if (CHAIN && tid == 0) layer_stamp(p, bid, 5);
 #pragma unroll(C::BIAS_REG ? 2 : 1)
             for (int c0 = 0; c0 < ((p.dbg & 4) ? 0 : C::NC); c0 += 32) {
                 uint32_t v[32];
@@ -329,6 +363,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
             }
             tc_fence_before();
             mbar_arrive(&accEmpty[acc]);
+            if (CHAIN && tid == 0) layer_stamp(p, bid, 6);
         }
     } else if (warp == C::W_MMA || (C::RESIDENT && warp == C::W_MMA2)) {
         // ======================= MMA issuer: the whole warp runs the (uniform) control flow and the waits,
@@ -360,9 +395,9 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
             // tcgen05.commit tracks the MMAs of the issuing thread, so each tile's barriers see exactly its own MMAs)
             const uint32_t iss = warp == C::W_MMA ? 0u : 1u;
             uint32_t j = iss;
-            for (int tile = blockIdx.x + iss * gridDim.x; tile < ntiles; tile += 2 * gridDim.x, j += 2) {
+            for (int tile = bid + iss * nblk; tile < ntiles; tile += 2 * nblk, j += 2) {
                 wait_tile(j); // each issuer has two tile-times per tile: the wait latency is off the critical path
-                if (p.trace != nullptr && blockIdx.x == 0 && j < 1024 && lane == 0) p.trace[j] = clock64();
+                if (p.trace != nullptr && bid == 0 && j < 1024 && lane == 0) p.trace[j] = clock64();
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (j % C::NACC) * C::ACC_COLS;
                 const uint32_t st0 = iss * C::NAS_HALF + ((j >> 1) * SPT) % C::NAS_HALF;
@@ -406,9 +441,9 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
         } else
         // One pass = TP tiles (a PAIR when the weights are streamed): every weight slab fetched from L2 feeds the MMAs of
         // both tiles, which halves the L2 -> smem weight traffic that otherwise bounds the 128/256-channel layers.
-        for (int tile = blockIdx.x; tile < ntiles; tile += C::TSTEP * gridDim.x) {
+        for (int tile = bid; tile < ntiles; tile += C::TSTEP * nblk) {
             // HILO_IN: the pair is (hi box, lo box) of the SAME tile and both halves feed one accumulator
-            const int np = C::HILO_IN ? 2 : ((C::TP == 2 && tile + (int)gridDim.x < ntiles) ? 2 : 1);
+            const int np = C::HILO_IN ? 2 : ((C::TP == 2 && tile + nblk < ntiles) ? 2 : 1);
             const int nacc = C::HILO_IN ? 1 : np; // accumulators of this pass
             uint32_t d_tmem[C::TP];
 #pragma unroll
@@ -439,6 +474,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
                     if (h < np) {
                         const uint32_t st = (a_it + h) % C::NAS;
                         mbar_wait(&fullA[st], ((a_it + h) / C::NAS) & 1); // TMA complete_tx: data visible to the async proxy
+                        if (CHAIN && lane == 0 && a_it == 0 && h == 0) layer_stamp(p, bid, 2);
                         a_lo0[h] = umma_desc_lo(sA + st * C::A_STAGE_BYTES, C::A_LBO);
                     }
                 }
@@ -461,12 +497,16 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
                     __syncwarp();
                 } else {
 #pragma unroll
-                    for (int tap = C::TAP0; tap < C::TAP0 + C::NTAPS; tap++, b_it++) {
+                    for (int tap = C::TAP0; tap < C::TAP0 + C::NTAPS; tap++) {
+                        const int tslot = (tap - C::TAP0) % C::TPS; // position inside the ring slot
                         const uint32_t bs = b_it % C::NBS;
-                        mbar_wait(&fullB[bs], (b_it / C::NBS) & 1);
-                        tc_fence_after();
+                        if (tslot == 0) {
+                            mbar_wait(&fullB[bs], (b_it / C::NBS) & 1);
+                            tc_fence_after();
+                            if (CHAIN && lane == 0 && b_it == 0) layer_stamp(p, bid, 3);
+                        }
                         if (elect_one_sync()) {
-                            const uint32_t b_lo0 = umma_desc_lo(sB + bs * C::SLAB_BYTES, C::NC * 16);
+                            const uint32_t b_lo0 = umma_desc_lo(sB + bs * C::RSLOT_BYTES + tslot * C::SLAB_BYTES, C::NC * 16);
 #pragma unroll
                             for (int h = 0; h < C::TP; h++) {
                                 if (h < np) {
@@ -478,7 +518,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
                                                  (C::BIAS_REG && tap == C::TAP0 && ks == 0 && !(C::HILO_IN && h == 1)) ? (uint32_t)(cg != 0) : 1u);
                                 }
                             }
-                            umma_commit(&emptyB[bs]);
+                            if (tslot == C::TPS - 1) umma_commit(&emptyB[bs]);
                             if (tap == C::TAP0 + C::NTAPS - 1) {
 #pragma unroll
                                 for (int h = 0; h < C::TP; h++)
@@ -486,6 +526,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
                             }
                         }
                         __syncwarp();
+                        if (tslot == C::TPS - 1) b_it++;
                     }
                 }
             }
@@ -514,7 +555,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
                         }
                         if (elect_one_sync()) {
                             const uint32_t b_lo0 = C::RESIDENT ? umma_desc_lo(sB + C::W_MAIN_BYTES + (xs * C::XP + part) * C::X_SLAB_BYTES, C::COUT * 16)
-                                                               : umma_desc_lo(sB + bs * C::SLAB_BYTES, C::NC * 16);
+                                                               : umma_desc_lo(sB + bs * C::RSLOT_BYTES, C::NC * 16);
 #pragma unroll
                             for (int h = 0; h < C::TP; h++) {
                                 if (h < np) {
@@ -541,6 +582,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
                     if (h < nacc) umma_commit(&accFull[(acc_it + h) % C::NACC]);
             }
             __syncwarp();
+            if (CHAIN && lane == 0) layer_stamp(p, bid, 4);
             acc_it += nacc;
         }
     } else if (warp == C::W_BLOAD) {
@@ -558,23 +600,24 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
             }
         } else {
             uint32_t b_it = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += C::TSTEP * gridDim.x) { // once per pass (pair of tiles)
+            for (int tile = bid; tile < ntiles; tile += C::TSTEP * nblk) { // once per pass (pair of tiles)
                 // channel split: the weights are packed [split][cin_group][tap]... / [split][x slab]...
                 const int split = (p.reverse ? ntiles - 1 - tile : tile) % C::NSPLIT;
                 const uint8_t *gws = gw + (size_t)split * (C::NCG * 9 * C::SLAB_BYTES);
                 const uint8_t *gxs = gx + (size_t)split * (C::NXS * C::XP * C::X_SLAB_BYTES);
+                constexpr int MAIN_SLOTS = C::NCG * (C::NTAPS / C::TPS); // ring slots of the main operand per pass (TPS taps each)
 #pragma unroll 1
-                for (int s = 0; s < C::NCG * C::NTAPS + C::NXS * C::XP; s++, b_it++) {
+                for (int s = 0; s < MAIN_SLOTS + C::NXS * C::XP; s++, b_it++) {
                     const uint32_t bs = b_it % C::NBS;
                     mbar_wait(&emptyB[bs], ((b_it / C::NBS) & 1) ^ 1);
                     if (elect_one_sync()) {
-                        const bool is_x = s >= C::NCG * C::NTAPS;
-                        const uint32_t bytes = is_x ? C::X_SLAB_BYTES : C::SLAB_BYTES;
-                        // packed [cin_group][9 taps]: slab (s / NTAPS) * 9 + TAP0 + s % NTAPS
-                        const uint8_t *src = is_x ? gxs + (size_t)(s - C::NCG * C::NTAPS) * C::X_SLAB_BYTES
-                                                  : gws + (size_t)((s / C::NTAPS) * 9 + C::TAP0 + s % C::NTAPS) * C::SLAB_BYTES;
+                        const bool is_x = s >= MAIN_SLOTS;
+                        const uint32_t bytes = is_x ? C::X_SLAB_BYTES : C::RSLOT_BYTES;
+                        // packed [cin_group][9 taps]: first slab of slot s = (s * TPS / NTAPS) * 9 + TAP0 + (s * TPS) % NTAPS, TPS consecutive taps
+                        const uint8_t *src = is_x ? gxs + (size_t)(s - MAIN_SLOTS) * C::X_SLAB_BYTES
+                                                  : gws + (size_t)(((s * C::TPS) / C::NTAPS) * 9 + C::TAP0 + (s * C::TPS) % C::NTAPS) * C::SLAB_BYTES;
                         mbar_arrive_expect_tx(&fullB[bs], bytes);
-                        bulk_g2s(sB + bs * C::SLAB_BYTES, src, bytes, &fullB[bs]);
+                        bulk_g2s(sB + bs * C::RSLOT_BYTES, src, bytes, &fullB[bs]);
                     }
                 }
             }
@@ -584,14 +627,14 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
         // stride-2 conv]; the halo / zero padding comes from the TMA out-of-bounds fill
         if (lane == 0) { tma_prefetch_desc(&p.in_map); if (C::XC > 0) tma_prefetch_desc(&p.x_map); }
         uint32_t a_it = 0;
-        for (int tile0 = blockIdx.x; tile0 < ((C::RESIDENT && (p.dbg & 8)) ? 0 : ntiles); tile0 += C::TSTEP * gridDim.x) {
-            const int np = C::HILO_IN ? 2 : ((C::TP == 2 && tile0 + (int)gridDim.x < ntiles) ? 2 : 1);
+        for (int tile0 = bid; tile0 < ((C::RESIDENT && (p.dbg & 8)) ? 0 : ntiles); tile0 += C::TSTEP * nblk) {
+            const int np = C::HILO_IN ? 2 : ((C::TP == 2 && tile0 + nblk < ntiles) ? 2 : 1);
             // stage order of a pass: (step 0, tile 0), (step 0, tile 1), (step 1, tile 0), ... -- what the MMA issuer consumes
 #pragma unroll 1
             for (int it = 0; it < C::NCG + C::NXS; it++) {
 #pragma unroll 1
                 for (int h = 0; h < np; h++, a_it++) {
-                    const int ltile = C::HILO_IN ? tile0 : tile0 + h * (int)gridDim.x;
+                    const int ltile = C::HILO_IN ? tile0 : tile0 + h * nblk;
                     const int part = C::HILO_IN ? h : 0; // 0 = hi tensor, 1 = lo tensor (stored right behind it: plane index + planes)
                     const int tile = (p.reverse ? ntiles - 1 - ltile : ltile) / C::NSPLIT;
                     int unit, oy0, ox0;
@@ -640,10 +683,25 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_
 
     tc_fence_before();
     __syncthreads();
-    if (warp == C::W_MMA) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if constexpr (!CHAIN) {
+        if (warp == C::W_MMA) {
+            tc_fence_after();
+            tmem_dealloc(tmem_base, C::TMEM_COLS);
+        }
+    } else {
+        // every wait of this layer has returned (all roles are past their loops): the barrier objects may be destroyed, the next
+        // layer lays its own shared-memory carve-up over them
+        if (tid == 0)
+            for (int i = 0; i < C::NBAR; i++) mbar_inval(&bars[i]);
+        __syncthreads();
     }
+}
+
+template <class C>
+__global__ void __launch_bounds__(C::NTHREADS, 1) conv_umma_kernel(const __grid_constant__ ConvParams p)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    conv_layer_body<C, false>(p, smem, 0u, (int)blockIdx.x, (int)gridDim.x);
 }
 
 } // namespace mlt

@@ -120,9 +120,21 @@ ActLayout conv_umma_out_layout(int layer); // layout of the activation conv `lay
 cudaError_t conv_umma_prepare(int layer, ConvParams *p, const __half *in, const ActLayout &in_l, const __half *x, const ActLayout *x_l,
                               size_t images);
 cudaError_t launch_conv_umma(int layer, const ConvParams &p, int num_sms, cudaStream_t s);
+// Small batches (the in-encoder call: one CTU): convs 1..15 -- everything between the stem and the head -- as ONE kernel on one
+// thread-block cluster.  The 15 layers run back to back; a cluster barrier (hardware, ~1 us) replaces the kernel boundary
+// (~8 us of launch + prologue + drain each).  p[i] = the ConvParams of conv i + 1 (layer3 = the channel-split variants).
+constexpr int CHAIN_NCONV = 15, CHAIN_CLUSTER = 16, CHAIN_MAX_IMAGES = 2;
+struct ChainParams {
+    ConvParams p[CHAIN_NCONV];
+    unsigned long long *trace; // MLT_CHAIN_TRACE debug: CTA 0 stores %globaltimer at kernel start, after every layer and after every barrier
+};
+cudaError_t launch_conv_chain(const ChainParams &cp, cudaStream_t s);
+
 // layers 12..15 (layer3) also exist with their 256 output channels split over 4 CTAs, as "layers" 16..19: used when a
 // batch has fewer tiles than SMs (p.w / p.x_w then point at the split-packed weights)
 constexpr int CONV_SPLIT_FIRST = 12, CONV_SPLIT_OFFSET = 4, CONV_SPLIT_WAYS = 4;
+// tiny batches: layer3 (12..15) split 8 ways = "layers" 20..23, layer2 (8..11) split 4 ways = "layers" 24..27
+constexpr int CONV_SPLIT8_OFFSET = 8, CONV_SPLIT8_WAYS = 8, CONV_L2SPLIT_FIRST = 8, CONV_L2SPLIT_OFFSET = 16, CONV_L2SPLIT_WAYS = 4;
 // 5-D tiled tensor map over a chunk-planar activation tensor: dims (x*8, img, row, chunk, unit*plane), box (px, img, rows, chunks, 1)
 cudaError_t make_act_map(CUtensorMap *tm, const __half *base, const ActLayout &L, size_t units, int box_px, int box_img,
                          int box_rows, int box_chunks);

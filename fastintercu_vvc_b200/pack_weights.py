@@ -61,7 +61,10 @@ SEC_FC_B = 0x900
 SEC_X_W_F16 = 0xB00
 SEC_W_SPLIT = 0xC00  # layer3 weights again, output channels split 4 ways: [split][cin_group][tap][G/8][Cout/4][8]
 SEC_X_SPLIT = 0xD00  # and their extra-operand slabs: [split][xc/gx][(hi, lo)][gx/8][Cout/4][8]
-SPLIT_LAYERS, SPLIT_WAYS = (12, 13, 14, 15), 4  # = CONV_SPLIT_* of csrc/mlt_internal.h
+SEC_W_SPLIT8 = 0xE00  # layer3 split 8 ways (tiny batches)
+SEC_X_SPLIT8 = 0xF00
+SPLIT_LAYERS, SPLIT_WAYS = (8, 9, 10, 11, 12, 13, 14, 15), 4  # layer2 and layer3, = CONV_SPLIT_* / CONV_L2SPLIT_* of csrc/mlt_internal.h
+SPLIT8_LAYERS, SPLIT8_WAYS = (12, 13, 14, 15), 8
 ROUNDING = "diffused"  # "nearest" = independent round-to-nearest (tools/precision_ab.py compares the two)
 ALPHA = np.float32(1.0 / 1023)  # (float)(1.0/1023), bits 0x3A802008: cv::Mat::convertTo's alpha at EncCu.cpp:835-838
 
@@ -415,6 +418,8 @@ def build_sections(sd: dict, calib: np.ndarray | None = None, correct_bias: bool
         corr = bias_correction(wf, quantize_fp16_diffused(wf), tm[prefix]) if tm is not None else 0.0
         if li in SPLIT_LAYERS:
             add(SEC_W_SPLIT + li, split_cout(packed, SPLIT_WAYS), np.float16)
+        if li in SPLIT8_LAYERS:
+            add(SEC_W_SPLIT8 + li, split_cout(packed, SPLIT8_WAYS), np.float16)
         add(SEC_W_F32 + li, wf.transpose(2, 3, 1, 0).reshape(9, cin, cout), np.float32)
         add(SEC_BIAS + li, bf, np.float32)
         fused = bf
@@ -426,6 +431,8 @@ def build_sections(sd: dict, calib: np.ndarray | None = None, correct_bias: bool
             add(SEC_X_W_F16 + li, xop, np.float16)
             if li in SPLIT_LAYERS:
                 add(SEC_X_SPLIT + li, split_cout(xop, SPLIT_WAYS), np.float16)
+            if li in SPLIT8_LAYERS:
+                add(SEC_X_SPLIT8 + li, split_cout(xop, SPLIT8_WAYS), np.float16)
             add(SEC_SC_W_F32 + sc, ws.reshape(cout, csc).T, np.float32)
             add(SEC_SC_BIAS + sc, bs, np.float32)
             fused = (bf.astype(np.float32) + bs.astype(np.float32)).astype(np.float32)
@@ -435,6 +442,8 @@ def build_sections(sd: dict, calib: np.ndarray | None = None, correct_bias: bool
             add(SEC_X_W_F16 + li, xop, np.float16)
             if li in SPLIT_LAYERS:
                 add(SEC_X_SPLIT + li, split_cout(xop, SPLIT_WAYS), np.float16)
+            if li in SPLIT8_LAYERS:
+                add(SEC_X_SPLIT8 + li, split_cout(xop, SPLIT8_WAYS), np.float16)
         fused = (fused.astype(np.float64) - corr).astype(np.float32)  # tcgen05 path only: SEC_BIAS (fp32 engine, exact weights) stays exact
         add(SEC_BIAS_FUSED + li, fused, np.float32)
         add(SEC_BIAS_MMA + li, bias_operand(fused), np.float16)

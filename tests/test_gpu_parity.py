@@ -811,3 +811,33 @@ def test_patched_vtm_encoder_matches_the_reference_hook_encoder(tmp_path):
     assert mlt["bitstream_md5"] == ref["bitstream_md5"] == staged["bitstream_md5"]
     assert mlt["recon_md5"] == ref["recon_md5"]
     assert mlt["hook_calls"] == 6
+
+
+def test_cluster_chain_kernel_is_bit_identical_to_the_per_layer_kernels(blob, ctus):
+    """MLT_CHAIN=1 runs convs 1..15 of a one- / two-CTU call as ONE kernel on a 16-CTA cluster (cluster barriers between the layers,
+    mbarriers re-initialised per layer, TMEM allocated once): same tiles, same MMA order -> byte-identical results, 3 launches per call."""
+    orgpred, pocqp = ctus
+    np.save(os.path.join(os.path.dirname(blob), "chain_ctus.npy"), orgpred[:6])
+    np.save(os.path.join(os.path.dirname(blob), "chain_pq.npy"), pocqp[:6])
+    code = f"""
+import numpy as np, sys
+sys.path.insert(0, {ROOT!r})
+import fastintercu_vvc_b200 as pkg
+o, q = np.load({os.path.join(os.path.dirname(blob), 'chain_ctus.npy')!r}), np.load({os.path.join(os.path.dirname(blob), 'chain_pq.npy')!r})
+with pkg.MltPredictor({blob!r}, device=0, max_batch=8) as p:
+    full = p.predict_batch_dense(o, q)
+    l0 = p.launch_count
+    one = [p.predict_ctu(o[i, 0], o[i, 1], int(q[i, 0]), int(q[i, 1])).tobytes() for i in range(6)]
+    per_call = (p.launch_count - l0) / 6
+    pair = p.predict_batch_dense(o[2:4], q[2:4]).tobytes()
+print(per_call, all(one[i] == full[i].tobytes() for i in range(6)), pair == full[2:4].tobytes())
+"""
+    out = {}
+    for tag, env in (("chain", {"MLT_CHAIN": "1"}), ("layers", {})):
+        e = {k: v for k, v in os.environ.items() if k not in ("MLT_CHAIN", "MLT_NO_CHAIN")}
+        e.update(env)
+        r = subprocess.run(["timeout", "-s", "KILL", "120", sys.executable, "-c", code], env=e, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-500:]
+        out[tag] = r.stdout.split()
+    assert out["chain"] == ["3.0", "True", "True"], out
+    assert out["layers"] == ["17.0", "True", "True"], out
