@@ -813,17 +813,17 @@ def test_patched_vtm_encoder_matches_the_reference_hook_encoder(tmp_path):
     assert mlt["hook_calls"] == 6
 
 
-def test_cluster_chain_kernel_is_bit_identical_to_the_per_layer_kernels(blob, ctus):
+def test_cluster_chain_kernel_is_bit_identical_to_the_per_layer_kernels(blob, ctus, tmp_path):
     """MLT_CHAIN=1 runs convs 1..15 of a one- / two-CTU call as ONE kernel on a 16-CTA cluster (cluster barriers between the layers,
     mbarriers re-initialised per layer, TMEM allocated once): same tiles, same MMA order -> byte-identical results, 3 launches per call."""
     orgpred, pocqp = ctus
-    np.save(os.path.join(os.path.dirname(blob), "chain_ctus.npy"), orgpred[:6])
-    np.save(os.path.join(os.path.dirname(blob), "chain_pq.npy"), pocqp[:6])
+    np.save(str(tmp_path / "chain_ctus.npy"), orgpred[:6])
+    np.save(str(tmp_path / "chain_pq.npy"), pocqp[:6])
     code = f"""
 import numpy as np, sys
 sys.path.insert(0, {ROOT!r})
 import fastintercu_vvc_b200 as pkg
-o, q = np.load({os.path.join(os.path.dirname(blob), 'chain_ctus.npy')!r}), np.load({os.path.join(os.path.dirname(blob), 'chain_pq.npy')!r})
+o, q = np.load({str(tmp_path / 'chain_ctus.npy')!r}), np.load({str(tmp_path / 'chain_pq.npy')!r})
 with pkg.MltPredictor({blob!r}, device=0, max_batch=8) as p:
     full = p.predict_batch_dense(o, q)
     l0 = p.launch_count
