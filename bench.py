@@ -40,7 +40,7 @@ FLOP_PER_CTU = 1_134_562_340  # SURVEY.md section 8a (2*MAC, all 21 convs + 3 FC
 FLOP_CONV1 = 18_874_368
 FLOP_FC = 3_108
 FLOP_UMMA_PER_CTU = FLOP_PER_CTU - FLOP_CONV1 - FLOP_FC  # the 16 tcgen05 conv launches
-NCU_DRAM_BYTES_PER_CTU = 4_838_900  # measured: 18.581 GB per 3840-CTU step (profiles/r01/ncu_full_v17_summary.csv; v11: 18.757 GB)
+NCU_DRAM_BYTES_PER_CTU = 4_827_100  # measured: 18.536 GB per 3840-CTU step (profiles/r02/ncu_full_d_summary.csv; r01: 18.581 GB)
 METRIC = "mlt_cnn_split_ctus_per_s"
 
 
@@ -782,8 +782,13 @@ def main():
                           "note": "the same device-resident step repeated back to back for >= --sustain-s seconds; nvidia-smi sampled inside the window"},
             "roofline": {"bound": "tensor", "achieved": ach, "peak": sustained, "unit": "TFLOP/s", "frac": ach / sustained,
                          "peak_burst": burst, "frac_vs_burst": ach / burst,
-                         "traffic": NCU_DRAM_BYTES_PER_CTU * n, "traffic_note": "ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the launches of one 3840-CTU step (profiles/r01/ncu_full_v17_summary.csv), scaled to this step; algorithmic minimum is 65,536 B/CTU -- the rest is inter-layer fp16 activations",
-                         "kernel": "stem_umma_kernel + conv_umma_kernel x15 (every tcgen05 launch of a step: all 21 convs)",
+                         "traffic": NCU_DRAM_BYTES_PER_CTU * n, "traffic_note": "ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the launches of one 3840-CTU step (profiles/r02/ncu_full_d_summary.csv), scaled to this step; algorithmic minimum is 65,536 B/CTU -- the rest is inter-layer fp16 activations",
+                         "kernel": "stem5_umma_kernel + conv_umma_kernel x15 (every tcgen05 launch of a step: all 21 convs)",
+                         "frac_note": "achieved = algorithmic FLOPs / sum of the per-launch CUDA-event times, launches serialised on one stream; the timed step "
+                                      "overlaps two half-batches on two streams and is faster: whole_step_* = value x FLOP/CTU",
+                         "whole_step_achieved": value / world * (FLOP_PER_CTU - FLOP_FC) / 1e12,
+                         "whole_step_frac": value / world * (FLOP_PER_CTU - FLOP_FC) / 1e12 / sustained,
+                         "whole_step_frac_vs_burst": value / world * (FLOP_PER_CTU - FLOP_FC) / 1e12 / burst,
                          "peak_source": f"{how} bf16 sustained", "kernel_ms_per_step": umma_ms, "stem_ms": float(prof[0]),
                          "head_ms": float(prof[17]), "per_layer_ms": [round(float(x), 4) for x in prof[2:17]]},
             "frame_latency_ms": frame_ms,
