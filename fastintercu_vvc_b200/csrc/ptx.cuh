@@ -70,6 +70,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// non-suspending poll (mbarrier.test_wait): lower wake-up latency than try_wait, at the price of issue slots while spinning
+__device__ __forceinline__ bool mbar_test_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_spin(uint64_t *bar, uint32_t parity)
+{
+    while (!mbar_test_wait(bar, parity)) {
+    }
+}
 
 // ------------------------------------------------------------------ cp.async (LDGSTS), 16 B with zero-fill
 __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void *gsrc, bool valid)

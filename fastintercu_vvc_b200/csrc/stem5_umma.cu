@@ -40,7 +40,7 @@ constexpr int CORRW_FLOATS = 2 * 5 * 2 * 32 + 2 * 32;      // SEC_STEM5_CORR: Wt
 constexpr int CORR_BYTES = 32 * 32 * 4;                    // per buffer: 16 top + 16 left border pixels x 32 channels, fp32
 constexpr int OFF_EP = 0;
 constexpr int OFF_RAW = OFF_EP + 2 * EP_BYTES;
-constexpr int OFF_W = (OFF_RAW + RAW_BYTES + 127) / 128 * 128;
+constexpr int OFF_W = (OFF_RAW + 2 * RAW_BYTES + 127) / 128 * 128; // two H planes: one per stager group
 constexpr int OFF_CORRW = OFF_W + W_BYTES;
 constexpr int OFF_CORR = OFF_CORRW + CORRW_FLOATS * 4;
 constexpr int OFF_BIAS = OFF_CORR + 2 * CORR_BYTES;
@@ -73,7 +73,10 @@ template <int S, int NSTG>
 __global__ void __launch_bounds__(stem5::nthreads(NSTG), 2) stem5_umma_kernel(const Stem5Params p)
 {
     using namespace stem5;
-    constexpr int NTHREADS = nthreads(NSTG), STG_THREADS = NSTG * 32;
+    // GROUPS = 2 (two stager groups of four warps staging alternate units into their own H plane / EP buffer: a unit's staging is a
+    // latency chain that more threads do not shorten, two chains in flight would) is wired below but DISABLED: it passes up to ~20
+    // units per CTA and hangs beyond (n = 900), cause not found in this round -- see profiles/r02/README.md.
+    constexpr int NTHREADS = nthreads(NSTG), GROUPS = 1, STG_THREADS = NSTG * 32 / GROUPS;
     constexpr int OH = S / 2, UW = S / 32, UPI = UW * UW; // output map size; work units per row / per block
     auto out_off = [&](int b, int oy, int ox) -> size_t {
         return S == 128 ? (size_t)b * (4 * OH * OH * 8) + (size_t)(oy * OH + ox) * 8 : ((size_t)(oy * p.cap + b) * OH + ox) * 8;
@@ -89,9 +92,9 @@ __global__ void __launch_bounds__(stem5::nthreads(NSTG), 2) stem5_umma_kernel(co
 
     if (tid == 0) {
         for (int i = 0; i < 2; i++) {
-            mbar_init(&ep_full[i], NSTG); mbar_init(&ep_empty[i], 1);
+            mbar_init(&ep_full[i], NSTG / GROUPS); mbar_init(&ep_empty[i], 1);
             mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], NEPI);
-            mbar_init(&corr_full[i], NSTG);
+            mbar_init(&corr_full[i], NSTG / GROUPS);
         }
         mbar_fence_init();
     }
@@ -107,13 +110,23 @@ __global__ void __launch_bounds__(stem5::nthreads(NSTG), 2) stem5_umma_kernel(co
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const uint32_t sEP = smem_u32(smem + OFF_EP);
+    const bool spin = (p.dbg & 128) != 0; // timing experiment: mbarrier.test_wait polling instead of try_wait
+    auto bwait = [&](uint64_t *bar, uint32_t parity) {
+        if (spin) mbar_wait_spin(bar, parity);
+        else mbar_wait(bar, parity);
+    };
     griddep_launch_dependents(); // PDL: the prologue above overlapped the previous kernel's tail
     griddep_wait();
 
     if (warp >= W_STG) {
         // ======================= stagers: int16 window -> fp16 {org, res} plane H -> expanded, parity-split operand EP (+ border terms)
-        const int st = tid - W_STG * 32; // 0 .. STG_THREADS - 1
-        uint32_t *H = reinterpret_cast<uint32_t *>(smem + OFF_RAW);
+        const int grp = (tid - W_STG * 32) / STG_THREADS, st = (tid - W_STG * 32) % STG_THREADS; // stager group; thread within the group
+        uint32_t *H = reinterpret_cast<uint32_t *>(smem + OFF_RAW + grp * RAW_BYTES);
+        const int u_first = blockIdx.x + grp * gridDim.x, u_step = GROUPS * gridDim.x; // group g stages this CTA's units g, g + GROUPS, ...
+        auto group_sync = [&]() { // named barrier of this group (immediate ids: a register id makes ptxas reserve all 16 barriers)
+            if (grp == 0) asm volatile("bar.sync 1, %0;" ::"n"(STG_THREADS) : "memory");
+            else asm volatile("bar.sync 2, %0;" ::"n"(STG_THREADS) : "memory");
+        };
         constexpr int NV = RAW_ROWS * 6;          // 210 (row, 8-sample vector) pairs of the window
         constexpr int NE = 4 * EP_ROWS * PE;      // 1296 entry slots
         constexpr int EPT = (NE + STG_THREADS - 1) / STG_THREADS; // entry slots per thread
@@ -147,12 +160,14 @@ __global__ void __launch_bounds__(stem5::nthreads(NSTG), 2) stem5_umma_kernel(co
             }
         };
         uint4 vo[VPT], vp[VPT];
-        if ((int)blockIdx.x < total_units) load_window(blockIdx.x, vo, vp);
+        if (u_first < total_units) load_window(u_first, vo, vp);
         const float *cw = reinterpret_cast<const float *>(smem + OFF_CORRW);
-        uint32_t ul = 0;
-        for (int u = blockIdx.x; u < total_units; u += gridDim.x, ul++) {
+        uint32_t it = 0;
+        for (int u = u_first; u < total_units; u += u_step, it++) {
             const int oy0 = ((u % UPI) / UW) * 16, ox0 = ((u % UPI) % UW) * 16;
-            asm volatile("bar.sync 1, %0;" ::"n"(STG_THREADS) : "memory"); // every stager is done reading the previous unit's H
+            // this CTA's unit index ul = it * GROUPS + grp uses buffer ul & 1 for the (ul >> 1)-th time
+            const uint32_t ul = it * GROUPS + grp;
+            group_sync(); // every stager of the group is done reading the previous unit's H
 #pragma unroll
             for (int k = 0; k < VPT; k++) {
                 const int i = st + k * STG_THREADS;
@@ -173,10 +188,10 @@ __global__ void __launch_bounds__(stem5::nthreads(NSTG), 2) stem5_umma_kernel(co
                     dst[1] = make_uint4(hv[4], hv[5], hv[6], hv[7]);
                 }
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(STG_THREADS) : "memory");
-            if (u + (int)gridDim.x < total_units) load_window(u + gridDim.x, vo, vp); // prefetch: lands while we gather
+            group_sync();
+            if (u + u_step < total_units) load_window(u + u_step, vo, vp); // prefetch: lands while we gather
             const uint32_t buf = ul & 1;
-            mbar_wait(&ep_empty[buf], ((ul >> 1) & 1) ^ 1);
+            bwait(&ep_empty[buf], ((ul >> 1) & 1) ^ 1);
             uint8_t *ep = smem + OFF_EP + buf * EP_BYTES;
 #pragma unroll
             for (int k = 0; k < EPT; k++) {
@@ -191,7 +206,7 @@ __global__ void __launch_bounds__(stem5::nthreads(NSTG), 2) stem5_umma_kernel(co
             if ((oy0 == 0 || ox0 == 0) && st < 128) {
                 // border terms (see the header): slot ps < 16 = output (0, ox0 + ps), top; ps >= 16 = output (oy0 + ps - 16, 0), left;
                 // the epilogue of the unit that used this buffer two units ago must be done with it
-                mbar_wait(&d_empty[buf], ((ul >> 1) & 1) ^ 1);
+                bwait(&d_empty[buf], ((ul >> 1) & 1) ^ 1);
                 const int ps = st >> 2, cg = (st & 3) * 8;
                 const bool top = ps < 16;
                 if (top ? oy0 == 0 : ox0 == 0) {
@@ -230,8 +245,8 @@ __global__ void __launch_bounds__(stem5::nthreads(NSTG), 2) stem5_umma_kernel(co
         const int my_units = total_units > (int)blockIdx.x ? (total_units - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
         for (int v = 0; v < my_units; v++) {
             const uint32_t buf = v & 1;
-            mbar_wait(&ep_full[buf], (v >> 1) & 1);
-            mbar_wait(&d_empty[buf], ((v >> 1) & 1) ^ 1);
+            bwait(&ep_full[buf], (v >> 1) & 1);
+            bwait(&d_empty[buf], ((v >> 1) & 1) ^ 1);
             tc_fence_after();
             if (elect_one_sync()) {
                 const uint32_t ep = sEP + buf * EP_BYTES;
@@ -266,8 +281,8 @@ __global__ void __launch_bounds__(stem5::nthreads(NSTG), 2) stem5_umma_kernel(co
         for (int u = blockIdx.x; u < total_units; u += gridDim.x, ul++) {
             const int ctu = u / UPI, oy0 = ((u % UPI) / UW) * 16, ox0 = ((u % UPI) % UW) * 16;
             const uint32_t buf = ul & 1;
-            mbar_wait(&corr_full[buf], (ul >> 1) & 1);
-            mbar_wait(&d_full[buf], (ul >> 1) & 1);
+            bwait(&corr_full[buf], (ul >> 1) & 1);
+            bwait(&d_full[buf], (ul >> 1) & 1);
             tc_fence_after();
             const uint32_t tbase = tmem + ((uint32_t)(wq * 32) << 16) + buf * 128 + half * 32;
             uint32_t v[32];

@@ -45,6 +45,6 @@ if __name__ == "__main__":
     write_blob(make_state_dict(10), blob)
     for v in VARIANTS:
         env = dict(os.environ, **v)
-        r = subprocess.run([sys.executable, __file__, blob], env=env, capture_output=True, text=True)
+        r = subprocess.run(["timeout", "-s", "KILL", "60", sys.executable, __file__, blob], env=env, capture_output=True, text=True)
         print(v, r.stdout.strip() or r.stderr[-300:], flush=True)
     os.unlink(blob)
