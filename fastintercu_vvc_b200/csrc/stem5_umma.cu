@@ -73,10 +73,10 @@ template <int S, int NSTG>
 __global__ void __launch_bounds__(stem5::nthreads(NSTG), 2) stem5_umma_kernel(const Stem5Params p)
 {
     using namespace stem5;
-    // GROUPS = 2 (two stager groups of four warps staging alternate units into their own H plane / EP buffer: a unit's staging is a
-    // latency chain that more threads do not shorten, two chains in flight would) is wired below but DISABLED: it passes up to ~20
-    // units per CTA and hangs beyond (n = 900), cause not found in this round -- see profiles/r02/README.md.
-    constexpr int NTHREADS = nthreads(NSTG), GROUPS = 1, STG_THREADS = NSTG * 32 / GROUPS;
+    // NSTG = 8: TWO stager groups of four warps, each staging alternate units into its own H plane / EP buffer.  A unit's staging is a
+    // latency chain (global loads -> bar.sync -> convert -> bar.sync -> gather -> arrive) that more threads do not shorten; two
+    // chains in flight do.
+    constexpr int NTHREADS = nthreads(NSTG), GROUPS = NSTG == 8 ? 2 : 1, STG_THREADS = NSTG * 32 / GROUPS;
     constexpr int OH = S / 2, UW = S / 32, UPI = UW * UW; // output map size; work units per row / per block
     auto out_off = [&](int b, int oy, int ox) -> size_t {
         return S == 128 ? (size_t)b * (4 * OH * OH * 8) + (size_t)(oy * OH + ox) * 8 : ((size_t)(oy * p.cap + b) * OH + ox) * 8;
@@ -203,10 +203,14 @@ __global__ void __launch_bounds__(stem5::nthreads(NSTG), 2) stem5_umma_kernel(co
                         odd ? make_uint4(w0.y, w1.x, w1.y, w2.x) : make_uint4(w0.x, w0.y, w1.x, w1.y);
                 }
             }
+            // The epilogue of the unit that used this buffer two units ago must be done before this unit's corr_full arrival (and
+            // before corr[buf] is rewritten): corr_full may run at most ONE phase ahead of its waiter.  Without this wait the
+            // arrival for use k can land while the epilogue still waits for use k - 1 -- the barrier is then in phase k + 1, whose
+            // parity equals that of k - 1, the epilogue's parity wait never returns and the pipeline deadlocks (seen with two stager
+            // groups from ~25 units per CTA on; with one group the stagers were always the slowest role, so it stayed latent).
+            bwait(&d_empty[buf], ((ul >> 1) & 1) ^ 1);
             if ((oy0 == 0 || ox0 == 0) && st < 128) {
-                // border terms (see the header): slot ps < 16 = output (0, ox0 + ps), top; ps >= 16 = output (oy0 + ps - 16, 0), left;
-                // the epilogue of the unit that used this buffer two units ago must be done with it
-                bwait(&d_empty[buf], ((ul >> 1) & 1) ^ 1);
+                // border terms (see the header): slot ps < 16 = output (0, ox0 + ps), top; ps >= 16 = output (oy0 + ps - 16, 0), left
                 const int ps = st >> 2, cg = (st & 3) * 8;
                 const bool top = ps < 16;
                 if (top ? oy0 == 0 : ox0 == 0) {
