@@ -841,3 +841,30 @@ print(per_call, all(one[i] == full[i].tobytes() for i in range(6)), pair == full
         out[tag] = r.stdout.split()
     assert out["chain"] == ["3.0", "True", "True"], out
     assert out["layers"] == ["17.0", "True", "True"], out
+
+
+@pytest.mark.parametrize("stagers", ["4", "8"])
+def test_stem_pipeline_survives_many_units_per_cta(blob, ctus, stagers, tmp_path):
+    """Regression for a parity-aliasing deadlock in stem5_umma_kernel: the border-term barrier (corr_full) was not gated on its
+    consumer, so its producer could run two phases ahead and the epilogue's parity wait never returned.  It needed ~25+ units per
+    CTA and fast stagers (two stager groups, MLT_STEM5_STAGERS=8) to show.  900 CTUs = 49 units per CTA, in a subprocess under a
+    hard timeout; results must equal the small-batch ones."""
+    orgpred, pocqp = ctus
+    np.save(str(tmp_path / "c.npy"), orgpred)
+    np.save(str(tmp_path / "q.npy"), pocqp)
+    code = f"""
+import numpy as np, sys
+sys.path.insert(0, {ROOT!r})
+import fastintercu_vvc_b200 as pkg
+o, q = np.load({str(tmp_path / 'c.npy')!r}), np.load({str(tmp_path / 'q.npy')!r})
+idx = np.arange(900) % len(o)
+with pkg.MltPredictor({blob!r}, device=0, max_batch=900) as p:
+    small = p.predict_batch_dense(o, q)
+    for _ in range(3):
+        big = p.predict_batch_dense(np.ascontiguousarray(o[idx]), np.ascontiguousarray(q[idx]))
+print(bool(np.array_equal(big["logits"].view(np.uint32), small["logits"][idx].view(np.uint32))))
+"""
+    e = dict(os.environ, MLT_STEM5_STAGERS=stagers)
+    r = subprocess.run(["timeout", "-s", "KILL", "120", sys.executable, "-c", code], env=e, capture_output=True, text=True)
+    assert r.returncode == 0, f"rc {r.returncode} (killed by the timeout = the pipeline hung): {r.stderr[-400:]}"
+    assert r.stdout.split() == ["True"], r.stdout
