@@ -2,6 +2,7 @@
 #include <cassert>
 #include <cstdio>
 #include <cstdlib>
+#include <unistd.h>
 #include <vector>
 
 #include "mlt_hook.h"
@@ -73,6 +74,11 @@ int main()
 
     // ---- predictor failure convention: no usable GPU / weights here -> -1, never throws, never falls back
     setenv("MLT_WEIGHTS", "/nonexistent/weights.mltw", 1);
+    char trace_path[] = "/tmp/mlt_hook_trace_XXXXXX", dump_path[] = "/tmp/mlt_hook_dump_XXXXXX";
+    close(mkstemp(trace_path));
+    close(mkstemp(dump_path));
+    setenv("MLT_TRACE", trace_path, 1);       // read once, by the constructor
+    setenv("MLT_DUMP_INPUTS", dump_path, 1);
     SplitPredictor &p = SplitPredictor::instance();
     std::vector<int16_t> blk(128 * 128, 512);
     const int r = p.predict(blk.data(), 128, blk.data(), 128, 1, 32);
@@ -88,6 +94,34 @@ int main()
         assert(!p.prepassPictureCu(64, blk.data(), 128, blk.data(), 128, 128, 128, 1, nullptr, 32));
         assert(p.pictureSplit(0, 0) == -1 && p.pictureSplitCu(64, 0, 0) == -1);
     }
+    // predictAt = the one call the VTM patch makes (integration/apply_vtm_patch.py): same -1 convention, one trace line and one
+    // input record per 128x128 call (poc, qp, strided org block, strided pred block)
+    if (!p.enabled()) {
+        std::vector<int16_t> pic(160 * 200);
+        for (size_t i = 0; i < pic.size(); i++) pic[i] = (int16_t)(i % 1000);
+        assert(p.predictAt(128, 128, 256, pic.data() + 3, 200, blk.data(), 128, 7, 35) == -1);
+        assert(p.predictAt(64, 64, 0, pic.data(), 200, blk.data(), 128, 7, 35) == -1); // no trace record for the inputs of smaller CUs
+        FILE *tf = std::fopen(trace_path, "r");
+        int a, b, c, d, e, lines = 0;
+        while (tf && std::fscanf(tf, "%d %d %d %d %d", &a, &b, &c, &d, &e) == 5) {
+            if (lines == 0) assert(a == 7 && b == 128 && c == 256 && d == 35 && e == -1);
+            lines++;
+        }
+        if (tf) std::fclose(tf);
+        assert(lines == 2);
+        FILE *df = std::fopen(dump_path, "rb");
+        assert(df);
+        int32_t hdr[2];
+        std::vector<int16_t> rec(2 * 128 * 128);
+        assert(std::fread(hdr, 4, 2, df) == 2 && hdr[0] == 7 && hdr[1] == 35);
+        assert(std::fread(rec.data(), 2, rec.size(), df) == rec.size());
+        assert(rec[0] == pic[3] && rec[128] == pic[200 + 3] && rec[127 * 128 + 127] == pic[127 * 200 + 127 + 3]); // stride honoured
+        assert(rec[128 * 128] == 512);
+        assert(std::fgetc(df) == EOF); // exactly one record
+        std::fclose(df);
+    }
+    std::remove(trace_path);
+    std::remove(dump_path);
     setenv("MLT_PREPASS", "1", 1);
     setenv("MLT_PREPASS_RANGE", "40", 1);
     assert(SplitPredictor::prepassFromEnv() && SplitPredictor::prepassRangeFromEnv() == 16);
