@@ -927,6 +927,14 @@ void EncCu::xCompressCU( CodingStructure*& tempCS, CodingStructure*& bestCS, Par
                 // --- added here 210622
                 if (const char *mltTrace = getenv("MLT_TRACE")) // oracle build only: same "poc x y qp split" line as mlt_hook
                     if (FILE *mltTf = fopen(mltTrace, "a")) { fprintf(mltTf, "%d %d %d %d %d\n", poc, cux, cuy, cuQP, predictedSplitMode); fclose(mltTf); }
+                if (const char *mltDump = getenv("MLT_DUMP_INPUTS")) // oracle build only: the call's inputs, same records as mlt_hook writes
+                    if (FILE *mltDf = fopen(mltDump, "ab")) {
+                        const int32_t mltHdr[2] = { poc, cuQP };
+                        fwrite(mltHdr, 4, 2, mltDf);
+                        for (int i = 0; i < cuh; i++) fwrite(sOrg + i * bestCS->getOrgBuf().Y().stride, 2, cuw, mltDf);
+                        for (int i = 0; i < cuh; i++) fwrite(sPred + i * bestCS->getPredBuf().Y().stride, 2, cuw, mltDf);
+                        fclose(mltDf);
+                    }
                 m_modeCtrl->setNewModeList(*tempCS, partitioner, predictedSplitMode, currTestMode.qp);
                 // ---
             }

@@ -71,7 +71,7 @@ def test_patch_anchors_hold_on_the_reference_tree(tmp_path):
     src = open(os.path.join(REF_ENC, "EncCu.cpp")).readlines()
     for dev in ("cpu", "cuda"):
         out = patcher.apply_reference_edits(src, dev)
-        assert len(out) == len(src) + 2  # the two trace lines; everything else token edits
+        assert len(out) == len(src) + 10  # the trace line and the input dump (oracle build only); everything else token edits
         changed = [i for i, (a, b) in enumerate(zip(src[:926], out[:926])) if a != b]
         assert changed == ([803, 898] if dev == "cpu" else [898])  # 0-based: EncCu.cpp:804 (device), :899 (model directory)
         blk = patcher.hook_block(src, dev)

@@ -11,7 +11,15 @@ with pkg.MltPredictor(blob, max_batch=8) as p:
     r = p.predict_batch_dense(op, pq)
     p.submit_batch_dense(op, pq); r2 = p.collect()
     assert r.tobytes() == r2.tobytes()
+    # round 2: 10-bit packed transport, the one-CTU call (tiny-batch channel splits), a pair
+    from fastintercu_vvc_b200.capi import pack10
+    assert p.predict_batch_packed10(pack10(op), pq).tobytes() == r.tobytes()
+    p.submit_batch_packed10(pack10(op), pq); assert p.collect().tobytes() == r.tobytes()
+    assert p.predict_ctu(op[1, 0], op[1, 1], int(pq[1, 0]), int(pq[1, 1])).tobytes() == r[1].tobytes()
+    assert p.predict_batch_dense(op[2:4], pq[2:4]).tobytes() == r[2:4].tobytes()
 print("ctu ok", r["split_l3"].tolist())
+if os.environ.get("MLT_CHAIN"):
+    print("(cluster chain kernel was used for the 1- and 2-CTU calls)")
 # frame-level pre-pass: gather kernels with MVs that hang over every picture border, odd width pitch, strided planes
 rng = np.random.RandomState(1)
 w, h = 264, 136  # 2 x 1 CTUs + a partial column / row; pitch 264
