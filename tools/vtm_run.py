@@ -45,6 +45,10 @@ ENCODERS = {
     "anchor": ("EncoderApp_mlt", {"MLT_DISABLE": "1"}),
     "prepass0": ("EncoderApp_mlt", {"MLT_PREPASS": "1", "MLT_PREPASS_RANGE": "0"}),
     "prepass8": ("EncoderApp_mlt", {"MLT_PREPASS": "1", "MLT_PREPASS_RANGE": "8"}),
+    # the smaller-CU models inside the encoder: the reference's own cuw < 128 branch with the size gate of
+    # EncCu.cpp:754 un-commented (64 / 32 / 16 px, per-size model files, level-1 argmax) against the patched encoder with MLT_CU_SIZES
+    "ref_cpu_cu": ("EncoderApp_ref_cpu_cu", {}),
+    "mlt_cu": ("EncoderApp_mlt", {"MLT_CU_SIZES": "64,32,16"}),
 }
 
 
@@ -88,7 +92,7 @@ def synth_clip(path: str, w: int, h: int, frames: int, bits: int, seed: int = 10
             f.write(chroma)
 
 
-def make_weights(d: str) -> tuple[str, str]:
+def make_weights(d: str, cu_models: bool = False) -> tuple[str, str]:
     """Seeded weights (oracle.ref_arch.make_state_dict(10)) in both containers: TorchScript traced exactly as
     model2torchScript.py:37-48 for the reference hook, MLTW blob for libmltcnn.so."""
     import torch
@@ -103,6 +107,15 @@ def make_weights(d: str) -> tuple[str, str]:
     traced.save(os.path.join(d, "MLTORPQ_splitMode_128.pt"))
     blob = os.path.join(d, "MLTORPQ_splitMode_128.mltw")
     write_blob(sd, blob)
+    if cu_models:  # per-size models: MLTORPQ_splitMode_<cuw>.pt (EncCu.cpp:899) and MLT_WEIGHTS_<cuw> blobs
+        from fastintercu_vvc_b200.pack_weights import write_cu_blob
+
+        for size in (64, 32, 16):
+            csd = ref_arch.make_cu_state_dict(10, size)
+            torch.manual_seed(0)
+            tr = torch.jit.trace(ref_arch.build_cu_model(csd), (torch.rand(1, 2, size, size), torch.rand(1), torch.rand(1)))
+            tr.save(os.path.join(d, f"MLTORPQ_splitMode_{size}.pt"))
+            write_cu_blob(csd, size, os.path.join(d, f"MLTORPQ_splitMode_{size}.mltw"))
     return d, blob
 
 
@@ -119,6 +132,8 @@ def run_encode(enc: str, clip: dict, qp: int, work: str, model_dir: str, blob: s
             os.remove(p)
     env = dict(os.environ)
     env.update({"MLT_REF_MODEL_DIR": model_dir, "MLT_WEIGHTS": blob, "MLT_TRACE": trace, "MLT_STATS": "1"})
+    for size in (64, 32, 16):
+        env[f"MLT_WEIGHTS_{size}"] = os.path.join(model_dir, f"MLTORPQ_splitMode_{size}.mltw")
     env.update(env_add)
     env.update(extra_env or {})
     if device is not None:
@@ -188,6 +203,14 @@ def compare(results: list[dict]) -> dict:
     out = {"decode_ok": all(r.get("decode_matches_recon") for r in by.values()), "pairs": [], "bd_rate": [], "time": []}
     for c in clips:
         for q in qps:
+            for ref_name, e in (("ref_cpu_cu", "mlt_cu"),):
+                ref, got = by.get((c, q, ref_name)), by.get((c, q, e))
+                if ref and got:
+                    tr, tg = ref["trace"], got["trace"]
+                    out["pairs"].append({"clip": c, "qp": q, "a": ref_name, "b": e, "calls_a": len(tr), "calls_b": len(tg),
+                                         "decisions_equal": sum(1 for x, y in zip(tr, tg) if x == y), "all_decisions_equal": tr == tg,
+                                         "bitstream_equal": ref["bitstream_md5"] == got["bitstream_md5"],
+                                         "recon_equal": ref["recon_md5"] == got["recon_md5"]})
             ref = by.get((c, q, "ref_cpu")) or by.get((c, q, "ref_cuda"))
             for e in ("mlt", "staged", "ref_cuda"):
                 got = by.get((c, q, e))
@@ -235,7 +258,8 @@ def main() -> None:
         a.size, a.bits, a.frames, a.qps = ["416x240"], 8, 8, "32"
     work = a.work or tempfile.mkdtemp(prefix="vtm_run_")
     os.makedirs(work, exist_ok=True)
-    model_dir, blob = make_weights(work)
+    encs = a.encoders.split(",")
+    model_dir, blob = make_weights(work, cu_models=any(e.endswith("_cu") for e in encs))
     clips = []
     for s in a.size:
         w, h = map(int, s.split("x"))
@@ -254,7 +278,7 @@ def main() -> None:
     def one(job):
         e, c, q = job
         dev = None
-        if e not in ("ref_cpu", "anchor"):
+        if e not in ("ref_cpu", "ref_cpu_cu", "anchor"):
             dev = gpu_rr[0] % a.gpus
             gpu_rr[0] += 1
         extra = {"OMP_NUM_THREADS": str(a.ref_threads)} if (a.ref_threads and e.startswith("ref_")) else None
