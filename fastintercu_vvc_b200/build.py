@@ -8,7 +8,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["api.cu", "conv_umma.cu", "stem_umma.cu", "stem5_umma.cu", "conv_simt.cu", "stage_conv1.cu", "head.cu", "picture_pred.cu", "picture_me.cu", "pack10.cu",
+SOURCES = ["api.cu", "conv_umma.cu", "stem_umma.cu", "stem5_umma.cu", "stem5_cu16.cu", "conv_simt.cu", "stage_conv1.cu", "head.cu", "picture_pred.cu", "picture_me.cu", "pack10.cu",
            # smaller-CU models (64 / 32 / 16 px): one translation unit of tcgen05 conv instantiations per CU size
            "cu_api.cu", "cu_net.cu", "cu_net_64.cu", "cu_net_32.cu", "cu_net_16.cu", "cu_stem.cu", "cu_head.cu"]
 LIB = os.path.join(HERE, "libmltcnn.so")

@@ -158,6 +158,8 @@ int run_network(mlt_cu_ctx *c, int n, const int16_t *d_orgpred, const int32_t *d
     if (c->fused && old_stem)
         CU(launch_cu_stem_umma(c->size, c->d_cus, n, secp<__half>(c, SEC_STEM_CONV1), secp<__half>(c, SEC_W_F16 + 0),
                                secp<float>(c, SEC_BIAS_FUSED + 0), c->act0q, c->act[1], c->cap, c->num_sms, s));
+    else if (c->fused && c->size == 16) // the composed stem with two CUs per MMA tile (stem5_cu16.cu)
+        CU(launch_cu16_stem5(c->d_cus, n, secp<__half>(c, SEC_STEM5_W), secp<float>(c, SEC_STEM5_CORR), c->act0q, c->act[1], c->cap, c->num_sms, s));
     else if (c->fused) // conv1 o layer0.0.conv1 composed into one 5x5 stride-2 conv (stem5_umma.cu)
         CU(launch_cu_stem5_umma(c->size, c->d_cus, n, secp<__half>(c, SEC_STEM5_W), secp<float>(c, SEC_STEM5_CORR), secp<float>(c, SEC_STEM5_CORR) + 704,
                                 c->act0q, c->act[1], c->cap, c->num_sms, s));
@@ -339,7 +341,9 @@ int mlt_cu_create(mlt_cu_ctx **out, const char *weights_path, int cuda_device, i
         CU(cu_conv_init(cu_size));
         CU(stem_umma_init());
         CU(stem5_umma_init());
-        c->fused = cu_size >= 32 && getenv("MLT_CU_UNFUSED") == nullptr; // a 16-px CU is smaller than one stem work unit
+        CU(stem5_cu16_init());
+        // every size runs a fused stem; the round-1 stem kernel (MLT_STEM_OLD=1) has no 16-px form (a 16-px CU is smaller than its work unit)
+        c->fused = (cu_size >= 32 || getenv("MLT_STEM_OLD") == nullptr) && getenv("MLT_CU_UNFUSED") == nullptr;
         // every activation is ONE strip over the whole batch: [plane][C/8][row][cap images][x][8] fp16
         c->lay[0] = ActLayout{cu_size, 32, 1, 0, c->cap};
         for (int li = 0; li < CU_NCONV; li++) c->lay[li + 1] = ActLayout{c->info[li].hout, c->info[li].cout, c->info[li].out_par, 0, c->cap};

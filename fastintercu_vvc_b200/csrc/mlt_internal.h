@@ -69,6 +69,11 @@ cudaError_t launch_stem5_umma(const CtuDev *ctus, int n, const __half *w /*SEC_S
 cudaError_t launch_cu_stem5_umma(int size, const CtuDev *cus, int n, const __half *w, const float *corrw, const float *bias, __half *act0q,
                                  __half *act1, int cap, int num_sms, cudaStream_t s);
 
+// ---- stem5_cu16.cu : the composed stem for the 16-px CU network (a tile = two CUs side by side, a work unit = four CUs)
+cudaError_t stem5_cu16_init();
+cudaError_t launch_cu16_stem5(const CtuDev *cus, int n, const __half *w, const float *corrw, __half *act0q, __half *act1, int cap, int num_sms,
+                              cudaStream_t s);
+
 // the same fused stem for the 64- / 32-px CU networks (strip-layout outputs; a 16-px CU is smaller than one work unit)
 cudaError_t launch_cu_stem_umma(int size, const CtuDev *cus, int n, const __half *w1, const __half *w0, const float *bias, __half *act0q,
                                 __half *act1, int cap, int num_sms, cudaStream_t s);
