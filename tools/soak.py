@@ -25,6 +25,12 @@ def run(name, pred, base, pq, nmax, pipelined):
             a = pred.collect().copy(); b = pred.collect().copy()
             assert a.tobytes() == b.tobytes(), (name, n, "pipelined pair differs")
             got = a
+        elif pipelined and iters % 5 == 1:  # CTU model: the 10-bit packed transport, blocking and pipelined
+            from fastintercu_vvc_b200.capi import pack10
+            pk = pack10(op)
+            got = pred.predict_batch_packed10(pk, q).copy()
+            pred.submit_batch_packed10(pk, q)
+            assert pred.collect().tobytes() == got.tobytes(), (name, n, "packed pipelined differs")
         else:
             got = pred.predict_batch_dense(op, q)
         if got.tobytes() != ref[idx].tobytes():
