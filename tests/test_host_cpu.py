@@ -315,3 +315,47 @@ def test_pack10_host_packer_roundtrip_and_range_check():
         assert L.mlt_pack10(y.ctypes.data, y.size, out.ctypes.data) == count
         with pytest.raises(ValueError):
             capi.pack10(y[None])
+
+
+def test_stem5_composite_is_the_two_reference_convs(sd):
+    """conv1 (arch.py:278, no BN / activation) followed by layer0.0.conv1 (3x3 stride 2, folded BN) == ONE 5x5 stride-2 conv of the
+    input minus the 1-D border terms at output row 0 / column 0 (pack_weights.stem5_composite), to float64 rounding; and the packed
+    tcgen05 operands hold exactly those weights (fp16-rounded, staging scale folded in) in the chunk layout stem5_umma.cu reads."""
+    import torch
+    import torch.nn.functional as F
+
+    w1 = sd["conv1.weight"]
+    w0f, b0f = pw.fold_bn(sd["layer0.0.conv1.weight"], sd, "layer0.0.bn1")
+    W5, Wtop, Wleft, Wc = pw.stem5_composite(w1, w0f)
+    x = torch.rand(2, 2, 32, 32, dtype=torch.float64, generator=torch.Generator().manual_seed(1))
+    ref = F.conv2d(F.conv2d(x, torch.from_numpy(w1).double(), padding=1), torch.from_numpy(w0f).double(), stride=2, padding=1)
+    z = F.conv2d(x, torch.from_numpy(W5), stride=2, padding=2)
+    xp = F.pad(x, (2, 2, 2, 2))
+    z[:, :, 0, :] -= F.conv1d(xp[:, :, 2, :], torch.from_numpy(Wtop), stride=2)
+    z[:, :, :, 0] -= F.conv1d(xp[:, :, :, 2], torch.from_numpy(Wleft), stride=2)
+    z[:, :, 0, 0] += x[:, :, 0, 0] @ torch.from_numpy(Wc).T
+    assert (z - ref).abs().max() < 1e-12
+    op, corr = pw.stem5_operands(w1, w0f)
+    assert op.shape == (7, 2, 32, 8) and op.dtype == np.float16 and corr.shape == (2 * 5 * 2 * 32 + 2 * 32,)
+    scale = float(pw.ALPHA) * 1024.0
+    for dy, dx, ch, co in ((0, 0, 0, 0), (4, 3, 1, 31), (2, 4, 0, 7), (1, 4, 1, 19)):
+        got = float(op[dy, 0, co, dx * 2 + ch]) if dx < 4 else float(op[dy, 1, co, ch])
+        assert abs(got - W5[co, ch, dy, dx] * scale) <= 2.0 ** -11 * abs(W5[co, ch, dy, dx] * scale) + 1e-7
+    assert not op[:5, 1, :, 2:].any() and not op[6, 1].any()  # unused K slots carry zero weights
+    assert float(op[5, 1, 3, 2 * 2 + 1]) == np.float16(w1[3, 1, 2, 2] * scale)  # conv1 quarter: MMA 5 chunk 1 = kernel row 2
+    assert np.allclose(corr[: 5 * 2 * 32].reshape(5, 2, 32), (Wtop * scale).transpose(2, 1, 0), rtol=1e-6)
+    secs = dict(pw.build_sections(sd))
+    assert secs[pw.SEC_STEM5_CORR].shape == (2 * 5 * 2 * 32 + 2 * 32 + 32,)  # ... + the stem kernel's own (bias-corrected) bias
+    assert np.abs(secs[pw.SEC_STEM5_CORR][-32:] - b0f).max() < 5e-3  # the correction is a small shift of the folded bias
+
+
+def test_bias_correction_is_the_mean_rounding_error():
+    """bias_correction == E[sum (w_q - w) x] for inputs whose per-tap means are the calibration means (exact for constant inputs)."""
+    rs = np.random.RandomState(0)
+    w = rs.standard_normal((8, 4, 3, 3)).astype(np.float32) * 0.1
+    q = pw.quantize_fp16_diffused(w)
+    mu = rs.uniform(0, 2, (4, 3, 3))
+    got = pw.bias_correction(w, q, mu)
+    want = ((q.astype(np.float64) - w.astype(np.float64)) * mu[None]).sum((1, 2, 3))
+    assert np.allclose(got, want, rtol=0, atol=1e-15)
+    assert np.abs(got).max() < 9 * 4 * 2.0 ** -11 * 0.5 * 2  # bounded by the fp16 rounding of 36 weights times the largest mean
