@@ -111,8 +111,12 @@ __global__ void __launch_bounds__(stem5::nthreads(NSTG), 2) stem5_umma_kernel(co
     const uint32_t tmem = *tmem_slot;
     const uint32_t sEP = smem_u32(smem + OFF_EP);
     const bool spin = (p.dbg & 128) != 0; // timing experiment: mbarrier.test_wait polling instead of try_wait
+    const bool lane0_poll = (p.dbg & 256) != 0; // timing experiment: one lane per warp polls, the others park at __syncwarp
     auto bwait = [&](uint64_t *bar, uint32_t parity) {
-        if (spin) mbar_wait_spin(bar, parity);
+        if (lane0_poll) {
+            if (lane == 0) mbar_wait(bar, parity);
+            __syncwarp();
+        } else if (spin) mbar_wait_spin(bar, parity);
         else mbar_wait(bar, parity);
     };
     griddep_launch_dependents(); // PDL: the prologue above overlapped the previous kernel's tail
@@ -124,6 +128,7 @@ __global__ void __launch_bounds__(stem5::nthreads(NSTG), 2) stem5_umma_kernel(co
         uint32_t *H = reinterpret_cast<uint32_t *>(smem + OFF_RAW + grp * RAW_BYTES);
         const int u_first = blockIdx.x + grp * gridDim.x, u_step = GROUPS * gridDim.x; // group g stages this CTA's units g, g + GROUPS, ...
         auto group_sync = [&]() { // named barrier of this group (immediate ids: a register id makes ptxas reserve all 16 barriers)
+            if (p.dbg & 1024) return; // timing experiment
             if (grp == 0) asm volatile("bar.sync 1, %0;" ::"n"(STG_THREADS) : "memory");
             else asm volatile("bar.sync 2, %0;" ::"n"(STG_THREADS) : "memory");
         };
@@ -208,8 +213,8 @@ __global__ void __launch_bounds__(stem5::nthreads(NSTG), 2) stem5_umma_kernel(co
             // arrival for use k can land while the epilogue still waits for use k - 1 -- the barrier is then in phase k + 1, whose
             // parity equals that of k - 1, the epilogue's parity wait never returns and the pipeline deadlocks (seen with two stager
             // groups from ~25 units per CTA on; with one group the stagers were always the slowest role, so it stayed latent).
-            bwait(&d_empty[buf], ((ul >> 1) & 1) ^ 1);
-            if ((oy0 == 0 || ox0 == 0) && st < 128) {
+            if (!(p.dbg & 512)) bwait(&d_empty[buf], ((ul >> 1) & 1) ^ 1);
+            if ((oy0 == 0 || ox0 == 0) && st < 128 && !(p.dbg & 512)) {
                 // border terms (see the header): slot ps < 16 = output (0, ox0 + ps), top; ps >= 16 = output (oy0 + ps - 16, 0), left
                 const int ps = st >> 2, cg = (st & 3) * 8;
                 const bool top = ps < 16;
