@@ -72,6 +72,23 @@ class ClockSampler:
         return sum(1 for r in self.rows if self.t0 is not None and self.t1 is not None and self.t0 <= r[-1] <= self.t1)
 
     def start(self):
+        # NVML polled every ~5 ms from a thread (a K-step timed region lasts ~0.1 s: nvidia-smi's 50 ms loop gives it 1-2 samples);
+        # nvidia-smi -lms as the fallback when NVML is not usable
+        self._halt = False
+        try:
+            import pynvml
+            import torch
+
+            pynvml.nvmlInit()
+            pr = torch.cuda.get_device_properties(self.index)
+            self._h = pynvml.nvmlDeviceGetHandleByPciBusId(f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0".encode())
+            self._nvml = pynvml
+            self.source = "nvml"
+            threading.Thread(target=self._pump_nvml, daemon=True).start()
+            return
+        except Exception:
+            self._nvml = None
+        self.source = "nvidia-smi"
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
@@ -80,11 +97,26 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _pump_nvml(self):
+        nv, h = self._nvml, self._h
+        bits = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        while not self._halt:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+                rs = get(h)
+                self.rows.append([str(sm), str(mx), "0"] + ["Active" if rs & b else "Not Active" for b, _ in bits] + [time.time()])
+            except Exception:
+                pass
+            time.sleep(0.005)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")] + [time.time()])
 
     def stop(self):
+        self._halt = True
         if self.proc:
             self.proc.terminate()
         sm, mx, reasons = [], 0, set()
@@ -98,7 +130,8 @@ class ClockSampler:
                         reasons.add(nm)
             except Exception:
                 pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm),
+                "source": getattr(self, "source", "nvidia-smi")}
 
 
 def synth_frames(n_ctus: int, seed: int):
