@@ -65,10 +65,34 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
         : "memory");
     return ok != 0;
 }
+// MLT_WAIT_MODE (build-time experiment, default 0): 1 = __nanosleep back-off between polls, 2 = try_wait with a suspend-time hint
+#ifndef MLT_WAIT_MODE
+#define MLT_WAIT_MODE 0
+#endif
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t *bar, uint32_t parity, uint32_t ns)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
+#if MLT_WAIT_MODE == 1
+    if (mbar_try_wait(bar, parity)) return;
+    while (!mbar_try_wait(bar, parity)) __nanosleep(40);
+#elif MLT_WAIT_MODE == 2
+    while (!mbar_try_wait_hint(bar, parity, 2000)) {
+    }
+#else
     while (!mbar_try_wait(bar, parity)) {
     }
+#endif
 }
 // non-suspending poll (mbarrier.test_wait): lower wake-up latency than try_wait, at the price of issue slots while spinning
 __device__ __forceinline__ bool mbar_test_wait(uint64_t *bar, uint32_t parity)

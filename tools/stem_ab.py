@@ -28,12 +28,26 @@ def child(blob):
         for _ in range(60): step()
         e1.record(st); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 60
+        sus = lat = 0.0
+        if os.environ.get("STEM_AB_SUSTAIN"):  # power-capped regime: ~3 s back to back, then the one-CTU latency
+            e0.record(st)
+            for _ in range(600): step()
+            e1.record(st); torch.cuda.synchronize()
+            sus = e0.elapsed_time(e1) / 600
+            one = lambda: p.predict_batch_device(1, d_in.data_ptr(), d_pq.data_ptr(), d_out.data_ptr(), st.cuda_stream)
+            for _ in range(20): one()
+            torch.cuda.synchronize()
+            e0.record(st)
+            for _ in range(200): one()
+            e1.record(st); torch.cuda.synchronize()
+            lat = e0.elapsed_time(e1) / 200 * 1000
         p.set_profiling(True)
         prof = np.zeros(18)
         for _ in range(5):
             step(); torch.cuda.synchronize(); prof += p.get_profile()
         prof /= 5
-    print(f"step {ms:.3f} ms ({n / ms:.0f} k CTU/s)  stem {prof[0]:.3f} ms  convs {prof[2:17].sum():.3f} ms")
+    print(f"step {ms:.3f} ms ({n / ms:.0f} k CTU/s)  stem {prof[0]:.3f} ms  convs {prof[2:17].sum():.3f} ms" +
+          (f"  sustained {sus:.3f} ms ({n / sus:.0f} k CTU/s)  one CTU {lat:.1f} us" if sus else ""))
 
 if __name__ == "__main__":
     if len(sys.argv) > 1:
