@@ -7,8 +7,9 @@
 // (EP[col parity][row parity][pair][10 entry rows][2 CUs][10 entries][8 fp16]: SBO = 10 entries, LBO = 2 entries as in stem5_umma).
 // Work unit = 4 CUs = two pairs = two tiles for the composite conv + two for the conv1 quarter: the same 14 MMAs, 128 TMEM columns
 // and barrier protocol per unit as the big kernel.  Every CU has a top row and a left column, so every unit carries the fp32
-// border terms (pack_weights.stem5_composite) for 4 x (8 + 8) pixels.  With this kernel the 16-px network no longer writes and
+// border terms (pack_weights.stem5_composite) for 4 x (8 + 8) pixels -- evaluated by a border warp of their own, as in stem5_umma.cu.  With this kernel the 16-px network no longer writes and
 // re-reads conv1's 16 x 16 x 32 activation (16 KB per CU each way): it goes from 23 to 22 launches like the 64- / 32-px networks.
+#include <cstdlib>
 #include "mlt_internal.h"
 #include "ptx.cuh"
 
@@ -17,7 +18,8 @@ namespace mlt {
 namespace stem16 {
 constexpr int NEPI = 8, NSTG = 4;
 constexpr int W_MMA = NEPI, W_STG = NEPI + 1;
-constexpr int NTHREADS = (NEPI + 1 + NSTG) * 32;           // 416
+constexpr int W_BRD = NEPI + 1 + NSTG;                     // the border warp
+constexpr int NTHREADS = (NEPI + 1 + NSTG + 1) * 32;       // 448
 constexpr int CUS = 4;                                     // CUs per work unit (two pairs)
 constexpr int ER = 10, EC = 10, ROWP = 2 * EC;             // entry rows per pair; entries per CU per row; entries per row (two CUs)
 constexpr int EP_ARR = 2 * ER * ROWP * 16;                 // one (col parity, row parity) array: [pair][ER][ROWP] entries = 6,400 B
@@ -29,12 +31,12 @@ constexpr int CORRW_FLOATS = 2 * 5 * 2 * 32 + 2 * 32;      // Wtop, Wleft [e][ch
 constexpr int CORR_BYTES = CUS * 16 * 32 * 4;              // per buffer: per CU 8 top + 8 left pixels x 32 channels, fp32
 constexpr int OFF_EP = 0;
 constexpr int OFF_H = OFF_EP + 2 * EP_BYTES;
-constexpr int OFF_W = (OFF_H + H_BYTES + 127) / 128 * 128;
+constexpr int OFF_W = (OFF_H + 2 * H_BYTES + 127) / 128 * 128; // two H planes (alternate units; border-warp mode)
 constexpr int OFF_CORRW = OFF_W + W_BYTES;
 constexpr int OFF_CORR = OFF_CORRW + CORRW_FLOATS * 4;
 constexpr int OFF_BIAS = OFF_CORR + 2 * CORR_BYTES;
 constexpr int OFF_BAR = OFF_BIAS + 32 * 4;
-constexpr int NBAR = 10;
+constexpr int NBAR = 14;
 constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16;
 constexpr int TMEM_COLS = 256;
@@ -49,6 +51,8 @@ struct Stem16Params {
     __half *act0q;       // conv1 at even rows / columns: strip [4 chunks][8 rows][cap][8][8]
     __half *act1;        // layer0.0.conv1 output, same layout
     int n, cap;
+    int early;           // MLT_STEM16_EARLY=1 (experiment, results valid): hand EP to the issuer before the border terms
+    int bw;              // border-warp mode (MLT_STEM16_BW): the fp32 border terms run on their own warp, off the stagers' chain
 };
 
 __global__ void __launch_bounds__(stem16::NTHREADS, 2) stem5_cu16_kernel(const Stem16Params p)
@@ -56,7 +60,7 @@ __global__ void __launch_bounds__(stem16::NTHREADS, 2) stem5_cu16_kernel(const S
     using namespace stem16;
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + OFF_BAR);
-    uint64_t *ep_full = bars, *ep_empty = bars + 2, *d_full = bars + 4, *d_empty = bars + 6, *corr_full = bars + 8;
+    uint64_t *ep_full = bars, *ep_empty = bars + 2, *d_full = bars + 4, *d_empty = bars + 6, *corr_full = bars + 8, *h_full = bars + 10, *h_empty = bars + 12;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_TMEM);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int total_units = (p.n + CUS - 1) / CUS;
@@ -67,7 +71,8 @@ __global__ void __launch_bounds__(stem16::NTHREADS, 2) stem5_cu16_kernel(const S
         for (int i = 0; i < 2; i++) {
             mbar_init(&ep_full[i], NSTG); mbar_init(&ep_empty[i], 1);
             mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], NEPI);
-            mbar_init(&corr_full[i], NSTG);
+            mbar_init(&corr_full[i], p.bw ? 1 : NSTG);
+            mbar_init(&h_full[i], NSTG); mbar_init(&h_empty[i], 1);
         }
         mbar_fence_init();
     }
@@ -75,7 +80,7 @@ __global__ void __launch_bounds__(stem16::NTHREADS, 2) stem5_cu16_kernel(const S
     for (int i = tid; i < CORRW_FLOATS; i += NTHREADS) reinterpret_cast<float *>(smem + OFF_CORRW)[i] = __ldg(p.corrw + i);
     if (tid < 32) reinterpret_cast<float *>(smem + OFF_BIAS)[tid] = __ldg(p.corrw + CORRW_FLOATS + tid);
     // EP slots no stager writes meet zero weights only; the margins of H ARE the CUs' zero padding and are never written again
-    for (int i = tid; i < (2 * EP_BYTES + H_BYTES) / 16; i += NTHREADS) reinterpret_cast<uint4 *>(smem + OFF_EP)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < (2 * EP_BYTES + 2 * H_BYTES) / 16; i += NTHREADS) reinterpret_cast<uint4 *>(smem + OFF_EP)[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async_smem();
     if (warp == W_MMA) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
     tc_fence_before();
@@ -86,7 +91,63 @@ __global__ void __launch_bounds__(stem16::NTHREADS, 2) stem5_cu16_kernel(const S
     griddep_launch_dependents();
     griddep_wait();
 
-    if (warp >= W_STG) {
+    if (warp == W_BRD) {
+        // ======================= border warp: the fp32 border terms of every unit (4 CUs x (8 top + 8 left) pixels x 32 channels)
+        if (p.bw) {
+            const float *cw = reinterpret_cast<const float *>(smem + OFF_CORRW);
+            const int my_units = total_units > (int)blockIdx.x ? (total_units - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+            const int px = lane >> 2, cg = (lane & 3) * 8;
+            for (int v = 0; v < my_units; v++) {
+                const uint32_t buf = v & 1;
+                const uint32_t *Hp = reinterpret_cast<const uint32_t *>(smem + OFF_H + buf * H_BYTES);
+                // both waits every unit: no producer of this pipeline may run more than ONE phase ahead of a parity waiter
+                mbar_wait(&h_full[buf], (v >> 1) & 1);
+                mbar_wait(&d_empty[buf], ((v >> 1) & 1) ^ 1); // the epilogue two units ago is done with corr[buf]
+                float *corr = reinterpret_cast<float *>(smem + OFF_CORR + buf * CORR_BYTES);
+#pragma unroll 1
+                for (int side = 0; side < 2; side++) {
+                    const bool top = side == 0;
+                    const float *wv = cw + (top ? 0 : 5 * 2 * 32);
+                    float acc[CUS][8];
+#pragma unroll
+                    for (int c = 0; c < CUS; c++)
+#pragma unroll
+                        for (int k = 0; k < 8; k++) acc[c][k] = 0.0f;
+#pragma unroll
+                    for (int e = 0; e < 5; e++) {
+                        const float4 *w0 = reinterpret_cast<const float4 *>(wv + (e * 2 + 0) * 32 + cg), *w1 = reinterpret_cast<const float4 *>(wv + (e * 2 + 1) * 32 + cg);
+                        const float4 a0 = w0[0], a1 = w0[1], b0 = w1[0], b1 = w1[1];
+                        const float wo[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, wr[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                        // top: in(0, 2 j - 2 + e) = H[2][2 j + 6 + e];  left: in(2 i - 2 + e, 0) = H[2 i + e][8]
+                        const int hidx = top ? 2 * HC + 2 * px + 6 + e : (2 * px + e) * HC + 8;
+#pragma unroll
+                        for (int c = 0; c < CUS; c++) {
+                            const float2 xv = __half22float2(*reinterpret_cast<const __half2 *>(Hp + c * HCU + hidx));
+#pragma unroll
+                            for (int k = 0; k < 8; k++) acc[c][k] = fmaf(wo[k], xv.x, fmaf(wr[k], xv.y, acc[c][k]));
+                        }
+                    }
+                    if (!top && px == 0) { // conv1(-1, -1)'s share sits in both terms of output (0, 0): take it out of the left one
+                        const float *wc = cw + 2 * 5 * 2 * 32;
+#pragma unroll
+                        for (int c = 0; c < CUS; c++) {
+                            const float2 xv = __half22float2(*reinterpret_cast<const __half2 *>(Hp + c * HCU + 2 * HC + 8));
+#pragma unroll
+                            for (int k = 0; k < 8; k++) acc[c][k] -= fmaf(wc[cg + k], xv.x, wc[32 + cg + k] * xv.y);
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < CUS; c++) {
+                        float4 *dst = reinterpret_cast<float4 *>(corr + (c * 16 + side * 8 + px) * 32 + cg);
+                        dst[0] = make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
+                        dst[1] = make_float4(acc[c][4], acc[c][5], acc[c][6], acc[c][7]);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(&corr_full[buf]); mbar_arrive(&h_empty[buf]); }
+            }
+        }
+    } else if (warp >= W_STG) {
         // ======================= stagers: one 8-sample vector of org / pred per thread and unit -> H -> EP (+ border terms)
         const int st = tid - W_STG * 32; // 0..127
         uint32_t *H = reinterpret_cast<uint32_t *>(smem + OFF_H);
@@ -120,7 +181,14 @@ __global__ void __launch_bounds__(stem16::NTHREADS, 2) stem5_cu16_kernel(const S
         const float *cw = reinterpret_cast<const float *>(smem + OFF_CORRW);
         uint32_t ul = 0;
         for (int u = blockIdx.x; u < total_units; u += gridDim.x, ul++) {
-            asm volatile("bar.sync 1, 128;" ::: "memory"); // every stager is done reading the previous unit's H
+            if (p.bw) {
+                // two H planes: the plane of unit ul - 2 is free once the border warp is done with it (every stager passed the barrier
+                // below in unit ul - 1, i.e. finished its own gather of unit ul - 2)
+                H = reinterpret_cast<uint32_t *>(smem + OFF_H + (ul & 1) * H_BYTES);
+                mbar_wait(&h_empty[ul & 1], ((ul >> 1) & 1) ^ 1);
+            } else {
+                asm volatile("bar.sync 1, 128;" ::: "memory"); // every stager is done reading the previous unit's H
+            }
             {
                 const uint32_t ow[4] = {vo.x, vo.y, vo.z, vo.w}, pw[4] = {vp.x, vp.y, vp.z, vp.w};
                 uint32_t hv[8];
@@ -138,6 +206,7 @@ __global__ void __launch_bounds__(stem16::NTHREADS, 2) stem5_cu16_kernel(const S
                 dst[1] = make_uint4(hv[4], hv[5], hv[6], hv[7]);
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (p.bw && lane == 0) mbar_arrive(&h_full[ul & 1]); // H is complete: the border warp may start
             if (u + (int)gridDim.x < total_units) load_vec(u + gridDim.x, vo, vp); // prefetch: lands while we gather
             const uint32_t buf = ul & 1;
             mbar_wait(&ep_empty[buf], ((ul >> 1) & 1) ^ 1);
@@ -154,6 +223,12 @@ __global__ void __launch_bounds__(stem16::NTHREADS, 2) stem5_cu16_kernel(const S
             }
             // a producer may run at most one phase ahead of a parity waiter (stem5_umma.cu): the epilogue of the unit that used this
             // buffer two units ago must be done before corr[buf] is rewritten and corr_full arrives again
+            if (p.early) {
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ep_full[buf]);
+            }
+            if (p.bw) continue;
             mbar_wait(&d_empty[buf], ((ul >> 1) & 1) ^ 1);
             {
                 // border terms: slot = st >> 1 -> CU (slot >> 4), top row (bit 3 clear) / left column (set), pixel slot & 7; 16 channels per thread
@@ -182,9 +257,12 @@ __global__ void __launch_bounds__(stem16::NTHREADS, 2) stem5_cu16_kernel(const S
 #pragma unroll
                 for (int k = 0; k < 4; k++) dst[k] = make_float4(acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]);
             }
-            fence_proxy_async_smem();
+            if (!p.early) fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) { mbar_arrive(&ep_full[buf]); mbar_arrive(&corr_full[buf]); }
+            if (lane == 0) {
+                if (!p.early) mbar_arrive(&ep_full[buf]);
+                mbar_arrive(&corr_full[buf]);
+            }
         }
     } else if (warp == W_MMA) {
         // ======================= MMA issuer: per pair of CUs 5 MMAs (composite 5x5 stride-2 conv) + 2 MMAs (conv1 at even positions)
@@ -298,7 +376,9 @@ cudaError_t launch_cu16_stem5(const CtuDev *cus, int n, const __half *w, const f
                               cudaStream_t s)
 {
     if (n <= 0) return cudaSuccess;
-    Stem16Params p{cus, w, corrw, act0q, act1, n, cap};
+    static const int early = getenv("MLT_STEM16_EARLY") ? atoi(getenv("MLT_STEM16_EARLY")) : 0;
+    static const int bw = getenv("MLT_STEM16_BW") ? atoi(getenv("MLT_STEM16_BW")) != 0 : 1; // default on; 0 = border terms on the stagers (A/B)
+    Stem16Params p{cus, w, corrw, act0q, act1, n, cap, early || bw, bw};
     const int units = (n + stem16::CUS - 1) / stem16::CUS, g = 2 * num_sms;
     return launch_pdl(stem5_cu16_kernel, dim3(units < g ? units : g), dim3(stem16::NTHREADS), stem16::SMEM_BYTES, s, p);
 }

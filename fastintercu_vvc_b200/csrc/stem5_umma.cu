@@ -8,7 +8,7 @@
 // kept it on chip but still spent 60 MMAs and 196 KB of TMEM reads per 16x16 outputs on it; this kernel spends 14 and 64 KB).
 // The only place the composition is not exact is layer0.0.conv1's own zero padding: at output row 0 / column 0 it replaces
 // conv1's outputs at row / column -1 by zeros, whereas W5 sees conv1's (non-zero) values there.  Those terms are 5-tap
-// 1-D filters over input row 0 / column 0 (pack_weights.stem5_composite: Wtop, Wleft, Wc); the stager warps evaluate them on
+// 1-D filters over input row 0 / column 0 (pack_weights.stem5_composite: Wtop, Wleft, Wc); a border warp evaluates them on
 // the CUDA cores for the 16 + 16 border pixels of a border unit and the epilogue subtracts them (fp32).
 // layer0.0's shortcut reads conv1 at the even rows / columns (1x1 stride 2): that quarter is still produced here, as a 3x3
 // stride-2 conv of the input (K = 18 -> two K=16 MMAs), and stored for layer0.0.conv2's extra operand as before.
@@ -19,8 +19,9 @@
 // fp16; the weights carry (float)(1/1023) * 2^10).  Output pixel (i, j) then finds kernel row dy of W5 at entry
 // (i + dy/2, j) and (i + dy/2, j + 2) of array (0, dy & 1): SBO = one entry row, LBO = two entries -- five MMAs per tile, no
 // index math; conv1-at-even-positions reads arrays (1, *) the same way.
-// Pipeline per CTA (2 per SM, 13 warps): 4 stager warps (int16 -> H -> EP, border terms), 1 MMA issuer, 8 epilogue warps
-// (lane quadrant x tile half).  TMEM: 2 buffers x (2 x 32 columns W5 result + 2 x 32 columns conv1 quarter) = 256 columns.
+// Pipeline per CTA (2 per SM, 14 warps): 4 stager warps (int16 -> H -> EP), 1 MMA issuer, 8 epilogue warps (lane quadrant x
+// tile half), 1 border warp (the fp32 border terms from the unit's H plane -- two planes, alternate units -- into corr[buf]; on the
+// stagers they were ~15 % of the chain that bounds the kernel: stem 0.757 -> 0.672 ms per 3840 CTUs; MLT_STEM5_BW=0 puts them back).  TMEM: 2 buffers x (2 x 32 columns W5 result + 2 x 32 columns conv1 quarter) = 256 columns.
 #include "mlt_internal.h"
 #include "ptx.cuh"
 
@@ -29,7 +30,7 @@ namespace mlt {
 namespace stem5 {
 constexpr int NEPI = 8;
 constexpr int W_EPI = 0, W_MMA = NEPI, W_STG = NEPI + 1;
-__host__ __device__ constexpr int nthreads(int nstg) { return (NEPI + 1 + nstg) * 32; } // 416 with 4 stager warps
+__host__ __device__ constexpr int nthreads(int nstg) { return (NEPI + 1 + nstg + 1) * 32; } // 448 with 4 stager warps: + the border warp
 constexpr int PE = 18, EP_ROWS = 18;
 constexpr int EP_ARR = EP_ROWS * PE * 16;                  // one (col parity, row parity) array: 324 entries
 constexpr int EP_BYTES = 4 * EP_ARR;                       // 20,736
@@ -40,12 +41,13 @@ constexpr int CORRW_FLOATS = 2 * 5 * 2 * 32 + 2 * 32;      // SEC_STEM5_CORR: Wt
 constexpr int CORR_BYTES = 32 * 32 * 4;                    // per buffer: 16 top + 16 left border pixels x 32 channels, fp32
 constexpr int OFF_EP = 0;
 constexpr int OFF_RAW = OFF_EP + 2 * EP_BYTES;
-constexpr int OFF_W = (OFF_RAW + 2 * RAW_BYTES + 127) / 128 * 128; // two H planes: one per stager group
+constexpr int NPLANES = 4;                                // H planes: two (alternate units) per stager group
+constexpr int OFF_W = (OFF_RAW + NPLANES * RAW_BYTES + 127) / 128 * 128;
 constexpr int OFF_CORRW = OFF_W + W_BYTES;
 constexpr int OFF_CORR = OFF_CORRW + CORRW_FLOATS * 4;
 constexpr int OFF_BIAS = OFF_CORR + 2 * CORR_BYTES;
 constexpr int OFF_BAR = OFF_BIAS + 32 * 4;
-constexpr int NBAR = 10;
+constexpr int NBAR = 10 + 2 * NPLANES;
 constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16;
 constexpr int TMEM_COLS = 256;
@@ -64,6 +66,7 @@ struct Stem5Params {
     __half *act1;        // layer0.0.conv1 output
     int n;
     int cap;             // strip layouts (S < 128): images per strip
+    int bw;              // border-warp mode (MLT_STEM5_BW): the fp32 border terms run on their own warp, off the stagers' chain
     int dbg;             // MLT_STEM5_DBG (timing experiments only, results invalid): 1 no global stores, 2 no global loads, 4 no EP gather
 };
 
@@ -85,6 +88,8 @@ __global__ void __launch_bounds__(stem5::nthreads(NSTG), 2) stem5_umma_kernel(co
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + OFF_BAR);
     uint64_t *ep_full = bars, *ep_empty = bars + 2, *d_full = bars + 4, *d_empty = bars + 6, *corr_full = bars + 8;
+    uint64_t *h_full = bars + 10, *h_empty = bars + 10 + NPLANES;
+    constexpr int W_BRD = NEPI + 1 + NSTG; // the border warp
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_TMEM);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -94,8 +99,9 @@ __global__ void __launch_bounds__(stem5::nthreads(NSTG), 2) stem5_umma_kernel(co
         for (int i = 0; i < 2; i++) {
             mbar_init(&ep_full[i], NSTG / GROUPS); mbar_init(&ep_empty[i], 1);
             mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], NEPI);
-            mbar_init(&corr_full[i], NSTG / GROUPS);
+            mbar_init(&corr_full[i], p.bw ? 1 : NSTG / GROUPS);
         }
+        for (int i = 0; i < NPLANES; i++) { mbar_init(&h_full[i], NSTG / GROUPS); mbar_init(&h_empty[i], 1); }
         mbar_fence_init();
     }
     for (int i = tid; i < W_BYTES / 16; i += NTHREADS) reinterpret_cast<uint4 *>(smem + OFF_W)[i] = __ldg(reinterpret_cast<const uint4 *>(p.w) + i);
@@ -122,10 +128,66 @@ __global__ void __launch_bounds__(stem5::nthreads(NSTG), 2) stem5_umma_kernel(co
     griddep_launch_dependents(); // PDL: the prologue above overlapped the previous kernel's tail
     griddep_wait();
 
-    if (warp >= W_STG) {
+    if (warp == W_BRD) {
+        // ======================= border warp: the fp32 border terms of every unit of this CTA, from the unit's H plane into corr[buf]
+        if (p.bw) {
+            const float *cw = reinterpret_cast<const float *>(smem + OFF_CORRW);
+            const int my_units = total_units > (int)blockIdx.x ? (total_units - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+            const int sb = lane >> 2, cg = (lane & 3) * 8; // pixel slots sb, sb + 8 of the top row / left column; 8 channels
+            for (int v = 0; v < my_units; v++) {
+                const int u = blockIdx.x + v * gridDim.x, oy0 = ((u % UPI) / UW) * 16, ox0 = ((u % UPI) % UW) * 16;
+                const int it = v / GROUPS, plane = (v % GROUPS) * 2 + (it & 1);
+                const uint32_t buf = v & 1;
+                const uint32_t *H = reinterpret_cast<const uint32_t *>(smem + OFF_RAW + plane * RAW_BYTES);
+                // both waits every unit: no producer of this pipeline may run more than ONE phase ahead of a parity waiter
+                mbar_wait(&h_full[plane], (it >> 1) & 1);
+                mbar_wait(&d_empty[buf], ((v >> 1) & 1) ^ 1); // the epilogue two units ago is done with corr[buf]
+                float *corr = reinterpret_cast<float *>(smem + OFF_CORR + buf * CORR_BYTES);
+#pragma unroll 1
+                for (int side = 0; side < 2; side++) {
+                    const bool top = side == 0;
+                    if (top ? oy0 != 0 : ox0 != 0) continue;
+                    const float *wv = cw + (top ? 0 : 5 * 2 * 32);
+                    // pixel slots sb and sb + 8: output (0, ox0 + px) of the top row / (oy0 + px, 0) of the left column
+                    float acc[2][8];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) acc[0][k] = acc[1][k] = 0.0f;
+#pragma unroll
+                    for (int e = 0; e < 5; e++) {
+                        // top: in(0, 2*(ox0+j) - 2 + e) = H[2][2j + 6 + e];  left: in(2*(oy0+i) - 2 + e, 0) = H[2i + e][8]
+                        const float4 *w0 = reinterpret_cast<const float4 *>(wv + (e * 2 + 0) * 32 + cg), *w1 = reinterpret_cast<const float4 *>(wv + (e * 2 + 1) * 32 + cg);
+                        const float4 a0 = w0[0], a1 = w0[1], b0 = w1[0], b1 = w1[1];
+                        const float wo[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, wr[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                        for (int r = 0; r < 2; r++) {
+                            const int px = sb + 8 * r;
+                            const int hidx = top ? 2 * RAW_COLS + 2 * px + 6 + e : (2 * px + e) * RAW_COLS + 8;
+                            const float2 xv = __half22float2(*reinterpret_cast<const __half2 *>(H + hidx));
+#pragma unroll
+                            for (int k = 0; k < 8; k++) acc[r][k] = fmaf(wo[k], xv.x, fmaf(wr[k], xv.y, acc[r][k]));
+                        }
+                    }
+                    if (!top && sb == 0 && oy0 == 0) { // conv1(-1, -1)'s share sits in both terms of output (0, 0): take it out of this one
+                        const float2 xv = __half22float2(*reinterpret_cast<const __half2 *>(H + 2 * RAW_COLS + 8));
+                        const float *wc = cw + 2 * 5 * 2 * 32;
+#pragma unroll
+                        for (int k = 0; k < 8; k++) acc[0][k] -= fmaf(wc[cg + k], xv.x, wc[32 + cg + k] * xv.y);
+                    }
+#pragma unroll
+                    for (int r = 0; r < 2; r++) {
+                        float4 *dst = reinterpret_cast<float4 *>(corr + ((top ? 0 : 16) + sb + 8 * r) * 32 + cg);
+                        dst[0] = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+                        dst[1] = make_float4(acc[r][4], acc[r][5], acc[r][6], acc[r][7]);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(&corr_full[buf]); mbar_arrive(&h_empty[plane]); }
+            }
+        }
+    } else if (warp >= W_STG) {
         // ======================= stagers: int16 window -> fp16 {org, res} plane H -> expanded, parity-split operand EP (+ border terms)
         const int grp = (tid - W_STG * 32) / STG_THREADS, st = (tid - W_STG * 32) % STG_THREADS; // stager group; thread within the group
-        uint32_t *H = reinterpret_cast<uint32_t *>(smem + OFF_RAW + grp * RAW_BYTES);
+        uint32_t *H = reinterpret_cast<uint32_t *>(smem + OFF_RAW + grp * 2 * RAW_BYTES);
         const int u_first = blockIdx.x + grp * gridDim.x, u_step = GROUPS * gridDim.x; // group g stages this CTA's units g, g + GROUPS, ...
         auto group_sync = [&]() { // named barrier of this group (immediate ids: a register id makes ptxas reserve all 16 barriers)
             if (p.dbg & 1024) return; // timing experiment
@@ -172,7 +234,14 @@ __global__ void __launch_bounds__(stem5::nthreads(NSTG), 2) stem5_umma_kernel(co
             const int oy0 = ((u % UPI) / UW) * 16, ox0 = ((u % UPI) % UW) * 16;
             // this CTA's unit index ul = it * GROUPS + grp uses buffer ul & 1 for the (ul >> 1)-th time
             const uint32_t ul = it * GROUPS + grp;
-            group_sync(); // every stager of the group is done reading the previous unit's H
+            if (p.bw) {
+                // two H planes per group: the plane of unit it - 2 is free once the border warp is done with it (every stager passed
+                // the barrier below in unit it - 1, i.e. finished its own gather of unit it - 2)
+                H = reinterpret_cast<uint32_t *>(smem + OFF_RAW + (grp * 2 + (it & 1)) * RAW_BYTES);
+                bwait(&h_empty[grp * 2 + (it & 1)], ((it >> 1) & 1) ^ 1);
+            } else {
+                group_sync(); // every stager of the group is done reading the previous unit's H
+            }
 #pragma unroll
             for (int k = 0; k < VPT; k++) {
                 const int i = st + k * STG_THREADS;
@@ -194,6 +263,7 @@ __global__ void __launch_bounds__(stem5::nthreads(NSTG), 2) stem5_umma_kernel(co
                 }
             }
             group_sync();
+            if (p.bw && lane == 0) mbar_arrive(&h_full[grp * 2 + (it & 1)]); // H is complete: the border warp may start
             if (u + u_step < total_units) load_window(u + u_step, vo, vp); // prefetch: lands while we gather
             const uint32_t buf = ul & 1;
             bwait(&ep_empty[buf], ((ul >> 1) & 1) ^ 1);
@@ -213,6 +283,13 @@ __global__ void __launch_bounds__(stem5::nthreads(NSTG), 2) stem5_umma_kernel(co
             // arrival for use k can land while the epilogue still waits for use k - 1 -- the barrier is then in phase k + 1, whose
             // parity equals that of k - 1, the epilogue's parity wait never returns and the pipeline deadlocks (seen with two stager
             // groups from ~25 units per CTA on; with one group the stagers were always the slowest role, so it stayed latent).
+            const bool early = p.bw || (p.dbg & 2048) != 0; // dbg 2048: experiment (results valid), EP goes to the issuer BEFORE the border terms
+            if (early) {
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ep_full[buf]);
+            }
+            if (p.bw) continue;
             if (!(p.dbg & 512)) bwait(&d_empty[buf], ((ul >> 1) & 1) ^ 1);
             if ((oy0 == 0 || ox0 == 0) && st < 128 && !(p.dbg & 512)) {
                 // border terms (see the header): slot ps < 16 = output (0, ox0 + ps), top; ps >= 16 = output (oy0 + ps - 16, 0), left
@@ -242,9 +319,12 @@ __global__ void __launch_bounds__(stem5::nthreads(NSTG), 2) stem5_umma_kernel(co
                     dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
                 }
             }
-            fence_proxy_async_smem();
+            if (!early) fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) { mbar_arrive(&ep_full[buf]); mbar_arrive(&corr_full[buf]); }
+            if (lane == 0) {
+                if (!early) mbar_arrive(&ep_full[buf]);
+                mbar_arrive(&corr_full[buf]);
+            }
         }
     } else if (warp == W_MMA) {
         // ======================= MMA issuer: 2 halves x (5 MMAs of the composite 5x5 stride-2 conv + 2 MMAs of conv1 at even positions)
@@ -362,6 +442,12 @@ static int stem5_dbg()
     return v;
 }
 
+static int stem5_bw()
+{
+    static const int v = getenv("MLT_STEM5_BW") ? atoi(getenv("MLT_STEM5_BW")) : 1; // default on; 0 = border terms on the stagers (A/B)
+    return v != 0;
+}
+
 static int stem5_nstg()
 {
     static const int v = getenv("MLT_STEM5_STAGERS") ? atoi(getenv("MLT_STEM5_STAGERS")) : STEM5_DEFAULT_STAGERS; // measurement override: 4 / 6 / 8
@@ -406,7 +492,7 @@ cudaError_t launch_stem5_umma(const CtuDev *ctus, int n, const __half *w, const 
                               int num_sms, cudaStream_t s)
 {
     if (n <= 0) return cudaSuccess;
-    Stem5Params p{ctus, w, corrw, bias, act0q, act1, n, 0, stem5_dbg()};
+    Stem5Params p{ctus, w, corrw, bias, act0q, act1, n, 0, stem5_bw(), stem5_dbg()};
     return stem5_launch<128>(p, stem5_grid(n * 16, num_sms), s);
 }
 
@@ -415,7 +501,7 @@ cudaError_t launch_cu_stem5_umma(int size, const CtuDev *cus, int n, const __hal
                                  __half *act1, int cap, int num_sms, cudaStream_t s)
 {
     if (n <= 0) return cudaSuccess;
-    Stem5Params p{cus, w, corrw, bias, act0q, act1, n, cap, stem5_dbg()};
+    Stem5Params p{cus, w, corrw, bias, act0q, act1, n, cap, stem5_bw(), stem5_dbg()};
     const int grid = stem5_grid(n * (size / 32) * (size / 32), num_sms);
     if (size == 64) return stem5_launch<64>(p, grid, s);
     if (size == 32) return stem5_launch<32>(p, grid, s);

@@ -371,3 +371,40 @@ def test_cu_picture_prepass_equals_the_dense_batch(size):
             assert e.value.rc == -7  # MLT_E_BATCH
     finally:
         os.unlink(path)
+
+
+@pytest.mark.parametrize("size", ref_arch.CU_SIZES)
+def test_cu_stem_border_warp_equals_border_terms_on_the_stagers(size, tmp_path):
+    """The composed stem's fp32 border terms run on a warp of their own (stem5_umma.cu / stem5_cu16.cu, default) or on the stager
+    warps (MLT_STEM5_BW=0 / MLT_STEM16_BW=0): the same expressions in the same order, so every logit must be bit-equal -- over enough
+    CUs that each CTA runs many units (the hand-off barriers h_full / h_empty / corr_full wrap many times).  Subprocesses under a
+    hard timeout: a barrier mistake shows as a hang."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    n = {64: 1500, 32: 6000, 16: 40000}[size]
+    code = f"""
+import numpy as np, sys, tempfile, os
+sys.path.insert(0, {root!r})
+import fastintercu_vvc_b200 as pkg
+from oracle import ref_arch
+size, n = {size}, {n}
+path = tempfile.NamedTemporaryFile(suffix=".mltw", delete=False).name
+pkg.write_cu_blob(ref_arch.make_cu_state_dict(10, size), size, path)
+base, pq = ref_arch.synth_cus(50, size, 31)
+idx = np.arange(n) % 50
+with pkg.MltCuPredictor(path, size, device=0, max_batch=n) as p:
+    for _ in range(2):
+        big = p.predict_batch_dense(np.ascontiguousarray(base[idx]), np.ascontiguousarray(pq[idx]))
+os.unlink(path)
+open(sys.argv[1], "wb").write(big.tobytes())
+"""
+    got = {}
+    for bw in ("1", "0"):
+        out = str(tmp_path / f"r{bw}.bin")
+        e = dict(os.environ, MLT_STEM5_BW=bw, MLT_STEM16_BW=bw)
+        r = subprocess.run(["timeout", "-s", "KILL", "150", sys.executable, "-c", code, out], env=e, capture_output=True, text=True)
+        assert r.returncode == 0, f"bw={bw} rc {r.returncode} (killed by the timeout = the pipeline hung): {r.stderr[-400:]}"
+        got[bw] = open(out, "rb").read()
+    assert len(got["1"]) > 0 and got["1"] == got["0"]

@@ -863,8 +863,14 @@ with pkg.MltPredictor({blob!r}, device=0, max_batch=900) as p:
     for _ in range(3):
         big = p.predict_batch_dense(np.ascontiguousarray(o[idx]), np.ascontiguousarray(q[idx]))
 print(bool(np.array_equal(big["logits"].view(np.uint32), small["logits"][idx].view(np.uint32))))
+np.save(sys.argv[1], big["logits"])
 """
-    e = dict(os.environ, MLT_STEM5_STAGERS=stagers)
-    r = subprocess.run(["timeout", "-s", "KILL", "120", sys.executable, "-c", code], env=e, capture_output=True, text=True)
-    assert r.returncode == 0, f"rc {r.returncode} (killed by the timeout = the pipeline hung): {r.stderr[-400:]}"
-    assert r.stdout.split() == ["True"], r.stdout
+    got = {}
+    for bw in ("1", "0"):  # border terms on their own warp (default) / on the stager warps: the same fp32 expressions, so bit-equal
+        e = dict(os.environ, MLT_STEM5_STAGERS=stagers, MLT_STEM5_BW=bw)
+        out = str(tmp_path / f"l{bw}.npy")
+        r = subprocess.run(["timeout", "-s", "KILL", "120", sys.executable, "-c", code, out], env=e, capture_output=True, text=True)
+        assert r.returncode == 0, f"bw={bw} rc {r.returncode} (killed by the timeout = the pipeline hung): {r.stderr[-400:]}"
+        assert r.stdout.split() == ["True"], r.stdout
+        got[bw] = np.load(out)
+    assert np.array_equal(got["1"].view(np.uint32), got["0"].view(np.uint32))
