@@ -5,7 +5,8 @@
 // six of the sixteen bits are zero: the packed form is a little-endian bit stream, sample i in bits [10 i, 10 i + 10), i.e. 4
 // samples per 5 bytes, 40 KiB per CTU (-37.5 %).  On a multi-GPU host the aggregate H2D rate is what bounds the end-to-end
 // throughput of the batch API (profiles/r01: 29-35 GB/s per rank at 4-8 ranks), so fewer bytes per CTU is the only lever.
-// The producers (one encoder process per encode) pack their own blocks with mlt_pack10 -- ~14 us per CTU on one core, against
+// The producers (one encoder process per encode) pack their own blocks with mlt_pack10 -- AVX2 where the host has it, 5x the scalar loop (5.8 against
+// 29 us per CTU on one core of the build container; scalar on the GPU box's host: ~14 us), against
 // seconds of RDO per CTU -- and the device unpacks into the dense int16 batch the stem kernel reads (one HBM-bound pass:
 // 40 KiB in + 64 KiB out per CTU, ~1 % of a step).  Samples outside [0, 1023] cannot be packed: mlt_pack10 counts them and the
 // caller falls back to the int16 entry points (the reference's staging treats such values through the (uint16_t) cast,
@@ -50,15 +51,52 @@ cudaError_t launch_unpack10(const uint8_t *packed, int16_t *out, size_t samples,
 
 } // namespace mlt
 
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+#define MLT_PACK10_AVX2 1
+// 16 samples -> 20 bytes per step: pmaddwd pairs two 10-bit fields into 20 bits, a 64-bit shift / or pairs those into 40 bits, one
+// byte shuffle per 128-bit lane compacts 2 x 5 bytes; the two 16-byte stores overlap (10 valid bytes each), so the caller leaves
+// the last 24 samples to the scalar loop.  Returns the OR of every raw sample it saw (range check).
+__attribute__((target("avx2"))) static uint32_t pack10_avx2(const int16_t *src, uint64_t blocks, uint8_t *dst)
+{
+    const __m256i m10 = _mm256_set1_epi16(0x03FF), mul = _mm256_set1_epi32(0x04000001), m20 = _mm256_set1_epi64x(0xFFFFF);
+    const __m256i shuf = _mm256_setr_epi8(0, 1, 2, 3, 4, 8, 9, 10, 11, 12, -1, -1, -1, -1, -1, -1, 0, 1, 2, 3, 4, 8, 9, 10, 11, 12, -1, -1, -1, -1, -1, -1);
+    __m256i any = _mm256_setzero_si256();
+    for (uint64_t b = 0; b < blocks; b++, src += 16, dst += 20) {
+        const __m256i x = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src));
+        any = _mm256_or_si256(any, x);
+        const __m256i y = _mm256_madd_epi16(_mm256_and_si256(x, m10), mul);                     // 8 x (a | b << 10)
+        const __m256i z = _mm256_or_si256(_mm256_and_si256(y, m20), _mm256_slli_epi64(_mm256_srli_epi64(y, 32), 20)); // 4 x 40 bits
+        const __m256i c = _mm256_shuffle_epi8(z, shuf);
+        _mm_storeu_si128(reinterpret_cast<__m128i *>(dst), _mm256_castsi256_si128(c));
+        _mm_storeu_si128(reinterpret_cast<__m128i *>(dst + 10), _mm256_extracti128_si256(c, 1));
+    }
+    alignas(32) uint16_t lanes[16];
+    _mm256_store_si256(reinterpret_cast<__m256i *>(lanes), any);
+    uint32_t r = 0;
+    for (int i = 0; i < 16; i++) r |= lanes[i];
+    return r;
+}
+#endif
+
 extern "C" {
 
 // Host: pack `count` int16 samples (count % 4 == 0) into count * 10 / 8 bytes; returns the number of samples outside [0, 1023]
 // (their low 10 bits are stored; a non-zero return means this block must go through the int16 entry points instead).
 MLT_API uint64_t mlt_pack10(const int16_t *src, uint64_t count, uint8_t *dst)
 {
-    uint64_t bad = 0;
+    uint64_t bad = 0, i0 = 0;
     uint32_t any = 0;
-    for (uint64_t i = 0; i + 4 <= count; i += 4, dst += 5) {
+#ifdef MLT_PACK10_AVX2
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    if (avx2 && count >= 40) {
+        const uint64_t blocks = (count - 24) / 16; // the vector stores write 6 bytes past their 20: keep >= 24 samples for the scalar tail
+        any = pack10_avx2(src, blocks, dst);
+        i0 = blocks * 16;
+        dst += blocks * 20;
+    }
+#endif
+    for (uint64_t i = i0; i + 4 <= count; i += 4, dst += 5) {
         const uint32_t a = (uint16_t)src[i], b = (uint16_t)src[i + 1], c = (uint16_t)src[i + 2], d = (uint16_t)src[i + 3];
         any |= a | b | c | d;
         const uint64_t v = (uint64_t)(a & 0x3FFu) | ((uint64_t)(b & 0x3FFu) << 10) | ((uint64_t)(c & 0x3FFu) << 20) | ((uint64_t)(d & 0x3FFu) << 30);

@@ -317,6 +317,27 @@ def test_pack10_host_packer_roundtrip_and_range_check():
             capi.pack10(y[None])
 
 
+def test_pack10_vector_and_scalar_paths_agree_at_every_length():
+    """mlt_pack10 takes an AVX2 path for all but the last >= 24 samples (its 16-byte stores overlap) and a scalar loop for the rest:
+    every length around the switch-over must give the same bit stream, count out-of-range samples in both parts, and never write
+    past count * 10 / 8 bytes."""
+    from fastintercu_vvc_b200 import capi
+
+    L = capi.load_library()
+    rs = np.random.RandomState(11)
+    for count in [4, 8, 20, 36, 40, 44, 52, 56, 60, 64, 72, 100, 1000, 4096 + 12, 2 * 128 * 128]:
+        x = rs.randint(0, 1024, count).astype(np.int16)
+        nbytes = count * 10 // 8
+        out = np.full(nbytes + 32, 0xAB, np.uint8)
+        assert L.mlt_pack10(x.ctypes.data, count, out.ctypes.data) == 0
+        bits = np.unpackbits(out[:nbytes], bitorder="little").reshape(-1, 10)
+        assert np.array_equal((bits.astype(np.int32) << np.arange(10)).sum(1).astype(np.int16), x), count
+        assert (out[nbytes:] == 0xAB).all(), f"wrote past the end at count {count}"
+        y = x.copy()
+        y[0], y[count - 1] = 1024, -1  # one in the vector part (when there is one), one in the scalar tail
+        assert L.mlt_pack10(y.ctypes.data, count, out.ctypes.data) == 2
+
+
 def test_stem5_composite_is_the_two_reference_convs(sd):
     """conv1 (arch.py:278, no BN / activation) followed by layer0.0.conv1 (3x3 stride 2, folded BN) == ONE 5x5 stride-2 conv of the
     input minus the 1-D border terms at output row 0 / column 0 (pack_weights.stem5_composite), to float64 rounding; and the packed
