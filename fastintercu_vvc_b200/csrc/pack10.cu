@@ -5,8 +5,8 @@
 // six of the sixteen bits are zero: the packed form is a little-endian bit stream, sample i in bits [10 i, 10 i + 10), i.e. 4
 // samples per 5 bytes, 40 KiB per CTU (-37.5 %).  On a multi-GPU host the aggregate H2D rate is what bounds the end-to-end
 // throughput of the batch API (profiles/r01: 29-35 GB/s per rank at 4-8 ranks), so fewer bytes per CTU is the only lever.
-// The producers (one encoder process per encode) pack their own blocks with mlt_pack10 -- AVX2 where the host has it, 5x the scalar loop (5.8 against
-// 29 us per CTU on one core of the build container; scalar on the GPU box's host: ~14 us), against
+// The producers (one encoder process per encode) pack their own blocks with mlt_pack10 -- AVX2 where the host has it (5.4 us per CTU on one core of
+// the GPU box's host against ~14 us for the scalar loop; 5.8 against 29 us in the build container), against
 // seconds of RDO per CTU -- and the device unpacks into the dense int16 batch the stem kernel reads (one HBM-bound pass:
 // 40 KiB in + 64 KiB out per CTU, ~1 % of a step).  Samples outside [0, 1023] cannot be packed: mlt_pack10 counts them and the
 // caller falls back to the int16 entry points (the reference's staging treats such values through the (uint16_t) cast,
